@@ -1,0 +1,34 @@
+// fj_dist.h — NCCL plumbing for the one-process-per-GPU multi-GPU joins (internal).
+// NCCL is resolved with dlopen at fj_comm_init time so that the single-GPU library has no
+// link-time dependency on it (and binds to whichever libnccl.so.2 the process already loaded).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fj {
+
+typedef int fj_status_t;
+fj_status_t set_err(fj_status_t code, const char* fmt, ...);
+
+struct NcclApi;  // resolved function table
+
+struct DistState {
+  bool ready = false;
+  int rank = 0, world = 1;
+  void* comm = nullptr;  // ncclComm_t
+  const NcclApi* api = nullptr;
+};
+
+fj_status_t dist_unique_id(void* id128);
+fj_status_t dist_init(DistState& d, int rank, int world, const void* id128);
+void dist_destroy(DistState& d);
+// collectives on 64-bit words
+fj_status_t dist_broadcast_u64(DistState& d, void* buf, size_t count, int root, cudaStream_t st);
+fj_status_t dist_allreduce_sum_u64(DistState& d, const void* send, void* recv, size_t count, cudaStream_t st);
+fj_status_t dist_allgather_u64(DistState& d, const void* send, void* recv, size_t count_per_rank, cudaStream_t st);
+// all-to-all-v of bytes: rank r sends send_counts[r] bytes from send + send_offs[r], receives recv_counts[r] at recv + recv_offs[r]
+fj_status_t dist_alltoallv_bytes(DistState& d, const void* send, const uint64_t* send_offs, const uint64_t* send_counts,
+                                 void* recv, const uint64_t* recv_offs, const uint64_t* recv_counts, cudaStream_t st);
+
+}  // namespace fj

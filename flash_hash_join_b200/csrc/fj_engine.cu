@@ -1,0 +1,683 @@
+// fj_engine.cu — host side of libflashjoin_b200: the C ABI (include/flashjoin_b200.h), the device
+// arena, path selection and the optimistic-attempt driver.
+//
+// Replaces the reference's L3/L4 host logic in /root/reference/hash_join.cpp:
+//   join drivers _hash_join_{scalar,radix}_{count,materialize} (:315-567)  -> Engine::attempt_*
+//   adaptive_hash_join_* + RADIX_JOIN_THRESHOLD (:576-594)                 -> Engine::choose_path
+//   SimpleTimer (:45-55)                                                   -> CUDA events per phase
+//   initialize_memory_system (:596)                                        -> fj_init
+// The reference allocates every table/partition/result buffer inside each call (std::vector,
+// make_unique through mimalloc); here buffers live in a grow-only device arena reused across calls.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/flashjoin_b200.h"
+#include "fj_dist.h"
+#include "fj_kernels.h"
+
+namespace fj {
+
+thread_local std::string g_err;
+
+fj_status set_err(fj_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define FJ_CUDA(expr)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) {                                                                             \
+      cudaGetLastError();                                                                                 \
+      return set_err(e__ == cudaErrorMemoryAllocation ? FJ_ERR_OOM : FJ_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                     #expr, cudaGetErrorString(e__), __FILE__, __LINE__);                                 \
+    }                                                                                                     \
+  } while (0)
+#define FJ_TRY(expr)              \
+  do {                            \
+    fj_status s__ = (expr);       \
+    if (s__ != FJ_OK) return s__; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  fj_status ensure(size_t bytes) {
+    if (bytes <= cap) return FJ_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+    FJ_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return FJ_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct RadixPlan {
+  bool ok = false;
+  bool narrow = false;
+  int bits = 0, bits1 = 0, bits2 = 0;
+  uint32_t P = 0, F1 = 0, F2 = 0;
+  uint64_t cap1_b = 0, cap1_p = 0, cap2_b = 0, cap2_p = 0;
+  uint32_t smax = 0, tcap = 0, chunk = 16384, max_chunks = 1;
+};
+
+static uint64_t round4(uint64_t x) { return (x + 3) & ~uint64_t(3); }
+static uint64_t cap_build(uint64_t n, uint64_t parts) {
+  const double m = (double)n / (double)parts;
+  return round4((uint64_t)std::ceil(m + 6.0 * std::sqrt(m) + 32.0));
+}
+static uint64_t cap_probe(uint64_t n, uint64_t parts) {
+  const double m = (double)n / (double)parts;
+  return round4((uint64_t)std::ceil(m * 1.10 + 8.0 * std::sqrt(m) + 64.0));
+}
+
+struct Engine {
+  std::mutex mu;
+  bool inited = false;
+  DeviceInfo di;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[8] = {};
+  Ctl* h_ctl = nullptr;  // pinned
+  DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
+  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush;
+  uint64_t pairs_n = 0;
+  bool pairs_valid = false, pairs_idx = false;
+  std::map<std::string, int64_t> cfg;
+  DistState dist;
+
+  Engine() {
+    cfg["load_pct"] = 50;
+    cfg["bloom_bits_per_key"] = 16;
+    cfg["adaptive_table_l2_pct"] = 50;
+    cfg["radix_sub_rows"] = 0;  // 0 = derive from shared memory
+    cfg["radix_optimistic"] = 1;
+    cfg["smem_bloom"] = 1;
+    cfg["probe_ctas_per_sm"] = 2;
+    cfg["narrow"] = 1;
+    cfg["chunk_rows"] = 1 << 24;
+  }
+
+  fj_status init(int device);
+  void shutdown();
+  int choose_path(int algo, unsigned flags, uint64_t nb, bool narrow_guess, const RadixPlan& plan) const;
+  RadixPlan plan_radix(uint64_t nb, uint64_t np, bool narrow) const;
+  fj_status attempt_scalar(unsigned flags, bool narrow, bool exact, const unsigned long long* bk,
+                           const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                           uint64_t idx_base, fj_stats* s);
+  fj_status attempt_radix(unsigned flags, const RadixPlan& pl, const unsigned long long* bk,
+                          const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                          fj_stats* s);
+  fj_status join_device(int algo, unsigned flags, const unsigned long long* bk, const unsigned long long* bv,
+                        uint64_t nb, const unsigned long long* pk, uint64_t np, uint64_t idx_base, fj_stats* s);
+  fj_status join(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb, const uint64_t* pk,
+                 size_t np, uint64_t* out_matches, double* out_seconds, fj_stats* stats);
+  fj_status ensure_out(unsigned flags, uint64_t np);
+  float ms(int a, int b) {
+    float m = 0.f;
+    cudaEventElapsedTime(&m, ev[a], ev[b]);
+    return m;
+  }
+};
+
+static Engine& E() {
+  static Engine* e = new Engine();  // intentionally leaked: no destructor order issues at exit
+  return *e;
+}
+
+fj_status Engine::init(int device) {
+  if (inited) return FJ_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_err(FJ_ERR_NO_DEVICE, "no CUDA device available (%s); flashjoin_b200 has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0) {
+    const char* lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % n : 0;
+  }
+  if (device >= n) return set_err(FJ_ERR_BAD_ARG, "device %d out of range (%d devices)", device, n);
+  FJ_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FJ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_err(FJ_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", device,
+                   prop.name, prop.major, prop.minor);
+  di.device = device;
+  di.sms = prop.multiProcessorCount;
+  di.l2_bytes = prop.l2CacheSize;
+  di.smem_optin = prop.sharedMemPerBlockOptin;
+  di.cc_major = prop.major;
+  di.cc_minor = prop.minor;
+  FJ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto& x : ev) FJ_CUDA(cudaEventCreate(&x));
+  FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl)));
+  FJ_TRY(ctl.ensure(sizeof(Ctl)));
+  inited = true;
+  return FJ_OK;
+}
+
+void Engine::shutdown() {
+  if (!inited) return;
+  dist_destroy(dist);
+  cudaStreamSynchronize(st);
+  for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
+                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush})
+    b->release();
+  if (h_ctl) cudaFreeHost(h_ctl);
+  h_ctl = nullptr;
+  for (auto& x : ev) { if (x) cudaEventDestroy(x); x = nullptr; }
+  if (st) cudaStreamDestroy(st);
+  st = nullptr;
+  pairs_valid = false;
+  inited = false;
+}
+
+// ---- planning ----------------------------------------------------------------------------------
+RadixPlan Engine::plan_radix(uint64_t nb, uint64_t np, bool narrow) const {
+  RadixPlan pl;
+  pl.narrow = narrow;
+  // two join CTAs per SM: half of the SM's shared memory each, minus the per-CTA reservation
+  const size_t budget = std::min<size_t>(di.smem_optin, (228 * 1024 - 2 * 1024) / 2 - 2048);
+  const size_t tb = narrow ? 8 : 16;
+  uint64_t smax_limit = (budget / (tb + 8)) & ~uint64_t(3);
+  if (smax_limit > 65532) smax_limit = 65532;  // tuple index + 1 must fit 16 bits
+  const int64_t user = cfg.at("radix_sub_rows");
+  if (user > 0 && (uint64_t)user < smax_limit) smax_limit = std::max<uint64_t>(64, (uint64_t)user & ~uint64_t(3));
+  uint64_t P = 16;
+  while (cap_build(nb, P) > smax_limit && P < (1u << 18)) P <<= 1;
+  if (cap_build(nb, P) > smax_limit) return pl;  // too large for two passes: not applicable
+  pl.P = (uint32_t)P;
+  int B = 0;
+  while ((1ull << B) < P) ++B;
+  pl.bits = B;
+  if (B <= 8) { pl.bits1 = B; pl.bits2 = 0; }
+  else { pl.bits1 = (B + 1) / 2; pl.bits2 = B - pl.bits1; }
+  pl.F1 = 1u << pl.bits1;
+  pl.F2 = 1u << pl.bits2;
+  pl.cap2_b = cap_build(nb, P);
+  pl.cap2_p = cap_probe(np, P);
+  pl.cap1_b = pl.bits2 ? cap_build(nb, pl.F1) + 32 : 0;
+  pl.cap1_p = pl.bits2 ? cap_probe(np, pl.F1) : 0;
+  pl.smax = (uint32_t)pl.cap2_b;
+  pl.tcap = pl.smax * 2;
+  pl.chunk = 16384;
+  pl.max_chunks = (uint32_t)((pl.cap2_p + pl.chunk - 1) / pl.chunk);
+  if (pl.max_chunks == 0) pl.max_chunks = 1;
+  if ((uint64_t)pl.P * pl.max_chunks > 0x7fffffffull) return pl;
+  pl.ok = true;
+  return pl;
+}
+
+int Engine::choose_path(int algo, unsigned flags, uint64_t nb, bool narrow_guess, const RadixPlan& plan) const {
+  (void)flags;
+  if (algo == FJ_ALGO_SCALAR) return FJ_ALGO_SCALAR;
+  if (algo == FJ_ALGO_RADIX) return plan.ok ? FJ_ALGO_RADIX : FJ_ALGO_SCALAR;
+  // adaptive (replaces RADIX_JOIN_THRESHOLD = 1'000'000 rows, hash_join.cpp:576): keep the global
+  // table when it stays L2 resident, partition otherwise.
+  const double load = (double)cfg.at("load_pct") / 100.0;
+  const double table_bytes = (double)nb / load * (narrow_guess ? 8.0 : 16.0);
+  const double l2_budget = (double)di.l2_bytes * (double)cfg.at("adaptive_table_l2_pct") / 100.0;
+  if (table_bytes <= l2_budget || !plan.ok) return FJ_ALGO_SCALAR;
+  return FJ_ALGO_RADIX;
+}
+
+fj_status Engine::ensure_out(unsigned flags, uint64_t np) {
+  if (!(flags & FJ_FLAG_MATERIALIZE)) return FJ_OK;
+  const size_t bytes = std::max<uint64_t>(np, 1) * 8;
+  FJ_TRY(out_keys.ensure(bytes));
+  FJ_TRY(out_vals.ensure(bytes));
+  if (flags & FJ_FLAG_PROBE_IDX) FJ_TRY(out_idx.ensure(bytes));
+  return FJ_OK;
+}
+
+// ---- one attempt on the global-table path ------------------------------------------------------
+fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const unsigned long long* bk,
+                                 const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                                 uint64_t idx_base, fj_stats* s) {
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
+  const uint64_t spb = narrow ? 4 : 2;
+  const uint64_t load = (uint64_t)std::max<int64_t>(10, std::min<int64_t>(90, cfg["load_pct"]));
+  uint64_t nbuckets = (nb * 100 + load * spb - 1) / (load * spb);
+  if (nbuckets < 1) nbuckets = 1;
+  if (nbuckets > 0xfffffff0ull) return set_err(FJ_ERR_BAD_ARG, "build side too large for one table (%llu rows)", (unsigned long long)nb);
+  TableView t;
+  t.narrow = narrow;
+  t.nbuckets = (uint32_t)nbuckets;
+  const size_t table_bytes = (size_t)nbuckets * 32;
+  FJ_TRY(table.ensure(table_bytes));
+  t.slots = table.as<unsigned long long>();
+  bool bloom_smem = false;
+  size_t bloom_bytes = 0;
+  if (flags & FJ_FLAG_BLOOM) {
+    const uint64_t bits = (uint64_t)std::max<int64_t>(4, cfg["bloom_bits_per_key"]);
+    uint64_t words = round4(std::max<uint64_t>(8, (nb * bits + 31) / 32));
+    const uint64_t lim = probe_smem_bloom_limit_words(di);
+    if (cfg["smem_bloom"] && round4((nb * 8 + 31) / 32) <= lim) {  // >= 8 bits/key still fit shared memory
+      words = std::min(words, lim);
+      bloom_smem = true;
+    }
+    if (words > 0xfffffff0ull) words = 0xfffffff0ull;
+    bloom_bytes = words * 4;
+    FJ_TRY(bloom.ensure(bloom_bytes));
+    t.bloom = bloom.as<uint32_t>();
+    t.bloom_words = (uint32_t)words;
+  }
+  int launches = 0;
+  Ctl* d_ctl = ctl.as<Ctl>();
+  FJ_CUDA(cudaEventRecord(ev[0], st));
+  launch_init_ctl(d_ctl, st);
+  ++launches;
+  FJ_CUDA(cudaMemsetAsync(t.slots, 0xff, table_bytes, st));
+  if (t.bloom) FJ_CUDA(cudaMemsetAsync(t.bloom, 0, bloom_bytes, st));
+  FJ_CUDA(cudaEventRecord(ev[1], st));
+  launch_build(t, bk, bv, nb, exact ? 1 : 0, d_ctl, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[2], st));
+  ProbeOut po;
+  if (mat) {
+    po.keys = out_keys.as<unsigned long long>();
+    po.vals = out_vals.as<unsigned long long>();
+    po.idx = (flags & FJ_FLAG_PROBE_IDX) ? out_idx.as<unsigned long long>() : nullptr;
+    po.idx_base = idx_base;
+  }
+  launch_probe(t, pk, np, bv, mat ? &po : nullptr, bloom_smem, (int)cfg["probe_ctas_per_sm"], d_ctl, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  FJ_CUDA(cudaGetLastError());
+  s->clear_s += ms(0, 1) * 1e-3;
+  s->build_s += ms(1, 2) * 1e-3;
+  s->probe_s += ms(2, 3) * 1e-3;
+  s->device_s += ms(0, 3) * 1e-3;
+  s->kernel_launches += launches;
+  s->table_bytes = table_bytes + bloom_bytes;
+  s->path = FJ_ALGO_SCALAR;
+  s->narrow = narrow ? 1 : 0;
+  s->bloom_kind = t.bloom ? (bloom_smem ? 1 : 2) : 0;
+  s->dedup_exact = exact ? 1 : 0;
+  s->radix_bits1 = s->radix_bits2 = 0;
+  return FJ_OK;
+}
+
+// ---- one attempt on the radix path -------------------------------------------------------------
+fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsigned long long* bk,
+                                const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                                fj_stats* s) {
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
+  const bool two = pl.bits2 > 0;
+  const size_t tb = radix_elem_bytes(true, pl.narrow), tp = radix_elem_bytes(false, pl.narrow);
+  if (two) {
+    FJ_TRY(part_a_b.ensure((size_t)pl.F1 * pl.cap1_b * tb));
+    FJ_TRY(part_a_p.ensure((size_t)pl.F1 * pl.cap1_p * tp));
+  }
+  FJ_TRY(part_b_b.ensure((size_t)pl.P * pl.cap2_b * tb));
+  FJ_TRY(part_b_p.ensure((size_t)pl.P * pl.cap2_p * tp));
+  // cursor layout: [A build F1][A probe F1][B build P][B probe P]
+  const size_t ncur = 2 * (size_t)pl.F1 + 2 * (size_t)pl.P;
+  FJ_TRY(cursors.ensure(ncur * 4));
+  uint32_t* cur_a_b = cursors.as<uint32_t>();
+  uint32_t* cur_a_p = cur_a_b + pl.F1;
+  uint32_t* cur_b_b = cur_a_p + pl.F1;
+  uint32_t* cur_b_p = cur_b_b + pl.P;
+  Ctl* d_ctl = ctl.as<Ctl>();
+  int launches = 0;
+
+  FJ_CUDA(cudaEventRecord(ev[0], st));
+  launch_init_ctl(d_ctl, st);
+  ++launches;
+  FJ_CUDA(cudaMemsetAsync(cursors.p, 0, ncur * 4, st));
+  FJ_CUDA(cudaEventRecord(ev[1], st));
+
+  ScatterArgs a;
+  a.ctl = d_ctl;
+  if (!two) {
+    a.in_keys = bk; a.in_vals = bv; a.n = nb;
+    a.out = part_b_b.p; a.out_cursor = cur_b_b; a.out_cap = pl.cap2_b; a.shift = 32 - pl.bits; a.fan = pl.P;
+    launch_scatter(true, pl.narrow, 1, a, di, st, &launches);
+    a.in_keys = pk; a.in_vals = nullptr; a.n = np;
+    a.out = part_b_p.p; a.out_cursor = cur_b_p; a.out_cap = pl.cap2_p;
+    launch_scatter(false, pl.narrow, 1, a, di, st, &launches);
+  } else {
+    a.in_keys = bk; a.in_vals = bv; a.n = nb;
+    a.out = part_a_b.p; a.out_cursor = cur_a_b; a.out_cap = pl.cap1_b; a.shift = 32 - pl.bits1; a.fan = pl.F1;
+    launch_scatter(true, pl.narrow, 1, a, di, st, &launches);
+    a.in_keys = pk; a.in_vals = nullptr; a.n = np;
+    a.out = part_a_p.p; a.out_cursor = cur_a_p; a.out_cap = pl.cap1_p;
+    launch_scatter(false, pl.narrow, 1, a, di, st, &launches);
+    ScatterArgs b;
+    b.ctl = d_ctl;
+    b.shift = 32 - pl.bits; b.fan = pl.F2; b.in_nparts = pl.F1;
+    b.in_part = part_a_b.p; b.in_counts = cur_a_b; b.in_cap = pl.cap1_b; b.n_upper = nb;
+    b.out = part_b_b.p; b.out_cursor = cur_b_b; b.out_cap = pl.cap2_b;
+    launch_scatter(true, pl.narrow, 2, b, di, st, &launches);
+    b.in_part = part_a_p.p; b.in_counts = cur_a_p; b.in_cap = pl.cap1_p; b.n_upper = np;
+    b.out = part_b_p.p; b.out_cursor = cur_b_p; b.out_cap = pl.cap2_p;
+    launch_scatter(false, pl.narrow, 2, b, di, st, &launches);
+  }
+  FJ_CUDA(cudaEventRecord(ev[2], st));
+
+  JoinArgs j;
+  j.build = part_b_b.p; j.bcnt = cur_b_b; j.cap_b = pl.cap2_b;
+  j.probe = part_b_p.p; j.pcnt = cur_b_p; j.cap_p = pl.cap2_p;
+  j.smax = pl.smax; j.tcap = pl.tcap; j.chunk = pl.chunk; j.max_chunks = pl.max_chunks; j.nparts = pl.P;
+  j.ctl = d_ctl;
+  j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
+  j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
+  launch_join(pl.narrow, mat, j, st, &launches);
+  if (!pl.narrow) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  FJ_CUDA(cudaGetLastError());
+  s->clear_s += ms(0, 1) * 1e-3;
+  s->partition_s += ms(1, 2) * 1e-3;
+  s->probe_s += ms(2, 3) * 1e-3;
+  s->device_s += ms(0, 3) * 1e-3;
+  s->kernel_launches += launches;
+  s->table_bytes = (uint64_t)pl.P * (pl.cap2_b * tb + pl.cap2_p * tp) + (two ? (uint64_t)pl.F1 * (pl.cap1_b * tb + pl.cap1_p * tp) : 0);
+  s->path = FJ_ALGO_RADIX;
+  s->narrow = pl.narrow ? 1 : 0;
+  s->bloom_kind = 0;
+  s->dedup_exact = 0;
+  s->radix_bits1 = pl.bits1;
+  s->radix_bits2 = pl.bits2;
+  return FJ_OK;
+}
+
+// ---- the optimistic-attempt driver (inputs resident in HBM) ------------------------------------
+fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long* bk, const unsigned long long* bv,
+                              uint64_t nb, const unsigned long long* pk, uint64_t np, uint64_t idx_base, fj_stats* s) {
+  pairs_valid = false;
+  s->matches = 0;
+  if (nb == 0 || np == 0) {  // hash_join.cpp: empty build or probe -> (0, t) on every path
+    s->path = algo == FJ_ALGO_RADIX ? FJ_ALGO_RADIX : FJ_ALGO_SCALAR;
+    s->attempts = 1;
+    if (flags & FJ_FLAG_MATERIALIZE) { pairs_valid = true; pairs_n = 0; pairs_idx = (flags & FJ_FLAG_PROBE_IDX) != 0; }
+    return FJ_OK;
+  }
+  FJ_TRY(ensure_out(flags, np));
+  bool narrow = !(flags & FJ_FLAG_FORCE_WIDE) && cfg["narrow"] != 0;
+  bool exact = false;
+  RadixPlan plan = plan_radix(nb, np, narrow);
+  int path = choose_path(algo, flags, nb, narrow, plan);
+  if ((flags & FJ_FLAG_PROBE_IDX) && (flags & FJ_FLAG_MATERIALIZE)) path = FJ_ALGO_SCALAR;  // radix drops row ids (:254-292)
+  for (int attempt = 1; attempt <= 5; ++attempt) {
+    s->attempts = attempt;
+    if (path == FJ_ALGO_RADIX) {
+      if (plan.narrow != narrow) plan = plan_radix(nb, np, narrow);
+      if (!plan.ok) { path = FJ_ALGO_SCALAR; }
+    }
+    if (path == FJ_ALGO_RADIX) FJ_TRY(attempt_radix(flags, plan, bk, bv, nb, pk, np, s));
+    else FJ_TRY(attempt_scalar(flags, narrow, exact, bk, bv, nb, pk, np, idx_base, s));
+    const unsigned f = h_ctl->flags;
+    if ((f & CTL_NEED_WIDE) && narrow) { narrow = false; continue; }
+    if ((f & CTL_OVERFLOW) && path == FJ_ALGO_RADIX) { path = FJ_ALGO_SCALAR; continue; }
+    if ((f & CTL_DUP) && !exact) { exact = true; narrow = false; path = FJ_ALGO_SCALAR; continue; }
+    s->matches = h_ctl->match_count;
+    if (flags & FJ_FLAG_MATERIALIZE) {
+      if (h_ctl->out_cursor != h_ctl->match_count)
+        return set_err(FJ_ERR_STATE, "internal: pair cursor %llu != match count %llu", (unsigned long long)h_ctl->out_cursor,
+                       (unsigned long long)h_ctl->match_count);
+      pairs_valid = true;
+      pairs_n = h_ctl->match_count;
+      pairs_idx = (flags & FJ_FLAG_PROBE_IDX) != 0;
+    }
+    return FJ_OK;
+  }
+  return set_err(FJ_ERR_STATE, "internal: join did not converge after 5 attempts (flags %u)", h_ctl->flags);
+}
+
+fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb, const uint64_t* pk,
+                       size_t np, uint64_t* out_matches, double* out_seconds, fj_stats* stats) {
+  if (algo < FJ_ALGO_ADAPTIVE || algo > FJ_ALGO_RADIX) return set_err(FJ_ERR_BAD_ARG, "unknown algo %d", algo);
+  if (flags & ~(FJ_FLAG_BLOOM | FJ_FLAG_MATERIALIZE | FJ_FLAG_DEVICE_INPUTS | FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX))
+    return set_err(FJ_ERR_BAD_ARG, "unknown flag bits 0x%x", flags);
+  if ((nb && (!bk || !bv)) || (np && !pk)) return set_err(FJ_ERR_BAD_ARG, "NULL input pointer with non-zero length");
+  if (!out_matches) return set_err(FJ_ERR_BAD_ARG, "out_matches is NULL");
+  FJ_TRY(init(-1));
+  FJ_CUDA(cudaSetDevice(di.device));
+  const double t0 = now_s();
+  fj_stats s;
+  memset(&s, 0, sizeof(s));
+  s.n_gpus = 1;
+  const unsigned long long *d_bk, *d_bv, *d_pk;
+  if (flags & FJ_FLAG_DEVICE_INPUTS) {
+    d_bk = reinterpret_cast<const unsigned long long*>(bk);
+    d_bv = reinterpret_cast<const unsigned long long*>(bv);
+    d_pk = reinterpret_cast<const unsigned long long*>(pk);
+  } else {
+    FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
+    FJ_TRY(in_bv.ensure(std::max<size_t>(nb, 1) * 8));
+    FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
+    const double th = now_s();
+    if (nb) {
+      FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyHostToDevice, st));
+      FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    s.h2d_s = now_s() - th;
+    s.h2d_bytes = (uint64_t)(2 * nb + np) * 8;
+    d_bk = in_bk.as<unsigned long long>();
+    d_bv = in_bv.as<unsigned long long>();
+    d_pk = in_pk.as<unsigned long long>();
+  }
+  FJ_TRY(join_device(algo, flags, d_bk, d_bv, nb, d_pk, np, 0, &s));
+  s.wall_s = now_s() - t0;
+  s.algorithmic_bytes = (flags & FJ_FLAG_MATERIALIZE) ? 16ull * nb + 8ull * np + 16ull * s.matches : 8ull * (nb + np);
+  *out_matches = s.matches;
+  if (out_seconds) *out_seconds = s.device_s;
+  if (stats) *stats = s;
+  return FJ_OK;
+}
+
+}  // namespace fj
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace fj;
+
+extern "C" {
+
+FJ_API const char* fj_last_error(void) { return g_err.c_str(); }
+FJ_API const char* fj_version(void) { return "flashjoin_b200 0.1.0 (sm_100a)"; }
+
+FJ_API fj_status fj_init(int device) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  return E().init(device);
+}
+FJ_API fj_status fj_shutdown(void) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  E().shutdown();
+  return FJ_OK;
+}
+FJ_API fj_status fj_device_count(int* count) {
+  if (!count) return set_err(FJ_ERR_BAD_ARG, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *count = n;
+  return FJ_OK;
+}
+
+FJ_API fj_status fj_join_u64(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb,
+                             const uint64_t* pk, size_t np, uint64_t* out_matches, double* out_seconds,
+                             fj_stats* stats) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  return E().join(algo, flags, bk, bv, nb, pk, np, out_matches, out_seconds, stats);
+}
+
+FJ_API fj_status fj_pairs_count(uint64_t* n) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  if (!n) return set_err(FJ_ERR_BAD_ARG, "n is NULL");
+  if (!E().pairs_valid) return set_err(FJ_ERR_STATE, "no materialized pairs: the last join was not a materialize call");
+  *n = E().pairs_n;
+  return FJ_OK;
+}
+FJ_API fj_status fj_pairs_fetch(uint64_t* keys, uint64_t* values, uint64_t* probe_idx_or_null, size_t capacity) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  Engine& e = E();
+  if (!e.pairs_valid) return set_err(FJ_ERR_STATE, "no materialized pairs: the last join was not a materialize call");
+  if (capacity < e.pairs_n) return set_err(FJ_ERR_BAD_ARG, "capacity %zu < %llu pairs", capacity, (unsigned long long)e.pairs_n);
+  if (e.pairs_n == 0) return FJ_OK;
+  if (!keys || !values) return set_err(FJ_ERR_BAD_ARG, "NULL output pointer");
+  if (probe_idx_or_null && !e.pairs_idx) return set_err(FJ_ERR_STATE, "probe indices were not requested (FJ_FLAG_PROBE_IDX)");
+  FJ_CUDA(cudaSetDevice(e.di.device));
+  FJ_CUDA(cudaMemcpyAsync(keys, e.out_keys.p, e.pairs_n * 8, cudaMemcpyDeviceToHost, e.st));
+  FJ_CUDA(cudaMemcpyAsync(values, e.out_vals.p, e.pairs_n * 8, cudaMemcpyDeviceToHost, e.st));
+  if (probe_idx_or_null) FJ_CUDA(cudaMemcpyAsync(probe_idx_or_null, e.out_idx.p, e.pairs_n * 8, cudaMemcpyDeviceToHost, e.st));
+  FJ_CUDA(cudaStreamSynchronize(e.st));
+  return FJ_OK;
+}
+FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values, const uint64_t** probe_idx, uint64_t* n) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  Engine& e = E();
+  if (!e.pairs_valid) return set_err(FJ_ERR_STATE, "no materialized pairs: the last join was not a materialize call");
+  if (keys) *keys = e.out_keys.as<uint64_t>();
+  if (values) *values = e.out_vals.as<uint64_t>();
+  if (probe_idx) *probe_idx = e.pairs_idx ? e.out_idx.as<uint64_t>() : nullptr;
+  if (n) *n = e.pairs_n;
+  return FJ_OK;
+}
+
+FJ_API fj_status fj_config_set(const char* key, int64_t value) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  if (!key) return set_err(FJ_ERR_BAD_ARG, "key is NULL");
+  auto it = E().cfg.find(key);
+  if (it == E().cfg.end()) return set_err(FJ_ERR_BAD_ARG, "unknown config key '%s'", key);
+  it->second = value;
+  return FJ_OK;
+}
+FJ_API fj_status fj_config_get(const char* key, int64_t* value) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  if (!key || !value) return set_err(FJ_ERR_BAD_ARG, "NULL argument");
+  auto it = E().cfg.find(key);
+  if (it == E().cfg.end()) return set_err(FJ_ERR_BAD_ARG, "unknown config key '%s'", key);
+  *value = it->second;
+  return FJ_OK;
+}
+
+FJ_API fj_status fj_dev_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return set_err(FJ_ERR_BAD_ARG, "ptr is NULL");
+  { std::lock_guard<std::mutex> lk(E().mu); FJ_TRY(E().init(-1)); FJ_CUDA(cudaSetDevice(E().di.device)); }
+  FJ_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+  return FJ_OK;
+}
+FJ_API fj_status fj_dev_free(void* ptr) {
+  if (ptr) FJ_CUDA(cudaFree(ptr));
+  return FJ_OK;
+}
+FJ_API fj_status fj_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes) {
+  if (bytes) FJ_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+  return FJ_OK;
+}
+FJ_API fj_status fj_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
+  if (bytes) FJ_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return FJ_OK;
+}
+FJ_API fj_status fj_host_alloc_pinned(void** ptr, size_t bytes) {
+  if (!ptr) return set_err(FJ_ERR_BAD_ARG, "ptr is NULL");
+  { std::lock_guard<std::mutex> lk(E().mu); FJ_TRY(E().init(-1)); }
+  FJ_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+  return FJ_OK;
+}
+FJ_API fj_status fj_host_free_pinned(void* ptr) {
+  if (ptr) FJ_CUDA(cudaFreeHost(ptr));
+  return FJ_OK;
+}
+FJ_API fj_status fj_device_synchronize(void) {
+  FJ_CUDA(cudaDeviceSynchronize());
+  return FJ_OK;
+}
+
+FJ_API fj_status fj_generate_g2(int side, uint64_t n_total, uint64_t ny, int match_pct, uint64_t seed, uint64_t start,
+                                uint64_t count, uint64_t* keys_dev, uint64_t* values_dev_or_null) {
+  (void)n_total;
+  std::lock_guard<std::mutex> lk(E().mu);
+  if (side != 0 && side != 1) return set_err(FJ_ERR_BAD_ARG, "side must be 0 (build) or 1 (probe)");
+  if (!keys_dev && count) return set_err(FJ_ERR_BAD_ARG, "keys_dev is NULL");
+  if (ny == 0 || match_pct < 0 || match_pct > 100) return set_err(FJ_ERR_BAD_ARG, "bad generator parameters");
+  FJ_TRY(E().init(-1));
+  FJ_CUDA(cudaSetDevice(E().di.device));
+  // mirrors flash_hash_join_b200/datagen.py:_perm_index
+  const uint64_t c = ny * (uint64_t)match_pct / 100, U = 2 * ny - c;
+  uint64_t a = 0x9E3779B1ull | 1ull;
+  auto gcd = [](uint64_t x, uint64_t y) { while (y) { uint64_t t = x % y; x = y; y = t; } return x; };
+  while (gcd(a, U) != 1) a += 2;
+  const uint64_t b = (uint64_t)(((unsigned __int128)seed * 0x85EBCA6Bull + 12345ull) % U);
+  launch_generate_g2(side, ny, c, U, a % U, b, seed, start, count, reinterpret_cast<unsigned long long*>(keys_dev),
+                     reinterpret_cast<unsigned long long*>(values_dev_or_null), E().st);
+  FJ_CUDA(cudaStreamSynchronize(E().st));
+  FJ_CUDA(cudaGetLastError());
+  return FJ_OK;
+}
+
+FJ_API fj_status fj_flush_l2(void) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  Engine& e = E();
+  FJ_TRY(e.init(-1));
+  FJ_CUDA(cudaSetDevice(e.di.device));
+  const size_t bytes = std::max<size_t>((size_t)e.di.l2_bytes * 2, size_t(256) << 20);
+  FJ_TRY(e.flush.ensure(bytes));
+  FJ_CUDA(cudaMemsetAsync(e.flush.p, 0x5a, bytes, e.st));
+  FJ_CUDA(cudaStreamSynchronize(e.st));
+  return FJ_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------
+FJ_API fj_status fj_comm_unique_id(void* id128) {
+  if (!id128) return set_err(FJ_ERR_BAD_ARG, "id128 is NULL");
+  return dist_unique_id(id128);
+}
+FJ_API fj_status fj_comm_init(int rank, int world, const void* id128) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return set_err(FJ_ERR_BAD_ARG, "bad rank/world/id");
+  FJ_TRY(E().init(-1));
+  FJ_CUDA(cudaSetDevice(E().di.device));
+  return dist_init(E().dist, rank, world, id128);
+}
+FJ_API fj_status fj_comm_destroy(void) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  dist_destroy(E().dist);
+  return FJ_OK;
+}
+FJ_API fj_status fj_join_dist_u64(int mode, int algo, unsigned flags, int root, const uint64_t* bk, const uint64_t* bv,
+                                  size_t nb, const uint64_t* pk, size_t np, uint64_t* out_matches_global,
+                                  uint64_t* out_matches_local, double* out_seconds, fj_stats* stats) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  Engine& e = E();
+  if (!e.dist.ready) return set_err(FJ_ERR_STATE, "fj_comm_init has not been called");
+  if (mode != FJ_DIST_BROADCAST && mode != FJ_DIST_SHUFFLE) return set_err(FJ_ERR_BAD_ARG, "unknown dist mode %d", mode);
+  if (!out_matches_global) return set_err(FJ_ERR_BAD_ARG, "out_matches_global is NULL");
+  FJ_CUDA(cudaSetDevice(e.di.device));
+  (void)algo; (void)flags; (void)root; (void)bk; (void)bv; (void)nb; (void)pk; (void)np;
+  (void)out_matches_local; (void)out_seconds; (void)stats;
+  return set_err(FJ_ERR_STATE, "distributed join driver not linked in this build");
+}
+
+}  // extern "C"

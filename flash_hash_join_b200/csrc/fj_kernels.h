@@ -1,0 +1,95 @@
+// fj_kernels.h — host-callable launchers of the CUDA kernels (internal; not part of the C ABI).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fj_common.cuh"
+
+namespace fj {
+
+struct DeviceInfo {
+  int device = -1;
+  int sms = 0;
+  int l2_bytes = 0;
+  size_t smem_optin = 0;
+  int cc_major = 0, cc_minor = 0;
+};
+
+// ---------------------------------------------------------------- global ("scalar") table path
+struct TableView {
+  unsigned long long* slots = nullptr;  // narrow: nbuckets*4 packed words; wide: nbuckets*2 {key,value}
+  uint32_t nbuckets = 0;                // 32-byte buckets
+  uint32_t* bloom = nullptr;            // nullptr = no Bloom filter
+  uint32_t bloom_words = 0;             // multiple of 4 (16-byte granularity for the bulk copy)
+  bool narrow = false;
+};
+
+struct ProbeOut {
+  unsigned long long* keys = nullptr;  // materialize: (probe key, build value[, probe row idx])
+  unsigned long long* vals = nullptr;
+  unsigned long long* idx = nullptr;
+  unsigned long long idx_base = 0;     // added to the local probe row index (distributed slices)
+};
+
+void launch_init_ctl(Ctl* ctl, cudaStream_t st);
+// build kernels: mode 0 = fast (CAS on key, plain value store, raises CTL_DUP on duplicates),
+//                mode 1 = exact keep-first (wide only: value word holds min row index, then fix-up)
+void launch_build(const TableView& t, const unsigned long long* bk, const unsigned long long* bv, uint64_t nb,
+                  int mode, Ctl* ctl, const DeviceInfo& di, cudaStream_t st, int* launches);
+// probe: count only (out == nullptr) or materialize.  bloom_in_smem selects the shared-memory
+// resident filter (requires bloom_words*4 + slack <= smem_optin).
+void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np, const unsigned long long* bv,
+                  const ProbeOut* out, bool bloom_in_smem, int ctas_per_sm, Ctl* ctl, const DeviceInfo& di,
+                  cudaStream_t st, int* launches);
+size_t probe_smem_bloom_limit_words(const DeviceInfo& di);
+
+// ---------------------------------------------------------------- radix-partitioned path
+struct ScatterArgs {
+  // stage 1 input: raw 64-bit columns
+  const unsigned long long* in_keys = nullptr;
+  const unsigned long long* in_vals = nullptr;
+  uint64_t n = 0;
+  // stage 2 input: the fixed-capacity partitions written by stage 1
+  const void* in_part = nullptr;
+  const uint32_t* in_counts = nullptr;
+  uint32_t in_nparts = 0;
+  uint64_t in_cap = 0;
+  uint64_t n_upper = 0;  // upper bound on the rows stage 2 will see (for grid sizing)
+  // output partitions: partition p occupies [p*out_cap, p*out_cap + cursor[p])
+  void* out = nullptr;
+  uint32_t* out_cursor = nullptr;
+  uint64_t out_cap = 0;
+  int shift = 0;      // digit = (hash32(key) >> shift) & (fan - 1)
+  uint32_t fan = 1;   // power of two, <= 512
+  Ctl* ctl = nullptr;
+};
+struct JoinArgs {
+  const void* build = nullptr;
+  const uint32_t* bcnt = nullptr;
+  uint64_t cap_b = 0;
+  const void* probe = nullptr;
+  const uint32_t* pcnt = nullptr;
+  uint64_t cap_p = 0;
+  uint32_t smax = 0;        // build tuples that fit the shared-memory staging area (multiple of 4)
+  uint32_t tcap = 0;        // slots of the shared-memory index table
+  uint32_t chunk = 0;       // probe rows per CTA (multiple of 4)
+  uint32_t max_chunks = 1;  // ceil(cap_p / chunk)
+  uint32_t nparts = 0;
+  Ctl* ctl = nullptr;
+  unsigned long long* out_keys = nullptr;
+  unsigned long long* out_vals = nullptr;
+};
+size_t radix_elem_bytes(bool build, bool narrow);
+void launch_scatter(bool build, bool narrow, int stage, const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st,
+                    int* launches);
+void launch_join(bool narrow, bool mat, const JoinArgs& a, cudaStream_t st, int* launches);
+void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
+                          unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
+
+// ---------------------------------------------------------------- synthetic data + utilities
+void launch_generate_g2(int side, uint64_t ny, uint64_t c, uint64_t U, uint64_t a_mod_u, uint64_t b, uint64_t seed,
+                        uint64_t start, uint64_t count, unsigned long long* keys, unsigned long long* vals,
+                        cudaStream_t st);
+
+}  // namespace fj

@@ -1,0 +1,441 @@
+// fj_scalar.cu — the non-partitioned ("scalar" in the reference's vocabulary) join path:
+// one open-addressing, linear-probing table in HBM/L2, built with 64-bit atomicCAS, probed by a
+// persistent streaming kernel.
+//
+// Replaces, from /root/reference/hash_join.cpp:
+//   FlashHashTable ctor/clear (:98-110)          -> cudaMemsetAsync(0xFF) of a 32 B-bucket table
+//   insert_concurrent / build_concurrent (:130-151, :193-203) -> k_build<NARROW, MODE>
+//   probe_vectorized (:153-182) + _hash_join_scalar_count (:536-567)        -> k_probe<.., MAT=false>
+//   probe_vectorized + _hash_join_scalar_materialize (:383-496)             -> k_probe<.., MAT=true>
+//   bloom set/test (:122/:142, :185-189)         -> fused into k_build / k_probe
+//
+// Table layout (HBM, 32-byte sector == one bucket; a probe reads exactly one sector per step):
+//   narrow: 4 packed words per bucket, word = key32 << 32 | value32, EMPTY = ~0
+//   wide  : 2 slots per bucket, slot = {key64, value64}, EMPTY key = ~0 (that key value itself is
+//           kept out of band in Ctl::sentinel_row)
+#include <cstdio>
+#include <type_traits>
+
+#include "fj_kernels.h"
+
+namespace fj {
+
+// =================================================================================== ctl init
+__global__ void k_init_ctl(Ctl* ctl) {
+  ctl->match_count = 0;
+  ctl->out_cursor = 0;
+  ctl->sentinel_row = EMPTY64;
+  ctl->sentinel_probes = 0;
+  ctl->flags = 0;
+  ctl->pad = 0;
+}
+void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ctl); }
+
+// =================================================================================== build
+// MODE 0: fast path.  MODE 1: exact keep-first (wide only) — the value word accumulates the
+// minimum build row index with atomicMin; k_fixup_values then replaces it by bv[row].
+template <bool NARROW, int MODE, bool BLOOM>
+__global__ void __launch_bounds__(256) k_build(unsigned long long* __restrict__ slots, uint32_t nbuckets,
+                                               uint32_t* __restrict__ bloom, uint32_t bloom_words,
+                                               const unsigned long long* __restrict__ bk,
+                                               const unsigned long long* __restrict__ bv, uint64_t nb,
+                                               Ctl* __restrict__ ctl) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nb; i += stride) {
+    const unsigned long long k = bk[i];
+    const unsigned long long v = bv[i];
+    if (NARROW) {
+      const unsigned long long packed = (k << 32) | (v & 0xffffffffull);
+      if (((k | v) >> 32) != 0 || packed == EMPTY64) {
+        atomicOr(&ctl->flags, CTL_NEED_WIDE);  // attempt is abandoned by the host
+        return;
+      }
+      const uint32_t h = hash32(k);
+      uint32_t b = reduce32(h, nbuckets);
+      bool done = false;
+      for (uint32_t it = 0; it < nbuckets && !done; ++it) {
+        unsigned long long* bp = slots + (size_t)b * 4;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (done) break;
+          unsigned long long cur = bp[s];
+          if (cur == EMPTY64) {
+            cur = atomicCAS(bp + s, EMPTY64, packed);
+            if (cur == EMPTY64) { done = true; break; }
+          }
+          if ((uint32_t)(cur >> 32) == (uint32_t)k) {  // same key already present
+            atomicOr(&ctl->flags, CTL_DUP);
+            done = true;
+          }
+        }
+        if (++b == nbuckets) b = 0;
+      }
+      if (BLOOM) atomicOr(bloom + bloom_word(h, bloom_words), bloom_mask(h));
+    } else {
+      if (k == EMPTY64) {  // the one key that collides with the empty marker: keep out of band
+        atomicMin(&ctl->sentinel_row, (unsigned long long)i);
+        continue;
+      }
+      const uint32_t h = hash32(k);
+      uint32_t b = reduce32(h, nbuckets);
+      bool done = false;
+      for (uint32_t it = 0; it < nbuckets && !done; ++it) {
+        unsigned long long* bp = slots + (size_t)b * 4;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (done) break;
+          unsigned long long cur = bp[2 * s];
+          if (cur == EMPTY64) {
+            cur = atomicCAS(bp + 2 * s, EMPTY64, k);
+            if (cur == EMPTY64) {
+              if (MODE == 0) bp[2 * s + 1] = v;
+              else atomicMin(bp + 2 * s + 1, (unsigned long long)i);
+              done = true;
+              break;
+            }
+          }
+          if (cur == k) {
+            if (MODE == 0) atomicOr(&ctl->flags, CTL_DUP);
+            else atomicMin(bp + 2 * s + 1, (unsigned long long)i);
+            done = true;
+          }
+        }
+        if (++b == nbuckets) b = 0;
+      }
+      if (BLOOM) atomicOr(bloom + bloom_word(h, bloom_words), bloom_mask(h));
+    }
+  }
+}
+
+// exact path: value word holds a build row index -> replace by the row's value
+__global__ void __launch_bounds__(256) k_fixup_values(unsigned long long* __restrict__ slots, uint64_t nslots,
+                                                      const unsigned long long* __restrict__ bv) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < nslots; s += stride) {
+    if (slots[2 * s] != EMPTY64) slots[2 * s + 1] = bv[slots[2 * s + 1]];
+  }
+}
+
+void launch_build(const TableView& t, const unsigned long long* bk, const unsigned long long* bv, uint64_t nb,
+                  int mode, Ctl* ctl, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  if (nb == 0) return;
+  const int threads = 256;
+  uint64_t want = (nb + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)di.sms * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  const bool bloom = t.bloom != nullptr;
+#define FJ_BUILD(N, M, B) \
+  k_build<N, M, B><<<grid, threads, 0, st>>>(t.slots, t.nbuckets, t.bloom, t.bloom_words, bk, bv, nb, ctl)
+  if (t.narrow) {
+    if (bloom) FJ_BUILD(true, 0, true); else FJ_BUILD(true, 0, false);
+  } else if (mode == 0) {
+    if (bloom) FJ_BUILD(false, 0, true); else FJ_BUILD(false, 0, false);
+  } else {
+    if (bloom) FJ_BUILD(false, 1, true); else FJ_BUILD(false, 1, false);
+  }
+#undef FJ_BUILD
+  ++*launches;
+  if (!t.narrow && mode == 1) {
+    const uint64_t nslots = (uint64_t)t.nbuckets * 2;
+    uint64_t w2 = (nslots + threads - 1) / threads;
+    const int g2 = (int)(w2 < cap ? w2 : cap);
+    k_fixup_values<<<g2, threads, 0, st>>>(t.slots, nslots, bv);
+    ++*launches;
+  }
+}
+
+// =================================================================================== probe
+// One lookup.  Returns true and the build value on the first (only) slot holding `key`.
+template <bool NARROW>
+__device__ __forceinline__ bool probe_resolve(unsigned long long key, uint32_t b, unsigned long long s0,
+                                              unsigned long long s1, unsigned long long s2, unsigned long long s3,
+                                              const unsigned long long* __restrict__ slots, uint32_t nbuckets,
+                                              unsigned long long& value) {
+  // s0..s3 = contents of the home bucket (already loaded); continue linearly only when the
+  // bucket is full and holds no match (rare at load factor <= 0.5).
+  for (uint32_t it = 0; it < nbuckets; ++it) {
+    if (NARROW) {
+      const uint32_t k32 = (uint32_t)key;
+      if ((uint32_t)(s0 >> 32) == k32 && s0 != EMPTY64) { value = s0 & 0xffffffffull; return true; }
+      if ((uint32_t)(s1 >> 32) == k32 && s1 != EMPTY64) { value = s1 & 0xffffffffull; return true; }
+      if ((uint32_t)(s2 >> 32) == k32 && s2 != EMPTY64) { value = s2 & 0xffffffffull; return true; }
+      if ((uint32_t)(s3 >> 32) == k32 && s3 != EMPTY64) { value = s3 & 0xffffffffull; return true; }
+      if (s0 == EMPTY64 || s1 == EMPTY64 || s2 == EMPTY64 || s3 == EMPTY64) return false;
+    } else {
+      if (s0 == key) { value = s1; return true; }
+      if (s2 == key) { value = s3; return true; }
+      if (s0 == EMPTY64 || s2 == EMPTY64) return false;
+    }
+    if (++b == nbuckets) b = 0;
+    ld_sector(slots + (size_t)b * 4, s0, s1, s2, s3);
+  }
+  return false;
+}
+
+constexpr int PROBE_KPT = 8;  // probe keys per thread per tile (4 x 128-bit loads)
+
+// occupancy targets: count kernels 2 x 512 threads (<= 64 regs); the shared-memory-Bloom count kernel
+// 1 x 1024; materialize kernels keep 8 (key, value) pairs live per thread and get more registers.
+template <int BLOOM, bool MAT, int THREADS>
+constexpr int probe_min_blocks() { return BLOOM == 1 ? 1 : (MAT ? 3 : 2); }
+
+template <bool NARROW, int BLOOM /*0 none, 1 smem, 2 global*/, bool MAT, bool IDX, int THREADS>
+__global__ void __launch_bounds__(THREADS, probe_min_blocks<BLOOM, MAT, THREADS>())
+    k_probe(const unsigned long long* __restrict__ pk, uint64_t np, const unsigned long long* __restrict__ slots,
+            uint32_t nbuckets, const uint32_t* __restrict__ bloom, uint32_t bloom_words,
+            const unsigned long long* __restrict__ bv, Ctl* __restrict__ ctl, unsigned long long* __restrict__ out_keys,
+            unsigned long long* __restrict__ out_vals, unsigned long long* __restrict__ out_idx,
+            unsigned long long idx_base, int vec_ok) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr uint32_t TILE = THREADS * PROBE_KPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t s_wcnt[MAT ? WARPS * PROBE_KPT : 1];
+  __shared__ unsigned long long s_base;
+  __shared__ __align__(8) uint64_t s_bar;
+  const uint32_t* sbloom = reinterpret_cast<const uint32_t*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (BLOOM == 1) {
+    // stage the whole filter in shared memory with TMA bulk copies (cp.async.bulk + mbarrier)
+    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = bloom_words * 4u;
+      mbar_expect_tx(&s_bar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(bloom) + off, n, &s_bar);
+      }
+    }
+    mbar_wait(&s_bar, 0);
+  }
+
+  // out-of-band key (wide tables only): value of the first build row whose key == EMPTY64
+  bool sent_present = false;
+  unsigned long long sent_value = 0;
+  if (!NARROW) {
+    const unsigned long long sr = ctl->sentinel_row;
+    if (sr != EMPTY64) { sent_present = true; sent_value = bv[sr]; }
+  }
+
+  unsigned long long local_count = 0;
+  const uint64_t ntiles = (np + TILE - 1) / TILE;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t tbase = tile * TILE;
+    unsigned long long key[PROBE_KPT];
+    bool valid[PROBE_KPT];
+    const bool vec = vec_ok && tbase + TILE <= np;
+    if (vec) {
+      // 128-bit coalesced loads: each warp instruction reads 512 contiguous bytes
+#pragma unroll
+      for (int r = 0; r < PROBE_KPT / 2; ++r) {
+        const uint64_t e = tbase + 2ull * ((uint64_t)r * THREADS + tid);
+        ld_stream2(pk + e, key[2 * r], key[2 * r + 1]);
+        valid[2 * r] = valid[2 * r + 1] = true;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const uint64_t e = tbase + (uint64_t)q * THREADS + tid;
+        valid[q] = e < np;
+        key[q] = valid[q] ? ld_stream1(pk + e) : 0ull;
+      }
+    }
+
+    using val_t = typename std::conditional<NARROW, uint32_t, unsigned long long>::type;
+    val_t val[PROBE_KPT];
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // batch of 4 lookups: issue all home-bucket sector loads before resolving any (MLP)
+      uint32_t b[4];
+      bool need[4];
+      unsigned long long s[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = half * 4 + j;
+        const unsigned long long k = key[q];
+        const uint32_t h = hash32(k);
+        b[j] = reduce32(h, nbuckets);
+        bool go = valid[q];
+        if (NARROW) go = go && ((k >> 32) == 0);  // a key >= 2^32 cannot be in a packed table
+        else go = go && (k != EMPTY64);
+        if (BLOOM != 0 && go) {
+          const uint32_t m = bloom_mask(h);
+          const uint32_t wi = bloom_word(h, bloom_words);
+          const uint32_t w = (BLOOM == 1) ? sbloom[wi] : __ldg(bloom + wi);
+          go = (w & m) == m;
+        }
+        need[j] = go;
+        if (go) ld_sector(slots + (size_t)b[j] * 4, s[j][0], s[j][1], s[j][2], s[j][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = half * 4 + j;
+        bool hit = false;
+        unsigned long long v = 0;
+        if (need[j]) hit = probe_resolve<NARROW>(key[q], b[j], s[j][0], s[j][1], s[j][2], s[j][3], slots, nbuckets, v);
+        if (!NARROW && valid[q] && key[q] == EMPTY64 && sent_present) { hit = true; v = sent_value; }
+        val[q] = (val_t)v;
+        if (hit) hitmask |= 1u << q;
+      }
+    }
+
+    if (!MAT) {
+      local_count += __popc(hitmask);
+    } else {
+      // compaction: per (warp, q) ballot -> block scan of WARPS*KPT counts -> one cursor bump per tile
+      uint32_t rank[PROBE_KPT];
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> q) & 1u);
+        rank[q] = __popc(bal & lanemask_lt());
+        if (lane == 0) s_wcnt[warp * PROBE_KPT + q] = __popc(bal);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        constexpr int PER = (WARPS * PROBE_KPT + 31) / 32;
+        uint32_t c[PER];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int e = lane * PER + u;
+          c[u] = e < WARPS * PROBE_KPT ? s_wcnt[e] : 0u;
+          sum += c[u];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int e = lane * PER + u;
+          if (e < WARPS * PROBE_KPT) s_wcnt[e] = run;
+          run += c[u];
+        }
+        if (lane == 31) {
+          s_base = incl ? atomicAdd(&ctl->out_cursor, (unsigned long long)incl) : 0ull;
+          local_count += incl;  // counted once per tile by this lane
+        }
+      }
+      __syncthreads();
+      const unsigned long long base = s_base;
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        if ((hitmask >> q) & 1u) {
+          const unsigned long long pos = base + s_wcnt[warp * PROBE_KPT + q] + rank[q];
+          st_stream(out_keys + pos, key[q]);
+          st_stream(out_vals + pos, (unsigned long long)val[q]);
+          if (IDX) {
+            const uint64_t row = vec ? tbase + 2ull * ((uint64_t)(q >> 1) * THREADS + tid) + (q & 1)
+                                     : tbase + (uint64_t)q * THREADS + tid;
+            st_stream(out_idx + pos, idx_base + row);
+          }
+        }
+      }
+      __syncthreads();  // s_wcnt / s_base are reused by the next tile
+    }
+  }
+
+  // one atomic per warp for the match count
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
+  if (lane == 0 && local_count) atomicAdd(&ctl->match_count, local_count);
+}
+
+size_t probe_smem_bloom_limit_words(const DeviceInfo& di) {
+  // leave 4 KB for the kernel's static shared memory
+  const size_t bytes = di.smem_optin > 8192 ? di.smem_optin - 4096 : 0;
+  return (bytes / 16) * 4;
+}
+
+template <bool NARROW, int BLOOM, bool MAT, bool IDX, int THREADS>
+static void launch_probe_inst(const TableView& t, const unsigned long long* pk, uint64_t np,
+                              const unsigned long long* bv, const ProbeOut* out, int ctas_per_sm, Ctl* ctl,
+                              const DeviceInfo& di, cudaStream_t st) {
+  auto kern = k_probe<NARROW, BLOOM, MAT, IDX, THREADS>;
+  size_t smem = 0;
+  if (BLOOM == 1) {
+    smem = (size_t)t.bloom_words * 4;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ctas_per_sm = 1;
+  }
+  const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
+  const uint64_t ntiles = (np + tile - 1) / tile;
+  uint64_t grid = (uint64_t)di.sms * ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(pk, np, t.slots, t.nbuckets, t.bloom, t.bloom_words, bv, ctl,
+                                             out ? out->keys : nullptr, out ? out->vals : nullptr,
+                                             out ? out->idx : nullptr, out ? out->idx_base : 0ull, vec_ok);
+}
+
+void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np, const unsigned long long* bv,
+                  const ProbeOut* out, bool bloom_in_smem, int ctas_per_sm, Ctl* ctl, const DeviceInfo& di,
+                  cudaStream_t st, int* launches) {
+  if (np == 0) return;
+  const int bloom = t.bloom == nullptr ? 0 : (bloom_in_smem ? 1 : 2);
+  const bool mat = out != nullptr;
+  const bool idx = mat && out->idx != nullptr;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+#define FJ_PROBE(N, B, M, I, T) launch_probe_inst<N, B, M, I, T>(t, pk, np, bv, out, ctas_per_sm, ctl, di, st)
+#define FJ_PROBE_B(N, M, I)                               \
+  do {                                                    \
+    if (bloom == 0) FJ_PROBE(N, 0, M, I, (M ? 256 : 512));            \
+    else if (bloom == 1) FJ_PROBE(N, 1, M, I, (M ? 512 : 1024));      \
+    else FJ_PROBE(N, 2, M, I, (M ? 256 : 512));                       \
+  } while (0)
+  if (t.narrow) {
+    if (!mat) FJ_PROBE_B(true, false, false);
+    else if (!idx) FJ_PROBE_B(true, true, false);
+    else FJ_PROBE_B(true, true, true);
+  } else {
+    if (!mat) FJ_PROBE_B(false, false, false);
+    else if (!idx) FJ_PROBE_B(false, true, false);
+    else FJ_PROBE_B(false, true, true);
+  }
+#undef FJ_PROBE_B
+#undef FJ_PROBE
+  ++*launches;
+}
+
+// =================================================================================== data generator G2
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull;
+  x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
+  x ^= x >> 33;
+  return x;
+}
+// mirrors flash_hash_join_b200/datagen.py:g2_slice bit for bit
+__global__ void __launch_bounds__(256) k_generate_g2(int side, uint64_t ny, uint64_t c, uint64_t U, uint64_t a, uint64_t b,
+                                                     uint64_t seed, uint64_t start, uint64_t count,
+                                                     unsigned long long* __restrict__ keys,
+                                                     unsigned long long* __restrict__ vals) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count; j += stride) {
+    const uint64_t idx = start + j;
+    uint64_t id;
+    if (side == 0) {
+      id = idx < c ? idx : idx - c + ny;
+      if (vals) vals[j] = mix64(idx + seed * 0x9E3779B97F4A7C15ull) % 100ull;
+    } else {
+      const unsigned long long r = mix64((idx + 1ull) * 0x9E3779B97F4A7C15ull + seed);
+      id = r % ny;
+    }
+    keys[j] = ((id * a) % U + b) % U + 1ull;
+  }
+}
+void launch_generate_g2(int side, uint64_t ny, uint64_t c, uint64_t U, uint64_t a_mod_u, uint64_t b, uint64_t seed,
+                        uint64_t start, uint64_t count, unsigned long long* keys, unsigned long long* vals,
+                        cudaStream_t st) {
+  if (count == 0) return;
+  uint64_t want = (count + 255) / 256;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  k_generate_g2<<<grid, 256, 0, st>>>(side, ny, c, U, a_mod_u, b, seed, start, count, keys, vals);
+}
+
+}  // namespace fj

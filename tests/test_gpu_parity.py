@@ -1,0 +1,364 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA engine, called through the reference-
+facing pybind11 module and through the C ABI, against the oracle on the same seeded inputs.
+
+Bar: bit-exact — identical match counts and identical sorted multiset of (probe key, build value)
+pairs.  All arithmetic on the path is integer; there is no tolerance anywhere in this file.
+Nothing here reads /root/reference (absent on the GPU box): the oracle is oracle/join_oracle.c,
+the numpy restatement, and the committed golden vectors produced by the reference binary."""
+import os
+
+import numpy as np
+import pytest
+
+from flash_hash_join_b200.datagen import g1, g2, g2_slice
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ALL = sorted(O.ENTRY_POINTS)  # (algo, bloom, materialize)
+
+
+@pytest.fixture(scope="module")
+def fj():
+    from flash_hash_join_b200 import flash_join
+
+    flash_join.initialize()
+    return flash_join
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from flash_hash_join_b200 import capi as c
+
+    return c
+
+
+def run_entry(fj, algo, bloom, mat, bk, bv, pk):
+    name = O.entry_point_name(algo, bloom, mat)
+    n, sec = getattr(fj, name)(bk, bv, pk)
+    assert isinstance(n, int) and isinstance(sec, float) and sec >= 0.0
+    pairs = fj.last_pairs() if mat else None
+    return n, pairs
+
+
+def check_all_entry_points(fj, bk, bv, pk, expect=None, algos=("adaptive", "scalar", "radix")):
+    if expect is None:
+        expect = O.np_join(bk, bv, pk)
+    n0, k0, v0 = expect
+    sp0 = O.sorted_pairs(k0, v0)
+    for algo, bloom, mat in ALL:
+        if algo not in algos:
+            continue
+        n, pairs = run_entry(fj, algo, bloom, mat, bk, bv, pk)
+        assert n == n0, (algo, bloom, mat, n, n0, fj.last_stats())
+        if mat:
+            k, v = pairs
+            assert k.size == n0 and v.size == n0
+            assert np.array_equal(O.sorted_pairs(k, v), sp0), (algo, bloom, mat, fj.last_stats())
+
+
+# ------------------------------------------------------------------------------------------------
+def test_smoke_first_kernel(fj):
+    bk = np.array([5, 7, 9, 11], dtype=np.uint64)
+    bv = np.array([50, 70, 90, 110], dtype=np.uint64)
+    pk = np.array([7, 7, 1, 11, 12, 5], dtype=np.uint64)
+    n, sec = fj.hash_join_count(bk, bv, pk)
+    assert n == 4
+    st = fj.last_stats()
+    assert st["kernel_launches"] >= 3 and st["path"] == "scalar"
+    n, sec = fj.hash_join(build_keys=bk, build_values=bv, probe_keys=pk)
+    k, v = fj.last_pairs()
+    assert n == 4 and np.array_equal(O.sorted_pairs(k, v), O.sorted_pairs([5, 7, 7, 11], [50, 70, 70, 110]))
+
+
+@pytest.mark.parametrize("nb,np_", [(0, 0), (0, 100), (100, 0), (1, 1), (1, 5000), (10, 2047), (1000, 2048), (1000, 2049),
+                                    (4095, 4097), (10**4, 10**5), (65536, 300001)])
+def test_shape_matrix_unique_build(fj, nb, np_):
+    rng = np.random.default_rng(nb * 31 + np_)
+    bk = (rng.permutation(max(3 * nb, 8))[:nb] + 1).astype(np.uint64)
+    bv = rng.integers(0, 1000, nb).astype(np.uint64)
+    pk = rng.integers(0, max(3 * nb, 8) + 2, np_).astype(np.uint64)
+    check_all_entry_points(fj, bk, bv, pk)
+
+
+@pytest.mark.parametrize("pct", [0, 10, 90, 100])
+def test_match_rates(fj, pct):
+    bk, bv, pk = g1(200_000, 20_000, pct)
+    n0 = O.np_join(bk, bv, pk)
+    assert abs(n0[0] / 200_000 - pct / 100) < 0.02
+    check_all_entry_points(fj, bk, bv, pk, expect=n0)
+
+
+def test_c_oracle_agrees_on_gpu_case(fj):
+    """Same seeded input through the C restatement of the reference (not only numpy)."""
+    bk, bv, pk = g1(300_000, 30_000, 90)
+    for algo, bloom, mat in ALL:
+        n0, k0, v0 = O.join(algo, bloom, mat, bk, bv, pk)
+        n, pairs = run_entry(fj, algo, bloom, mat, bk, bv, pk)
+        assert n == n0
+        if mat:
+            assert np.array_equal(O.sorted_pairs(*pairs), O.sorted_pairs(k0, v0))
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_golden_vectors(fj, golden_cases, idx):
+    """Counts and pair checksums the unmodified reference produced (tests/golden/g1_goldens.json)."""
+    cases = [c for c in golden_cases if c["N"] <= 10**7]
+    if idx >= len(cases):
+        pytest.skip("no such case")
+    c = cases[idx]
+    gen = g1 if c["gen"] == "g1" else g2
+    bk, bv, pk = gen(c["N"], c["ny"], c["match_pct"], c["seed"])
+    for algo, bloom, mat in ALL:
+        n, pairs = run_entry(fj, algo, bloom, mat, bk, bv, pk)
+        assert n == c["count"], (algo, bloom, mat)
+        if mat:
+            cs = O.checksums(*pairs)
+            assert (cs["sum_keys"], cs["xor_keys"], cs["sum_vals"]) == (c["sum_keys"], c["xor_keys"], c["sum_vals"])
+
+
+def test_reference_fixtures(fj, fixtures_npz):
+    """Committed input/output arrays of the reference binary, incl. edge keys (0, 2^64-1, >= 2^32,
+    64-bit values), duplicate build keys (keep-first = the reference's radix path) and probe skew."""
+    for name, f in fixtures_npz.items():
+        expect = (len(f["rk"]), f["rk"], f["rv"])
+        check_all_entry_points(fj, f["bk"], f["bv"], f["pk"], expect=expect)
+
+
+def test_edge_keys_and_sentinel(fj):
+    E = 2**64 - 1
+    bk = np.array([E, 0, 1, 2**32 - 1, 2**32, E - 1, 2**63], dtype=np.uint64)
+    bv = np.array([E, 0, 2**32, 5, 6, 7, E - 1], dtype=np.uint64)
+    pk = np.array([E, E, 0, 3, 2**32 - 1, 2**32, 2**63, E - 1, E - 2, 1, E], dtype=np.uint64)
+    check_all_entry_points(fj, bk, bv, pk)
+    # sentinel key present in the probe side only / build side only
+    check_all_entry_points(fj, bk[1:], bv[1:], pk)
+    check_all_entry_points(fj, bk, bv, pk[2:10])
+    # duplicate sentinel keys on the build side: keep-first
+    bk2 = np.array([E, 5, E, E], dtype=np.uint64)
+    bv2 = np.array([10, 20, 30, 40], dtype=np.uint64)
+    check_all_entry_points(fj, bk2, bv2, np.array([E, 5, E, 6], dtype=np.uint64))
+
+
+def test_wide_keys_and_values(fj):
+    rng = np.random.default_rng(5)
+    nb, np_ = 50_000, 400_000
+    bk = np.unique(rng.integers(0, 2**64 - 1, nb, dtype=np.uint64))
+    bv = rng.integers(0, 2**64 - 1, bk.size, dtype=np.uint64)
+    pk = np.concatenate([rng.choice(bk, np_ // 2), rng.integers(0, 2**64 - 1, np_ // 2, dtype=np.uint64)])
+    rng.shuffle(pk)
+    check_all_entry_points(fj, bk, bv, pk)
+    assert fj.last_stats()["narrow"] is False
+    # narrow keys but one 64-bit value: the optimistic packed attempt must be abandoned and re-run
+    bk, bv, pk = g1(100_000, 10_000, 90)
+    bv = bv.copy(); bv[1234] = 2**40
+    n0 = O.np_join(bk, bv, pk)
+    for algo in ("scalar", "radix"):
+        n, _ = run_entry(fj, algo, False, True, bk, bv, pk)
+        st = fj.last_stats()
+        assert n == n0[0] and st["attempts"] == 2 and st["narrow"] is False
+        assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(n0[1], n0[2]))
+
+
+def test_force_wide_flag(fj):
+    bk, bv, pk = g1(100_000, 10_000, 90)
+    n0 = O.np_join(bk, bv, pk)
+    for algo in ("scalar", "radix"):
+        for bloom in (False, True):
+            n, _ = fj.join_flags(algo, bloom, True, bk, bv, pk, force_wide=True)
+            assert n == n0[0] and fj.last_stats()["narrow"] is False
+            assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(n0[1], n0[2]))
+        n, _ = fj.join_flags(algo, False, True, bk, bv, pk)
+        assert n == n0[0] and fj.last_stats()["narrow"] is True
+
+
+def test_duplicate_build_keys_keep_first(fj):
+    """Duplicate build keys: the contract is keep-first (the reference's radix path and its
+    1-thread scalar path, hash_join.cpp:125/:191); the engine detects duplicates and re-runs the
+    exact path."""
+    rng = np.random.default_rng(9)
+    bk = rng.integers(0, 5000, 60_000).astype(np.uint64)
+    bv = np.arange(60_000, dtype=np.uint64)  # value identifies the build row
+    pk = rng.integers(0, 6000, 200_000).astype(np.uint64)
+    n0, k0, v0 = O.join("radix", False, True, bk, bv, pk)
+    assert (n0, ) == (O.np_join(bk, bv, pk)[0], )
+    for algo, bloom, mat in ALL:
+        n, pairs = run_entry(fj, algo, bloom, mat, bk, bv, pk)
+        assert n == n0
+        assert fj.last_stats()["dedup_exact"] is True
+        if mat:
+            assert np.array_equal(O.sorted_pairs(*pairs), O.sorted_pairs(k0, v0))
+
+
+def test_probe_skew(fj):
+    bk = np.arange(1, 50_001, dtype=np.uint64)
+    bv = bk * np.uint64(7)
+    pk = np.full(1_000_000, 4242, dtype=np.uint64)  # one partition receives every probe row
+    check_all_entry_points(fj, bk, bv, pk)
+    pk2 = np.full(1_000_000, 99_999_999, dtype=np.uint64)  # ...and none of them match
+    check_all_entry_points(fj, bk, bv, pk2)
+
+
+def test_bloom_invariance_and_kinds(fj):
+    bk, bv, pk = g1(500_000, 50_000, 10)
+    n_plain, _ = fj.hash_join_count(bk, bv, pk)
+    n_bloom, _ = fj.hash_join_count_bloom(bk, bv, pk)
+    assert fj.last_stats()["bloom_kind"] == "smem"
+    assert n_plain == n_bloom == O.np_join(bk, bv, pk)[0]
+    fj.configure(smem_bloom=0)
+    try:
+        n_g, _ = fj.hash_join_count_bloom(bk, bv, pk)
+        assert fj.last_stats()["bloom_kind"] == "global" and n_g == n_plain
+        n_g, _ = fj.hash_join_bloom(bk, bv, pk)
+        assert n_g == n_plain
+    finally:
+        fj.configure(smem_bloom=1)
+    # a build side too large for the shared-memory filter takes the global (L2) filter
+    bk, bv, pk = g1(600_000, 400_000, 10)
+    n_b, _ = fj.hash_join_count_bloom(bk, bv, pk)
+    assert fj.last_stats()["bloom_kind"] == "global" and n_b == O.np_join(bk, bv, pk)[0]
+
+
+def test_radix_two_pass_small_partitions(fj):
+    """Force tiny shared-memory partitions so that the two-pass scatter and many partitions are
+    exercised at a size the oracle checks in seconds."""
+    bk, bv, pk = g1(400_000, 300_000, 90)
+    expect = O.np_join(bk, bv, pk)
+    fj.configure(radix_sub_rows=256)
+    try:
+        check_all_entry_points(fj, bk, bv, pk, expect=expect, algos=("radix",))
+        st = fj.last_stats()
+        assert st["path"] == "radix" and st["radix_bits"][1] > 0, st
+        fj.configure(radix_sub_rows=2048)
+        check_all_entry_points(fj, bk, bv, pk, expect=expect, algos=("radix",))
+        assert fj.last_stats()["path"] == "radix"
+        # wide rows through the same machinery
+        n, _ = fj.join_flags("radix", False, True, bk, bv, pk, force_wide=True)
+        assert n == expect[0] and fj.last_stats()["path"] == "radix"
+        assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(expect[1], expect[2]))
+    finally:
+        fj.configure(radix_sub_rows=0)
+
+
+def test_adaptive_equals_explicit_on_both_sides_of_threshold(fj):
+    for ny in (20_000, 3_000_000):
+        bk, bv, pk = g1(3_000_000, ny, 90)
+        n_a, _ = fj.adaptive_join_count(bk, bv, pk)
+        path = fj.last_stats()["path"]
+        n_s, _ = fj.hash_join_count(bk, bv, pk)
+        n_r, _ = fj.hash_join_count_radix(bk, bv, pk)
+        assert n_a == n_s == n_r == O.np_join(bk, bv, pk)[0]
+        assert path in ("scalar", "radix")
+
+
+def test_probe_idx_output(fj):
+    bk, bv, pk = g1(200_000, 20_000, 90)
+    n, _ = fj.join_flags("scalar", False, True, bk, bv, pk, probe_idx=True)
+    k, v, ix = fj.last_pairs(with_probe_idx=True)
+    assert n == k.size == ix.size
+    assert np.array_equal(pk[ix.astype(np.int64)], k)  # idx maps back to the probe key
+    assert np.unique(ix).size == n  # each probe row at most once
+    assert np.array_equal(O.sorted_pairs(k, v), O.sorted_pairs(*O.np_join(bk, bv, pk)[1:]))
+
+
+def test_int64_and_forcecast_inputs(fj):
+    bk = np.array([-1, 5, 7], dtype=np.int64)  # -1 is the same bits as 2^64-1
+    bv = np.array([1, 2, 3], dtype=np.int64)
+    pk = np.array([-1, 7, 8], dtype=np.int64)
+    assert fj.hash_join_count(bk, bv, pk)[0] == 2
+    assert fj.hash_join_count([5, 7], [1, 2], [7, 7, 9])[0] == 2  # lists are converted like forcecast
+    assert fj.hash_join_count(np.array([5, 7], dtype=np.int32), np.array([1, 2], dtype=np.int32), np.array([7], dtype=np.uint8))[0] == 1
+    assert fj.hash_join_count(np.arange(10, dtype=np.uint64)[::2], np.arange(5, dtype=np.uint64), np.array([4, 5], dtype=np.uint64))[0] == 1
+
+
+def test_c_abi_device_resident_inputs(capi):
+    bk, bv, pk = g1(1_000_000, 100_000, 10)
+    n0, k0, v0 = O.np_join(bk, bv, pk)
+    dbk, dbv, dpk = (capi.DeviceArray.from_host(x) for x in (bk, bv, pk))
+    for algo in (capi.ALGO_ADAPTIVE, capi.ALGO_SCALAR, capi.ALGO_RADIX):
+        for flags in (0, capi.FLAG_BLOOM, capi.FLAG_MATERIALIZE, capi.FLAG_MATERIALIZE | capi.FLAG_BLOOM):
+            n, sec, st = capi.join(algo, flags, dbk, dbv, dpk)
+            assert n == n0 and st["h2d_bytes"] == 0 and sec > 0
+            if flags & capi.FLAG_MATERIALIZE:
+                assert np.array_equal(O.sorted_pairs(*capi.pairs()), O.sorted_pairs(k0, v0))
+                assert st["algorithmic_bytes"] == 16 * bk.size + 8 * pk.size + 16 * n0
+            else:
+                assert st["algorithmic_bytes"] == 8 * (bk.size + pk.size)
+    # unaligned device pointer (8-byte aligned only): the probe kernel must not use 128-bit loads
+    import ctypes as C
+
+    class View(capi.DeviceArray):
+        def __init__(self, base, off, n):
+            self.ptr, self.n, self._base = base.ptr + 8 * off, n, base
+
+        def free(self):
+            pass
+
+    n, _, _ = capi.join(capi.ALGO_SCALAR, 0, dbk, dbv, View(dpk, 1, pk.size - 1))
+    assert n == O.np_join(bk, bv, pk[1:])[0]
+    with pytest.raises(capi.FlashJoinError):
+        capi.join(7, 0, dbk, dbv, dpk)
+    with pytest.raises(capi.FlashJoinError):
+        capi.join(capi.ALGO_SCALAR, 1 << 12, dbk, dbv, dpk)
+
+
+def test_pairs_state_errors(fj, capi):
+    a = np.arange(100, dtype=np.uint64)
+    fj.hash_join_count(a, a, a)
+    with pytest.raises(RuntimeError):
+        fj.last_pairs()  # the last call was not a materialize call
+    fj.hash_join(a, a, a)
+    k, v = fj.last_pairs()
+    assert k.size == 100
+
+
+def test_device_generator_matches_numpy(capi):
+    N, ny, pct = 300_000, 40_000, 90
+    keys, vals = capi.generate_g2("build", N, ny, pct, 108, 0, ny)
+    bk, bv = g2_slice(N, ny, pct, 108, "build", 0, ny)
+    assert np.array_equal(keys.to_host(), bk) and np.array_equal(vals.to_host(), bv)
+    pk_d = capi.generate_g2("probe", N, ny, pct, 108, 1000, 50_000)
+    assert np.array_equal(pk_d.to_host(), g2_slice(N, ny, pct, 108, "probe", 1000, 51_000))
+
+
+def test_idempotence_and_arena_reuse(fj):
+    """Same call twice gives the same answer (the arena is reused, the table is re-cleared)."""
+    bk, bv, pk = g1(500_000, 200_000, 90)
+    r = [fj.hash_join_radix(bk, bv, pk)[0] for _ in range(3)] + [fj.hash_join(bk, bv, pk)[0] for _ in range(3)]
+    assert len(set(r)) == 1
+    small = np.arange(10, dtype=np.uint64)
+    assert fj.hash_join_count(small, small, small)[0] == 10  # a smaller join after a larger one
+
+
+# ------------------------------------------------------------------------------------------------ full sizes
+@pytest.mark.big
+def test_c2_full_size_golden(fj, golden_cases):
+    """BASELINE.json configs[1]: flash_join_bloom count, 1e8 x 1e5, ~10 % match."""
+    c = next(x for x in golden_cases if (x["N"], x["ny"], x["match_pct"], x["gen"]) == (10**8, 10**5, 10, "g1"))
+    bk, bv, pk = g1(c["N"], c["ny"], c["match_pct"])
+    for name in ("hash_join_count_bloom", "hash_join_count", "adaptive_join_count", "hash_join_count_radix"):
+        n, sec = getattr(fj, name)(bk, bv, pk)
+        assert n == c["count"], name
+    n, _ = fj.hash_join_bloom(bk, bv, pk)
+    cs = O.checksums(*fj.last_pairs())
+    assert (n, cs["sum_keys"], cs["xor_keys"], cs["sum_vals"]) == (c["count"], c["sum_keys"], c["xor_keys"], c["sum_vals"])
+
+
+@pytest.mark.big
+def test_c3_full_size_golden(fj, golden_cases):
+    """BASELINE.json configs[2]: flash_join_radix materialize, 1e8 x 1e8 (single GPU)."""
+    c = next(x for x in golden_cases if (x["N"], x["ny"], x["gen"]) == (10**8, 10**8, "g1"))
+    bk, bv, pk = g1(c["N"], c["ny"], c["match_pct"])
+    for name in ("hash_join_radix", "adaptive_join"):
+        n, sec = getattr(fj, name)(bk, bv, pk)
+        assert n == c["count"], name
+        k, v = fj.last_pairs()
+        cs = O.checksums(k, v)
+        assert (cs["sum_keys"], cs["xor_keys"], cs["sum_vals"]) == (c["sum_keys"], c["xor_keys"], c["sum_vals"]), name
+        # size-independent properties: every pair key is a build key with that build value; N == ny
+        # makes the probe a permutation, so matched keys are distinct
+        assert np.unique(k).size == n
+    n, _ = fj.hash_join_count_radix(bk, bv, pk)
+    assert n == c["count"]
+    n, _ = fj.hash_join_count(bk, bv, pk)
+    assert n == c["count"]
