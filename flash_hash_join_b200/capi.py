@@ -64,7 +64,7 @@ def lib():
             "fj_host_alloc_pinned": [C.POINTER(vp), C.c_size_t], "fj_host_free_pinned": [vp],
             "fj_device_synchronize": [],
             "fj_generate_g2": [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp],
-            "fj_flush_l2": [],
+            "fj_flush_l2": [], "fj_timer_start": [], "fj_timer_stop": [C.POINTER(C.c_double)],
             "fj_comm_unique_id": [vp], "fj_comm_init": [C.c_int, C.c_int, vp], "fj_comm_destroy": [],
             "fj_join_dist_u64": [C.c_int, C.c_int, C.c_uint, C.c_int, vp, vp, C.c_size_t, vp, C.c_size_t, u64p, u64p,
                                  C.POINTER(C.c_double), C.POINTER(Stats)],

@@ -115,7 +115,7 @@ struct Engine {
     cfg["radix_sub_rows"] = 0;  // 0 = derive from shared memory
     cfg["radix_optimistic"] = 1;
     cfg["smem_bloom"] = 1;
-    cfg["probe_ctas_per_sm"] = 2;
+    cfg["probe_ctas_per_sm"] = 0;  // 0 = occupancy-derived
     cfg["narrow"] = 1;
     cfg["chunk_rows"] = 1 << 24;
   }
@@ -646,6 +646,28 @@ FJ_API fj_status fj_flush_l2(void) {
   FJ_TRY(e.flush.ensure(bytes));
   FJ_CUDA(cudaMemsetAsync(e.flush.p, 0x5a, bytes, e.st));
   FJ_CUDA(cudaStreamSynchronize(e.st));
+  return FJ_OK;
+}
+
+FJ_API fj_status fj_timer_start(void) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  Engine& e = E();
+  FJ_TRY(e.init(-1));
+  FJ_CUDA(cudaSetDevice(e.di.device));
+  FJ_CUDA(cudaEventRecord(e.ev[6], e.st));
+  return FJ_OK;
+}
+FJ_API fj_status fj_timer_stop(double* seconds) {
+  std::lock_guard<std::mutex> lk(E().mu);
+  Engine& e = E();
+  if (!seconds) return set_err(FJ_ERR_BAD_ARG, "seconds is NULL");
+  if (!e.inited) return set_err(FJ_ERR_STATE, "fj_timer_start has not been called");
+  FJ_CUDA(cudaSetDevice(e.di.device));
+  FJ_CUDA(cudaEventRecord(e.ev[7], e.st));
+  FJ_CUDA(cudaEventSynchronize(e.ev[7]));
+  float m = 0.f;
+  FJ_CUDA(cudaEventElapsedTime(&m, e.ev[6], e.ev[7]));
+  *seconds = (double)m * 1e-3;
   return FJ_OK;
 }
 

@@ -364,6 +364,11 @@ static void launch_probe_inst(const TableView& t, const unsigned long long* pk, 
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ctas_per_sm = 1;
   }
+  if (ctas_per_sm <= 0 || BLOOM == 1) {  // auto: fill every SM to the kernel's occupancy limit
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    ctas_per_sm = occ;
+  }
   const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
   const uint64_t ntiles = (np + tile - 1) / tile;
   uint64_t grid = (uint64_t)di.sms * ctas_per_sm;
@@ -381,7 +386,6 @@ void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np,
   const int bloom = t.bloom == nullptr ? 0 : (bloom_in_smem ? 1 : 2);
   const bool mat = out != nullptr;
   const bool idx = mat && out->idx != nullptr;
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
 #define FJ_PROBE(N, B, M, I, T) launch_probe_inst<N, B, M, I, T>(t, pk, np, bv, out, ctas_per_sm, ctl, di, st)
 #define FJ_PROBE_B(N, M, I)                               \
   do {                                                    \

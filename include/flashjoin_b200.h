@@ -142,6 +142,12 @@ FJ_API fj_status fj_generate_g2(int side, uint64_t n_total, uint64_t ny, int mat
                                 uint64_t start, uint64_t count, uint64_t* keys_dev, uint64_t* values_dev_or_null);
 /* Write `bytes` of device memory (> L2) so that the next timed call starts with a cold L2. */
 FJ_API fj_status fj_flush_l2(void);
+/* CUDA-event stopwatch on the engine's own stream (the stream every kernel of this library is
+ * launched on): fj_timer_start records an event, fj_timer_stop records a second one, waits for it
+ * and returns the elapsed device time between the two, idle gaps between calls included.
+ * Replaces SimpleTimer (hash_join.cpp:45-55) for callers timing several joins back to back. */
+FJ_API fj_status fj_timer_start(void);
+FJ_API fj_status fj_timer_stop(double* seconds);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) ----------------------------------------
  * No reference counterpart (hash_join.cpp is single-process, std::thread only).  The caller
