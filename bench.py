@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — the contract benchmark.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation
+
+Workload (config.workload): BASELINE.json configs[1] — `flash_join_bloom` join COUNT, x = 1e8 probe
+rows vs y = 1e5 build rows, ~10 % probe match rate, per GPU (weak scaling: every GPU gets its own
+1e8-row probe slice; the 1e5-row build side lives on rank 0 and is ncclBroadcast inside the step).
+One "step" = one whole join: table clear + build + (broadcast) + probe + count (+ all-reduce).
+
+  value      probe rows / second, whole job, inputs resident in HBM, device time (CUDA events on the
+             engine's stream, bracketed by barrier + synchronize, max over ranks)
+  e2e        same metric through the reference-facing call with HOST (pinned) buffers: the
+             host->device copy of every input and the device->host read of the result are inside
+             the timed region
+  roofline   the dominant kernel (k_probe): algorithmic bytes (8 B per probe row) /
+             its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU code (oracle/_ref, built from /root/reference/hash_join.cpp
+             by oracle/build_ref.sh) on this box's host cores, same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (probe rows per GPU, build rows, match %, entry point, algo, bloom, materialize)
+    "C2": dict(N=100_000_000, ny=100_000, pct=10, entry="hash_join_count_bloom", algo="scalar", bloom=True, mat=False,
+               desc="C2: flash_join_bloom count, x=1e8 probe rows vs y=1e5 build rows, ~10% match (BASELINE.json configs[1])"),
+    "C1": dict(N=10_000_000, ny=10_000, pct=90, entry="adaptive_join_count", algo="adaptive", bloom=False, mat=False,
+               desc="C1: adaptive_join count, x=1e7 vs y=1e4, 90% match (BASELINE.json configs[0])"),
+    "C3": dict(N=100_000_000, ny=100_000_000, pct=90, entry="hash_join_radix", algo="radix", bloom=False, mat=True,
+               desc="C3: flash_join_radix materialize, x=1e8 vs y=1e8, 90% match (BASELINE.json configs[2])"),
+}
+SEED = 108
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        self.f.flush()
+        rows = []
+        try:
+            for line in Path(self.f.name).read_text().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) >= 9:
+                    rows.append(c)
+        finally:
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max((float(r[3]) for r in rows if r[3].replace(".", "").isdigit()), default=None)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference worker (separate process: numpy + the compiled reference only)
+def cpu_worker(args) -> None:
+    import numpy as np
+
+    from flash_hash_join_b200.datagen import g2_slice
+    from oracle import oracle as O
+
+    w = WORKLOADS[args.config]
+    t0 = time.perf_counter()
+    bk, bv = g2_slice(w["N"], w["ny"], w["pct"], SEED, "build", 0, w["ny"])
+    pk = g2_slice(w["N"], w["ny"], w["pct"], SEED, "probe", 0, w["N"])
+    gen_s = time.perf_counter() - t0
+    if O.reference_available("plain"):
+        kind = "reference"
+        fn = getattr(O.load_reference("plain"), w["entry"])
+        cores = os.cpu_count()
+
+        def step():
+            n, sec = fn(bk, bv, pk)
+            return n, sec  # the reference's own SimpleTimer seconds (hash_join.cpp:45-55)
+    else:
+        kind = "port"
+        cores = 1
+
+        def step():
+            t = time.perf_counter()
+            n, _, _ = O.join(w["algo"], w["bloom"], w["mat"], bk, bv, pk)
+            return n, time.perf_counter() - t
+    for _ in range(args.warmup):
+        step()
+    times, n = [], None
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        n, s = step()
+        times.append(s)
+    wall = time.perf_counter() - wall0
+    print(json.dumps({"kind": kind, "cores": cores, "matches": int(n), "core_s_mean": sum(times) / len(times), "core_s_best": min(times),
+                      "wall_s_per_step": wall / len(times), "gen_s": gen_s, "rows": w["N"]}))
+
+
+def run_cpu_worker(config: str, steps: int, warmup: int) -> dict:
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--_cpu_worker", "--config", config, "--steps", str(steps), "--warmup", str(warmup)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    if out.returncode != 0:
+        raise RuntimeError("cpu worker failed: " + out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus: int):
+    """torch.distributed (gloo) is plumbing only: rendezvous, barrier, max-over-ranks, and carrying the
+    NCCL unique id to every rank.  The data path uses the engine's own NCCL communicator."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return rank, world, local, None
+    import torch.distributed as dist
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    return rank, world, local, dist
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--_cpu_worker", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.warmup < 3 and not args._cpu_worker and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args._cpu_worker:
+        cpu_worker(args)
+        return
+    w = WORKLOADS[args.config]
+    metric = "probe rows/sec (join materialize)" if w["mat"] else "probe rows/sec (join count)"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        r = run_cpu_worker(args.config, args.steps, max(1, args.warmup))
+        value = r["rows"] / r["core_s_mean"]
+        line = {
+            "impl": "reference", "metric": metric, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["core_s_mean"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": f"synthetic (G2 counter-based h2o join shape, seed {SEED})",
+            "config": {"workload": w["desc"], "entry_point": w["entry"], "rows_probe": w["N"], "rows_build": w["ny"],
+                       "note": "reference CPU implementation on the host cores of this box; time = its own core seconds"},
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": f"full workload ({w['N']} probe rows) x {args.steps} steps"},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "matches": r["matches"],
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ this engine
+    rank, world, local, dist = dist_setup(args.gpus)
+    os.environ["LOCAL_RANK"] = str(local)
+    import ctypes as C
+
+    import numpy as np
+
+    from flash_hash_join_b200 import capi, flash_join
+
+    L = capi.lib()
+    capi.check(L.fj_init(local))
+    if world > 1:
+        ident = [None]
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            capi.check(L.fj_comm_unique_id(buf))
+            ident = [bytes(buf)]
+        dist.broadcast_object_list(ident, src=0)
+        capi.check(L.fj_comm_init(rank, world, ident[0]))
+
+    N, ny, pct = w["N"], w["ny"], w["pct"]
+    n_total = N * world
+    algo = {"adaptive": capi.ALGO_ADAPTIVE, "scalar": capi.ALGO_SCALAR, "radix": capi.ALGO_RADIX}[w["algo"]]
+    flags = (capi.FLAG_BLOOM if w["bloom"] else 0) | (capi.FLAG_MATERIALIZE if w["mat"] else 0)
+    # inputs resident in HBM: every rank its own probe slice; the build side on every rank (used by rank 0 only when world > 1)
+    d_bk, d_bv = capi.generate_g2("build", n_total, ny, pct, SEED, 0, ny)
+    d_pk = capi.generate_g2("probe", n_total, ny, pct, SEED, rank * N, N)
+
+    def step_device():
+        n = C.c_uint64(0)
+        nl = C.c_uint64(0)
+        sec = C.c_double(0)
+        st = capi.Stats()
+        if world == 1:
+            capi.check(L.fj_join_u64(algo, flags | capi.FLAG_DEVICE_INPUTS, d_bk.ptr, d_bv.ptr, ny, d_pk.ptr, N, C.byref(n), C.byref(sec), C.byref(st)))
+        else:
+            capi.check(L.fj_join_dist_u64(capi.DIST_BROADCAST, algo, flags | capi.FLAG_DEVICE_INPUTS, 0, d_bk.ptr, d_bv.ptr, ny, d_pk.ptr, N,
+                                          C.byref(n), C.byref(nl), C.byref(sec), C.byref(st)))
+        return n.value, st
+
+    def barrier():
+        capi.check(L.fj_device_synchronize())
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        matches, _ = step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    capi.check(L.fj_timer_start())
+    launches = 0
+    probe_s, device_s, phases = [], [], {"clear_s": 0.0, "build_s": 0.0, "partition_s": 0.0, "probe_s": 0.0, "comm_s": 0.0}
+    for _ in range(args.steps):
+        matches, st = step_device()
+        launches += st.kernel_launches
+        probe_s.append(st.probe_s)
+        device_s.append(st.device_s)
+        for k in phases:
+            phases[k] += getattr(st, k)
+    t = C.c_double(0)
+    capi.check(L.fj_timer_stop(C.byref(t)))
+    barrier()
+    clocks = sampler.stop()
+    elapsed = max_over_ranks(t.value)
+    value = n_total * args.steps / elapsed
+    last = st.as_dict()
+
+    # roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    dom_s = statistics.mean(probe_s)
+    if w["mat"]:
+        alg_bytes_kernel = 8.0 * N + 16.0 * matches / world  # probe keys read + pairs written
+    else:
+        alg_bytes_kernel = 8.0 * N  # 8 B per probe row; build-side bytes belong to the build kernel
+    achieved = alg_bytes_kernel / dom_s * 1e-9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.config, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_join (smem partition join)" if last["path"] == "radix" else "k_probe", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_kernel, "kernel_ms": dom_s * 1e3,
+                "whole_step_frac": (last["algorithmic_bytes"] / (elapsed / args.steps) * 1e-9) / peak}
+
+    # e2e: host (pinned) buffers through the reference-facing call
+    e2e = None
+    if not args.no_e2e:
+        h_bk, h_bv, h_pk = flash_join.pinned_empty(ny), flash_join.pinned_empty(ny), flash_join.pinned_empty(N)
+        capi.check(L.fj_memcpy_d2h(h_bk.ctypes.data, d_bk.ptr, ny * 8))
+        capi.check(L.fj_memcpy_d2h(h_bv.ctypes.data, d_bv.ptr, ny * 8))
+        capi.check(L.fj_memcpy_d2h(h_pk.ctypes.data, d_pk.ptr, N * 8))
+        e_steps = max(3, min(args.steps, 10))
+
+        def step_host():
+            if world == 1:
+                n, _sec = getattr(flash_join, w["entry"])(h_bk, h_bv, h_pk)  # the call a flash_join user makes
+                return n
+            n = C.c_uint64(0)
+            capi.check(L.fj_join_dist_u64(capi.DIST_BROADCAST, algo, flags, 0, h_bk.ctypes.data, h_bv.ctypes.data, ny, h_pk.ctypes.data, N,
+                                          C.byref(n), None, None, None))
+            return n.value
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            m2 = step_host()
+        capi.check(L.fj_device_synchronize())
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert m2 == matches, (m2, matches)
+        e2e = {"value": n_total * e_steps / dt, "unit": "rows/s", "h2d_bytes_per_step": (2 * ny + N) * 8, "d2h_bytes_per_step": 48,
+               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "host_memory": "pinned (flash_join.pinned_empty)",
+               "api": f"flash_join.{w['entry']}" if world == 1 else "fj_join_dist_u64 (C ABI, host buffers)"}
+        del h_bk, h_bv, h_pk
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_cpu_worker(args.config, 5, 1)
+            cpu = {"value": r["rows"] / r["core_s_mean"], "unit": "rows/s", "cores": r["cores"], "kind": r["kind"],
+                   "sample": f"full workload ({r['rows']} probe rows) x 5 steps, time = reference core seconds", "matches": r["matches"]}
+            if r["matches"] != matches:
+                cpu["MISMATCH"] = f"reference counted {r['matches']}, engine counted {matches}"
+        except Exception as e:  # the baseline is reported, never required for the engine number
+            cpu = {"value": None, "unit": "rows/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": f"synthetic (G2 counter-based h2o join shape, seed {SEED}; generated in HBM)",
+            "config": {"workload": w["desc"], "entry_point": w["entry"], "rows_probe_per_gpu": N, "rows_build": ny, "match_pct": pct,
+                       "l2": f"inputs {8 * N / 1e6:.0f} MB per step > 126 MB L2 (no flush needed); table and Bloom filter are rebuilt every step",
+                       "parallelism": "single GPU" if world == 1 else f"build side ncclBroadcast from rank 0, probe side split over {world} GPUs, count ncclAllReduce",
+                       "path": last["path"], "narrow_slots": bool(last["narrow"]), "bloom": last["bloom_kind"]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "matches": matches, "phases_ms_per_step": {k: v / args.steps * 1e3 for k, v in phases.items()},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        capi.check(L.fj_comm_destroy())
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

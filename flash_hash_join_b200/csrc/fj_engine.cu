@@ -134,7 +134,11 @@ struct Engine {
                         uint64_t nb, const unsigned long long* pk, uint64_t np, uint64_t idx_base, fj_stats* s);
   fj_status join(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb, const uint64_t* pk,
                  size_t np, uint64_t* out_matches, double* out_seconds, fj_stats* stats);
+  fj_status join_dist(int mode, int algo, unsigned flags, int root, const uint64_t* bk, const uint64_t* bv, size_t nb,
+                      const uint64_t* pk, size_t np, uint64_t* out_global, uint64_t* out_local, double* out_seconds,
+                      fj_stats* stats);
   fj_status ensure_out(unsigned flags, uint64_t np);
+  DevBuf dist_scratch;
   float ms(int a, int b) {
     float m = 0.f;
     cudaEventElapsedTime(&m, ev[a], ev[b]);
@@ -186,7 +190,7 @@ void Engine::shutdown() {
   dist_destroy(dist);
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
-                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush})
+                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &dist_scratch})
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
@@ -495,6 +499,86 @@ fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint6
   return FJ_OK;
 }
 
+// ---- multi-GPU drivers (one process per GPU) ---------------------------------------------------
+// BROADCAST (small build side, BASELINE.json configs[3]): the build rows given on `root` are
+// ncclBroadcast to every rank (16*nb bytes — cheaper than shipping the >= 2x larger table), every
+// rank builds its own table and probes its own probe slice; the per-rank counts are summed with
+// ncclAllReduce.  Materialized pairs stay sharded on the rank that produced them.
+fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const uint64_t* bk, const uint64_t* bv,
+                            size_t nb, const uint64_t* pk, size_t np, uint64_t* out_global, uint64_t* out_local,
+                            double* out_seconds, fj_stats* stats) {
+  if (!dist.ready) return set_err(FJ_ERR_STATE, "fj_comm_init has not been called");
+  if (mode != FJ_DIST_BROADCAST && mode != FJ_DIST_SHUFFLE) return set_err(FJ_ERR_BAD_ARG, "unknown dist mode %d", mode);
+  if (!out_global) return set_err(FJ_ERR_BAD_ARG, "out_matches_global is NULL");
+  if (root < 0 || root >= dist.world) return set_err(FJ_ERR_BAD_ARG, "root %d out of range", root);
+  if (algo < FJ_ALGO_ADAPTIVE || algo > FJ_ALGO_RADIX) return set_err(FJ_ERR_BAD_ARG, "unknown algo %d", algo);
+  if (np && !pk) return set_err(FJ_ERR_BAD_ARG, "NULL probe pointer with non-zero length");
+  FJ_CUDA(cudaSetDevice(di.device));
+  const double t0 = now_s();
+  fj_stats s;
+  memset(&s, 0, sizeof(s));
+  s.n_gpus = dist.world;
+  const bool dev_in = flags & FJ_FLAG_DEVICE_INPUTS;
+  const unsigned jflags = flags & ~FJ_FLAG_DEVICE_INPUTS;
+  FJ_TRY(dist_scratch.ensure(64));
+  unsigned long long* d_cnt = dist_scratch.as<unsigned long long>();
+
+  if (mode == FJ_DIST_BROADCAST) {
+    const bool is_root = dist.rank == root;
+    if (is_root && nb && (!bk || !bv)) return set_err(FJ_ERR_BAD_ARG, "root rank must supply the build side");
+    // stage inputs in HBM
+    const unsigned long long* d_pk;
+    FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
+    FJ_TRY(in_bv.ensure(std::max<size_t>(nb, 1) * 8));
+    const double th = now_s();
+    if (dev_in) {
+      d_pk = reinterpret_cast<const unsigned long long*>(pk);
+      if (is_root && nb) {
+        FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyDeviceToDevice, st));
+        FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyDeviceToDevice, st));
+      }
+    } else {
+      FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
+      if (is_root && nb) {
+        FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyHostToDevice, st));
+        FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyHostToDevice, st));
+      }
+      if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+      FJ_CUDA(cudaStreamSynchronize(st));
+      s.h2d_s = now_s() - th;
+      s.h2d_bytes = (uint64_t)((is_root ? 2 * nb : 0) + np) * 8;
+      d_pk = in_pk.as<unsigned long long>();
+    }
+    // broadcast the raw build rows
+    FJ_CUDA(cudaEventRecord(ev[4], st));
+    if (nb) {
+      FJ_TRY(dist_broadcast_u64(dist, in_bk.p, nb, root, st));
+      FJ_TRY(dist_broadcast_u64(dist, in_bv.p, nb, root, st));
+    }
+    FJ_CUDA(cudaEventRecord(ev[5], st));
+    FJ_TRY(join_device(algo, jflags, in_bk.as<unsigned long long>(), in_bv.as<unsigned long long>(), nb, d_pk, np, 0, &s));
+    // global count
+    FJ_CUDA(cudaEventRecord(ev[0], st));
+    FJ_CUDA(cudaMemcpyAsync(d_cnt, &s.matches, 8, cudaMemcpyHostToDevice, st));
+    FJ_TRY(dist_allreduce_sum_u64(dist, d_cnt, d_cnt + 1, 1, st));
+    unsigned long long total = 0;
+    FJ_CUDA(cudaMemcpyAsync(&total, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaEventRecord(ev[1], st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    s.comm_s = (ms(4, 5) + ms(0, 1)) * 1e-3;
+    s.device_s += s.comm_s;
+    *out_global = total;
+  } else {
+    return set_err(FJ_ERR_STATE, "FJ_DIST_SHUFFLE is not implemented in this build");
+  }
+  if (out_local) *out_local = s.matches;
+  s.wall_s = now_s() - t0;
+  s.algorithmic_bytes = (jflags & FJ_FLAG_MATERIALIZE) ? 16ull * nb + 8ull * np + 16ull * s.matches : 8ull * (nb + np);
+  if (out_seconds) *out_seconds = s.device_s;
+  if (stats) *stats = s;
+  return FJ_OK;
+}
+
 }  // namespace fj
 
 // ================================================================================================
@@ -692,14 +776,8 @@ FJ_API fj_status fj_join_dist_u64(int mode, int algo, unsigned flags, int root, 
                                   size_t nb, const uint64_t* pk, size_t np, uint64_t* out_matches_global,
                                   uint64_t* out_matches_local, double* out_seconds, fj_stats* stats) {
   std::lock_guard<std::mutex> lk(E().mu);
-  Engine& e = E();
-  if (!e.dist.ready) return set_err(FJ_ERR_STATE, "fj_comm_init has not been called");
-  if (mode != FJ_DIST_BROADCAST && mode != FJ_DIST_SHUFFLE) return set_err(FJ_ERR_BAD_ARG, "unknown dist mode %d", mode);
-  if (!out_matches_global) return set_err(FJ_ERR_BAD_ARG, "out_matches_global is NULL");
-  FJ_CUDA(cudaSetDevice(e.di.device));
-  (void)algo; (void)flags; (void)root; (void)bk; (void)bv; (void)nb; (void)pk; (void)np;
-  (void)out_matches_local; (void)out_seconds; (void)stats;
-  return set_err(FJ_ERR_STATE, "distributed join driver not linked in this build");
+  return E().join_dist(mode, algo, flags, root, bk, bv, nb, pk, np, out_matches_global, out_matches_local, out_seconds,
+                       stats);
 }
 
 }  // extern "C"
