@@ -46,16 +46,30 @@ __host__ __device__ __forceinline__ uint32_t reduce32(uint32_t h, uint32_t n) {
 }
 
 // ---- Bloom filter: sectorised, register-blocked ------------------------------------------------
-// One 32-bit word per key ("register-blocked": all k=3 bits of a key live in a single word, so a
-// check is one 4-byte load and one AND/compare); words are addressed so that the filter is a
-// dense array of 32-byte sectors.  Replaces the 16-bit-per-slot directory of :60-74, :183-189.
-__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t h) {
-  return (1u << (h & 31)) | (1u << ((h >> 5) & 31)) | (1u << ((h >> 10) & 31));
+// One 32-bit word per key ("register-blocked": both bits of a key live in a single word, so a
+// check is one 4-byte load and one AND/compare); the filter is a dense array of 32-byte sectors
+// and, when it fits, is staged in shared memory by the probe kernel.  Replaces the
+// 16-bit-per-slot directory of hash_join.cpp:60-74, :183-189.  The filter has its own, cheaper
+// hash (5 integer instructions): it runs for EVERY probe row, the table hash only for survivors.
+__host__ __device__ __forceinline__ uint32_t bloom_hash(uint64_t key) {
+  uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  return x;
 }
-__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t h, uint32_t nwords) {
-  uint32_t g = (h ^ (h >> 15)) * 0x2c1b3c6dU;  // decorrelate from the table index (top bits of h)
-  g ^= g >> 13;
-  return reduce32(g, nwords);
+__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(0u, 1u, x) | __funnelshift_l(0u, 1u, x >> 5);  // 1 << (x & 31) | 1 << ((x >> 5) & 31)
+#else
+  return (1u << (x & 31)) | (1u << ((x >> 5) & 31));
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t x, uint32_t nwords) { return reduce32(x, nwords); }
+
+// packed ("narrow") rows: key and value both fit 32 bits and key != 0xFFFFFFFF, so that a packed
+// slot key32<<32|value32 can never equal the empty marker and "high word == 0xFFFFFFFF" means empty.
+__host__ __device__ __forceinline__ bool narrow_ok(unsigned long long k, unsigned long long v) {
+  return ((k | v) >> 32) == 0 && (uint32_t)k != 0xFFFFFFFFu;
 }
 
 #ifdef __CUDACC__

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
             const unsigned long long v = ld_stream1(in_vals + in_base + e);
             if constexpr (NARROW) {
               const unsigned long long packed = (k << 32) | (v & 0xffffffffull);
-              if (((k | v) >> 32) != 0 || packed == EMPTY64) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
+              if (!narrow_ok(k, v)) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
               elem[i] = packed;
             } else {
               if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(in_base + e)); ok = false; }
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
             }
           } else {
             if constexpr (NARROW) {
-              if ((k >> 32) != 0) ok = false;  // cannot match a packed build side
+              if ((k >> 32) != 0 || (uint32_t)k == 0xFFFFFFFFu) ok = false;  // cannot match a packed build side
               elem[i] = (uint32_t)k;
             } else {
               if (k == EMPTY64) { ++sentinel_local; ok = false; }

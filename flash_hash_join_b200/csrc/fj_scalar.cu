@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_build(unsigned long long* __restrict__ 
     const unsigned long long v = bv[i];
     if (NARROW) {
       const unsigned long long packed = (k << 32) | (v & 0xffffffffull);
-      if (((k | v) >> 32) != 0 || packed == EMPTY64) {
+      if (!narrow_ok(k, v)) {
         atomicOr(&ctl->flags, CTL_NEED_WIDE);  // attempt is abandoned by the host
         return;
       }
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) k_build(unsigned long long* __restrict__ 
         }
         if (++b == nbuckets) b = 0;
       }
-      if (BLOOM) atomicOr(bloom + bloom_word(h, bloom_words), bloom_mask(h));
+      if (BLOOM) { const uint32_t x = bloom_hash(k); atomicOr(bloom + bloom_word(x, bloom_words), bloom_mask(x)); }
     } else {
       if (k == EMPTY64) {  // the one key that collides with the empty marker: keep out of band
         atomicMin(&ctl->sentinel_row, (unsigned long long)i);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) k_build(unsigned long long* __restrict__ 
         }
         if (++b == nbuckets) b = 0;
       }
-      if (BLOOM) atomicOr(bloom + bloom_word(h, bloom_words), bloom_mask(h));
+      if (BLOOM) { const uint32_t x = bloom_hash(k); atomicOr(bloom + bloom_word(x, bloom_words), bloom_mask(x)); }
     }
   }
 }
@@ -145,73 +145,264 @@ void launch_build(const TableView& t, const unsigned long long* bk, const unsign
 }
 
 // =================================================================================== probe
-// One lookup.  Returns true and the build value on the first (only) slot holding `key`.
+// Lookup of one key.  The home bucket (one 32-byte sector, loaded by the caller so that several
+// loads are in flight) is resolved branch-free; the linear continuation past a FULL home bucket
+// (rare at load factor 0.5) lives in a separate non-inlined function.  Buckets fill in slot order
+// (k_build claims the first empty slot), so "last slot empty" <=> "bucket not full".
 template <bool NARROW>
-__device__ __forceinline__ bool probe_resolve(unsigned long long key, uint32_t b, unsigned long long s0,
-                                              unsigned long long s1, unsigned long long s2, unsigned long long s3,
-                                              const unsigned long long* __restrict__ slots, uint32_t nbuckets,
-                                              unsigned long long& value) {
-  // s0..s3 = contents of the home bucket (already loaded); continue linearly only when the
-  // bucket is full and holds no match (rare at load factor <= 0.5).
-  for (uint32_t it = 0; it < nbuckets; ++it) {
+__device__ __noinline__ bool probe_chain(unsigned long long key, uint32_t b, const unsigned long long* __restrict__ slots,
+                                         uint32_t nbuckets, unsigned long long& value) {
+  for (uint32_t it = 1; it < nbuckets; ++it) {
+    if (++b == nbuckets) b = 0;
+    unsigned long long s0, s1, s2, s3;
+    ld_sector(slots + (size_t)b * 4, s0, s1, s2, s3);
     if (NARROW) {
       const uint32_t k32 = (uint32_t)key;
-      if ((uint32_t)(s0 >> 32) == k32 && s0 != EMPTY64) { value = s0 & 0xffffffffull; return true; }
-      if ((uint32_t)(s1 >> 32) == k32 && s1 != EMPTY64) { value = s1 & 0xffffffffull; return true; }
-      if ((uint32_t)(s2 >> 32) == k32 && s2 != EMPTY64) { value = s2 & 0xffffffffull; return true; }
-      if ((uint32_t)(s3 >> 32) == k32 && s3 != EMPTY64) { value = s3 & 0xffffffffull; return true; }
-      if (s0 == EMPTY64 || s1 == EMPTY64 || s2 == EMPTY64 || s3 == EMPTY64) return false;
+      if ((uint32_t)(s0 >> 32) == k32) { value = (uint32_t)s0; return true; }
+      if ((uint32_t)(s1 >> 32) == k32) { value = (uint32_t)s1; return true; }
+      if ((uint32_t)(s2 >> 32) == k32) { value = (uint32_t)s2; return true; }
+      if ((uint32_t)(s3 >> 32) == k32) { value = (uint32_t)s3; return true; }
+      if ((uint32_t)(s3 >> 32) == 0xFFFFFFFFu) return false;
     } else {
       if (s0 == key) { value = s1; return true; }
       if (s2 == key) { value = s3; return true; }
-      if (s0 == EMPTY64 || s2 == EMPTY64) return false;
+      if (s2 == EMPTY64) return false;
     }
-    if (++b == nbuckets) b = 0;
-    ld_sector(slots + (size_t)b * 4, s0, s1, s2, s3);
   }
   return false;
 }
 
-constexpr int PROBE_KPT = 8;  // probe keys per thread per tile (4 x 128-bit loads)
+template <bool NARROW>
+__device__ __forceinline__ bool probe_home(unsigned long long key, uint32_t b, unsigned long long s0,
+                                           unsigned long long s1, unsigned long long s2, unsigned long long s3,
+                                           const unsigned long long* __restrict__ slots, uint32_t nbuckets,
+                                           unsigned long long& value) {
+  if (NARROW) {
+    const uint32_t k32 = (uint32_t)key;
+    const bool ok = ((key >> 32) == 0) & (k32 != 0xFFFFFFFFu);  // else: cannot be in a packed table
+    const bool m0 = (uint32_t)(s0 >> 32) == k32, m1 = (uint32_t)(s1 >> 32) == k32;
+    const bool m2 = (uint32_t)(s2 >> 32) == k32, m3 = (uint32_t)(s3 >> 32) == k32;
+    const bool hit = ok & (m0 | m1 | m2 | m3);
+    value = m0 ? (uint32_t)s0 : m1 ? (uint32_t)s1 : m2 ? (uint32_t)s2 : (uint32_t)s3;
+    const bool full = (uint32_t)(s3 >> 32) != 0xFFFFFFFFu;
+    if (ok & !hit & full) return probe_chain<true>(key, b, slots, nbuckets, value);
+    return hit;
+  } else {
+    const bool ok = key != EMPTY64;  // the sentinel key is joined out of band by the caller
+    const bool m0 = s0 == key, m1 = s2 == key;
+    const bool hit = ok & (m0 | m1);
+    value = m0 ? s1 : s3;
+    if (ok & !hit & (s2 != EMPTY64)) return probe_chain<false>(key, b, slots, nbuckets, value);
+    return hit;
+  }
+}
 
-// occupancy targets: count kernels 2 x 512 threads (<= 64 regs); the shared-memory-Bloom count kernel
-// 1 x 1024; materialize kernels keep 8 (key, value) pairs live per thread and get more registers.
-template <int BLOOM, bool MAT, int THREADS>
-constexpr int probe_min_blocks() { return BLOOM == 1 ? 1 : (MAT ? 3 : 2); }
+constexpr int PROBE_KPT = 8;   // probe keys per thread per tile (4 x 128-bit loads)
+constexpr int PROBE_QCAP = 64; // per-warp survivor queue (Bloom variants), entries
 
-template <bool NARROW, int BLOOM /*0 none, 1 smem, 2 global*/, bool MAT, bool IDX, int THREADS>
-__global__ void __launch_bounds__(THREADS, probe_min_blocks<BLOOM, MAT, THREADS>())
-    k_probe(const unsigned long long* __restrict__ pk, uint64_t np, const unsigned long long* __restrict__ slots,
-            uint32_t nbuckets, const uint32_t* __restrict__ bloom, uint32_t bloom_words,
-            const unsigned long long* __restrict__ bv, Ctl* __restrict__ ctl, unsigned long long* __restrict__ out_keys,
-            unsigned long long* __restrict__ out_vals, unsigned long long* __restrict__ out_idx,
-            unsigned long long idx_base, int vec_ok) {
+// load one tile of probe keys: 128-bit coalesced loads when aligned and full, guarded otherwise
+template <int THREADS>
+__device__ __forceinline__ void load_tile(const unsigned long long* __restrict__ pk, uint64_t np, uint64_t tbase, bool vec,
+                                          unsigned long long (&key)[PROBE_KPT], bool (&valid)[PROBE_KPT]) {
+  const int tid = threadIdx.x;
+  if (vec) {
+#pragma unroll
+    for (int r = 0; r < PROBE_KPT / 2; ++r) {
+      const uint64_t e = tbase + 2ull * ((uint64_t)r * THREADS + tid);
+      ld_stream2(pk + e, key[2 * r], key[2 * r + 1]);
+      valid[2 * r] = valid[2 * r + 1] = true;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < PROBE_KPT; ++q) {
+      const uint64_t e = tbase + (uint64_t)q * THREADS + tid;
+      valid[q] = e < np;
+      key[q] = valid[q] ? ld_stream1(pk + e) : 0ull;
+    }
+  }
+}
+
+// stage the whole Bloom filter in shared memory with TMA bulk copies (cp.async.bulk + mbarrier)
+__device__ __forceinline__ void stage_bloom(unsigned char* smem_dst, const uint32_t* __restrict__ bloom, uint32_t bloom_words,
+                                            uint64_t* bar) {
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = bloom_words * 4u;
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+      bulk_g2s(smem_dst + off, reinterpret_cast<const unsigned char*>(bloom) + off, n, bar);
+    }
+  }
+  mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------------------------ count
+// Every probe row first goes through a dense, branch-free stage with all lanes active (Bloom test,
+// or the home-bucket test when there is no filter).  Rows that still need table work afterwards
+// ("survivors": filter hits, or keys whose home bucket was full without a match) are a sparse
+// subset; they are compacted into a per-warp shared-memory queue — one warp scan per tile, not one
+// ballot per row — and the table is probed only when a full warp of survivors is available, so the
+// sparse divergent work becomes dense warp work again.  When a tile has too many survivors for the
+// queue (filter useless, e.g. ~100 % match rate) the warp resolves that tile directly instead.
+template <bool NARROW, int BLOOM /*0 none, 1 smem, 2 global*/, int THREADS>
+__global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
+    k_probe_count(const unsigned long long* __restrict__ pk, uint64_t np, const unsigned long long* __restrict__ slots,
+                  uint32_t nbuckets, const uint32_t* __restrict__ bloom, uint32_t bloom_words, Ctl* __restrict__ ctl,
+                  int vec_ok) {
+  constexpr uint32_t TILE = THREADS * PROBE_KPT;
+  constexpr uint32_t QMASK = PROBE_QCAP - 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const uint32_t* sbloom = reinterpret_cast<const uint32_t*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long* queue =
+      reinterpret_cast<unsigned long long*>(smem_raw + (BLOOM == 1 ? (size_t)bloom_words * 4 : 0)) + warp * PROBE_QCAP;
+
+  if (BLOOM == 1) stage_bloom(smem_raw, bloom, bloom_words, &s_bar);
+  bool sent_present = false;
+  if (!NARROW) sent_present = ctl->sentinel_row != EMPTY64;
+
+  // full lookup of one key, starting `skip` buckets after its home bucket
+  auto lookup = [&](unsigned long long k, uint32_t skip) -> bool {
+    uint32_t b = reduce32(hash32(k), nbuckets) + skip;
+    if (b >= nbuckets) b -= nbuckets;
+    unsigned long long s0, s1, s2, s3, v;
+    ld_sector(slots + (size_t)b * 4, s0, s1, s2, s3);
+    bool hit = probe_home<NARROW>(k, b, s0, s1, s2, s3, slots, nbuckets, v);
+    if (!NARROW) hit |= (k == EMPTY64) & sent_present;
+    return hit;
+  };
+  constexpr uint32_t SKIP = BLOOM == 0 ? 1u : 0u;  // without a filter the queue holds keys past their home bucket
+
+  uint32_t cnt = 0, qh = 0, qt = 0;
+  const uint64_t ntiles = (np + TILE - 1) / TILE;
+  // register double buffering: the next tile's keys are requested before the current tile is
+  // processed, so the HBM latency of the key stream overlaps the filter / table work
+  unsigned long long nkey[PROBE_KPT];
+  bool nvalid[PROBE_KPT];
+  if (blockIdx.x < ntiles) {
+    const uint64_t tb0 = (uint64_t)blockIdx.x * TILE;
+    load_tile<THREADS>(pk, np, tb0, vec_ok && tb0 + TILE <= np, nkey, nvalid);
+  }
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    unsigned long long key[PROBE_KPT];
+    bool valid[PROBE_KPT];
+#pragma unroll
+    for (int q = 0; q < PROBE_KPT; ++q) { key[q] = nkey[q]; valid[q] = nvalid[q]; }
+    if (tile + gridDim.x < ntiles) {
+      const uint64_t tbn = (tile + gridDim.x) * TILE;
+      load_tile<THREADS>(pk, np, tbn, vec_ok && tbn + TILE <= np, nkey, nvalid);
+    }
+    uint32_t surv = 0;  // bit q set: key[q] needs (more) table work
+    if (BLOOM == 0) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        unsigned long long s[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 4 sector loads in flight per thread
+          const uint32_t b = reduce32(hash32(key[half * 4 + j]), nbuckets);
+          ld_sector(slots + (size_t)b * 4, s[j][0], s[j][1], s[j][2], s[j][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = half * 4 + j;
+          const unsigned long long k = key[q];
+          bool hit, more;
+          if (NARROW) {
+            const uint32_t k32 = (uint32_t)k;
+            const bool ok = valid[q] & ((k >> 32) == 0) & (k32 != 0xFFFFFFFFu);
+            hit = ok & (((uint32_t)(s[j][0] >> 32) == k32) | ((uint32_t)(s[j][1] >> 32) == k32) |
+                        ((uint32_t)(s[j][2] >> 32) == k32) | ((uint32_t)(s[j][3] >> 32) == k32));
+            more = ok & !hit & ((uint32_t)(s[j][3] >> 32) != 0xFFFFFFFFu);
+          } else {
+            const bool ok = valid[q] & (k != EMPTY64);
+            hit = ok & ((s[j][0] == k) | (s[j][2] == k));
+            more = ok & !hit & (s[j][2] != EMPTY64);
+            hit |= valid[q] & (k == EMPTY64) & sent_present;
+          }
+          cnt += hit ? 1u : 0u;
+          surv |= more ? (1u << q) : 0u;
+        }
+      }
+    } else {
+      uint32_t x[PROBE_KPT], w[PROBE_KPT];
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {  // all filter words requested before any is tested
+        x[q] = bloom_hash(key[q]);
+        const uint32_t wi = bloom_word(x[q], bloom_words);
+        w[q] = (BLOOM == 1) ? sbloom[wi] : __ldg(bloom + wi);
+      }
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const uint32_t m = bloom_mask(x[q]);
+        bool pass = valid[q] & ((~w[q] & m) == 0u);
+        if (!NARROW) pass |= valid[q] & (key[q] == EMPTY64);  // the out-of-band key is not in the filter
+        surv |= pass ? (1u << q) : 0u;
+      }
+    }
+    // ---- compact the tile's survivors into the warp queue (one scan per tile)
+    const uint32_t c = __popc(surv);
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;  // warp-uniform
+    if (qt - qh + total <= (uint32_t)PROBE_QCAP) {
+      uint32_t pos = qt + incl - c;
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        if ((surv >> q) & 1u) { queue[pos & QMASK] = key[q]; ++pos; }
+      }
+      qt += total;
+      while (qt - qh >= 32u) {
+        __syncwarp();
+        const unsigned long long k = queue[(qh + lane) & QMASK];
+        qh += 32u;
+        cnt += lookup(k, SKIP) ? 1u : 0u;
+      }
+      __syncwarp();
+    } else {
+      // dense tile: resolve the survivors in place
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        if ((surv >> q) & 1u) cnt += lookup(key[q], SKIP) ? 1u : 0u;
+      }
+    }
+  }
+  // drain the remainder (< 32 survivors)
+  __syncwarp();
+  if ((uint32_t)lane < qt - qh) cnt += lookup(queue[(qh + lane) & QMASK], SKIP) ? 1u : 0u;
+  unsigned long long total = cnt;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+  if (lane == 0 && total) atomicAdd(&ctl->match_count, total);
+}
+
+// ------------------------------------------------------------------------------------ materialize
+// Pairs are compacted per tile: per (warp, key slot) ballot -> block scan of the WARPS*KPT counts
+// -> one bump of the global cursor per tile -> each (warp, slot) writes one contiguous run.
+template <bool NARROW, int BLOOM, bool IDX, int THREADS>
+__global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 3)
+    k_probe_mat(const unsigned long long* __restrict__ pk, uint64_t np, const unsigned long long* __restrict__ slots,
+                uint32_t nbuckets, const uint32_t* __restrict__ bloom, uint32_t bloom_words,
+                const unsigned long long* __restrict__ bv, Ctl* __restrict__ ctl, unsigned long long* __restrict__ out_keys,
+                unsigned long long* __restrict__ out_vals, unsigned long long* __restrict__ out_idx,
+                unsigned long long idx_base, int vec_ok) {
   constexpr int WARPS = THREADS / 32;
   constexpr uint32_t TILE = THREADS * PROBE_KPT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint32_t s_wcnt[MAT ? WARPS * PROBE_KPT : 1];
+  __shared__ uint32_t s_wcnt[WARPS * PROBE_KPT];
   __shared__ unsigned long long s_base;
   __shared__ __align__(8) uint64_t s_bar;
   const uint32_t* sbloom = reinterpret_cast<const uint32_t*>(smem_raw);
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (BLOOM == 1) {
-    // stage the whole filter in shared memory with TMA bulk copies (cp.async.bulk + mbarrier)
-    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t bytes = bloom_words * 4u;
-      mbar_expect_tx(&s_bar, bytes);
-      for (uint32_t off = 0; off < bytes; off += 32768u) {
-        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-        bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(bloom) + off, n, &s_bar);
-      }
-    }
-    mbar_wait(&s_bar, 0);
-  }
-
-  // out-of-band key (wide tables only): value of the first build row whose key == EMPTY64
+  if (BLOOM == 1) stage_bloom(smem_raw, bloom, bloom_words, &s_bar);
   bool sent_present = false;
   unsigned long long sent_value = 0;
   if (!NARROW) {
@@ -226,157 +417,148 @@ __global__ void __launch_bounds__(THREADS, probe_min_blocks<BLOOM, MAT, THREADS>
     unsigned long long key[PROBE_KPT];
     bool valid[PROBE_KPT];
     const bool vec = vec_ok && tbase + TILE <= np;
-    if (vec) {
-      // 128-bit coalesced loads: each warp instruction reads 512 contiguous bytes
-#pragma unroll
-      for (int r = 0; r < PROBE_KPT / 2; ++r) {
-        const uint64_t e = tbase + 2ull * ((uint64_t)r * THREADS + tid);
-        ld_stream2(pk + e, key[2 * r], key[2 * r + 1]);
-        valid[2 * r] = valid[2 * r + 1] = true;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < PROBE_KPT; ++q) {
-        const uint64_t e = tbase + (uint64_t)q * THREADS + tid;
-        valid[q] = e < np;
-        key[q] = valid[q] ? ld_stream1(pk + e) : 0ull;
-      }
-    }
+    load_tile<THREADS>(pk, np, tbase, vec, key, valid);
 
     using val_t = typename std::conditional<NARROW, uint32_t, unsigned long long>::type;
     val_t val[PROBE_KPT];
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      // batch of 4 lookups: issue all home-bucket sector loads before resolving any (MLP)
       uint32_t b[4];
       bool need[4];
       unsigned long long s[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int q = half * 4 + j;
-        const unsigned long long k = key[q];
-        const uint32_t h = hash32(k);
-        b[j] = reduce32(h, nbuckets);
+        b[j] = reduce32(hash32(key[q]), nbuckets);
         bool go = valid[q];
-        if (NARROW) go = go && ((k >> 32) == 0);  // a key >= 2^32 cannot be in a packed table
-        else go = go && (k != EMPTY64);
-        if (BLOOM != 0 && go) {
-          const uint32_t m = bloom_mask(h);
-          const uint32_t wi = bloom_word(h, bloom_words);
+        if (BLOOM != 0) {
+          const uint32_t x = bloom_hash(key[q]);
+          const uint32_t wi = bloom_word(x, bloom_words);
           const uint32_t w = (BLOOM == 1) ? sbloom[wi] : __ldg(bloom + wi);
-          go = (w & m) == m;
+          const uint32_t m = bloom_mask(x);
+          go = go & ((w & m) == m);
         }
         need[j] = go;
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = EMPTY64;
         if (go) ld_sector(slots + (size_t)b[j] * 4, s[j][0], s[j][1], s[j][2], s[j][3]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int q = half * 4 + j;
-        bool hit = false;
-        unsigned long long v = 0;
-        if (need[j]) hit = probe_resolve<NARROW>(key[q], b[j], s[j][0], s[j][1], s[j][2], s[j][3], slots, nbuckets, v);
+        unsigned long long v;
+        bool hit = need[j] & probe_home<NARROW>(key[q], b[j], s[j][0], s[j][1], s[j][2], s[j][3], slots, nbuckets, v);
         if (!NARROW && valid[q] && key[q] == EMPTY64 && sent_present) { hit = true; v = sent_value; }
         val[q] = (val_t)v;
         if (hit) hitmask |= 1u << q;
       }
     }
 
-    if (!MAT) {
-      local_count += __popc(hitmask);
-    } else {
-      // compaction: per (warp, q) ballot -> block scan of WARPS*KPT counts -> one cursor bump per tile
-      uint32_t rank[PROBE_KPT];
+    uint32_t rank[PROBE_KPT];
 #pragma unroll
-      for (int q = 0; q < PROBE_KPT; ++q) {
-        const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> q) & 1u);
-        rank[q] = __popc(bal & lanemask_lt());
-        if (lane == 0) s_wcnt[warp * PROBE_KPT + q] = __popc(bal);
-      }
-      __syncthreads();
-      if (warp == 0) {
-        constexpr int PER = (WARPS * PROBE_KPT + 31) / 32;
-        uint32_t c[PER];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-          const int e = lane * PER + u;
-          c[u] = e < WARPS * PROBE_KPT ? s_wcnt[e] : 0u;
-          sum += c[u];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
-        }
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-          const int e = lane * PER + u;
-          if (e < WARPS * PROBE_KPT) s_wcnt[e] = run;
-          run += c[u];
-        }
-        if (lane == 31) {
-          s_base = incl ? atomicAdd(&ctl->out_cursor, (unsigned long long)incl) : 0ull;
-          local_count += incl;  // counted once per tile by this lane
-        }
-      }
-      __syncthreads();
-      const unsigned long long base = s_base;
-#pragma unroll
-      for (int q = 0; q < PROBE_KPT; ++q) {
-        if ((hitmask >> q) & 1u) {
-          const unsigned long long pos = base + s_wcnt[warp * PROBE_KPT + q] + rank[q];
-          st_stream(out_keys + pos, key[q]);
-          st_stream(out_vals + pos, (unsigned long long)val[q]);
-          if (IDX) {
-            const uint64_t row = vec ? tbase + 2ull * ((uint64_t)(q >> 1) * THREADS + tid) + (q & 1)
-                                     : tbase + (uint64_t)q * THREADS + tid;
-            st_stream(out_idx + pos, idx_base + row);
-          }
-        }
-      }
-      __syncthreads();  // s_wcnt / s_base are reused by the next tile
+    for (int q = 0; q < PROBE_KPT; ++q) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> q) & 1u);
+      rank[q] = __popc(bal & lanemask_lt());
+      if (lane == 0) s_wcnt[warp * PROBE_KPT + q] = __popc(bal);
     }
+    __syncthreads();
+    if (warp == 0) {
+      constexpr int PER = (WARPS * PROBE_KPT + 31) / 32;
+      uint32_t c[PER];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int e = lane * PER + u;
+        c[u] = e < WARPS * PROBE_KPT ? s_wcnt[e] : 0u;
+        sum += c[u];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int e = lane * PER + u;
+        if (e < WARPS * PROBE_KPT) s_wcnt[e] = run;
+        run += c[u];
+      }
+      if (lane == 31) {
+        s_base = incl ? atomicAdd(&ctl->out_cursor, (unsigned long long)incl) : 0ull;
+        local_count += incl;  // counted once per tile by this lane
+      }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+#pragma unroll
+    for (int q = 0; q < PROBE_KPT; ++q) {
+      if ((hitmask >> q) & 1u) {
+        const unsigned long long pos = base + s_wcnt[warp * PROBE_KPT + q] + rank[q];
+        st_stream(out_keys + pos, key[q]);
+        st_stream(out_vals + pos, (unsigned long long)val[q]);
+        if (IDX) {
+          const uint64_t row = vec ? tbase + 2ull * ((uint64_t)(q >> 1) * THREADS + tid) + (q & 1)
+                                   : tbase + (uint64_t)q * THREADS + tid;
+          st_stream(out_idx + pos, idx_base + row);
+        }
+      }
+    }
+    __syncthreads();  // s_wcnt / s_base are reused by the next tile
   }
-
-  // one atomic per warp for the match count
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
   if (lane == 0 && local_count) atomicAdd(&ctl->match_count, local_count);
 }
 
 size_t probe_smem_bloom_limit_words(const DeviceInfo& di) {
-  // leave 4 KB for the kernel's static shared memory
-  const size_t bytes = di.smem_optin > 8192 ? di.smem_optin - 4096 : 0;
+  // the count kernel runs 32 warps next to the filter: leave room for their survivor queues (16 KB)
+  // and the kernel's static shared memory
+  const size_t reserve = (size_t)32 * PROBE_QCAP * 8 + 4096;
+  const size_t bytes = di.smem_optin > reserve + 4096 ? di.smem_optin - reserve : 0;
   return (bytes / 16) * 4;
 }
 
-template <bool NARROW, int BLOOM, bool MAT, bool IDX, int THREADS>
-static void launch_probe_inst(const TableView& t, const unsigned long long* pk, uint64_t np,
-                              const unsigned long long* bv, const ProbeOut* out, int ctas_per_sm, Ctl* ctl,
+template <class K>
+static uint64_t persistent_grid(K kern, int threads, size_t smem, uint64_t ntiles, int ctas_per_sm, const DeviceInfo& di) {
+  if (ctas_per_sm <= 0) {  // auto: fill every SM to the kernel's occupancy limit
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    ctas_per_sm = occ;
+  }
+  uint64_t grid = (uint64_t)di.sms * ctas_per_sm;
+  return grid > ntiles ? ntiles : grid;
+}
+
+template <bool NARROW, int BLOOM, int THREADS>
+static void launch_count_inst(const TableView& t, const unsigned long long* pk, uint64_t np, int ctas_per_sm, Ctl* ctl,
                               const DeviceInfo& di, cudaStream_t st) {
-  auto kern = k_probe<NARROW, BLOOM, MAT, IDX, THREADS>;
+  auto kern = k_probe_count<NARROW, BLOOM, THREADS>;
+  size_t smem = 0;
+  if (BLOOM == 1) smem += (size_t)t.bloom_words * 4;
+  smem += (size_t)(THREADS / 32) * PROBE_QCAP * 8;
+  if (smem) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
+  const uint64_t grid = persistent_grid(kern, THREADS, smem, (np + tile - 1) / tile, BLOOM == 1 ? 0 : ctas_per_sm, di);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(pk, np, t.slots, t.nbuckets, t.bloom, t.bloom_words, ctl, vec_ok);
+}
+
+template <bool NARROW, int BLOOM, bool IDX, int THREADS>
+static void launch_mat_inst(const TableView& t, const unsigned long long* pk, uint64_t np, const unsigned long long* bv,
+                            const ProbeOut* out, int ctas_per_sm, Ctl* ctl, const DeviceInfo& di, cudaStream_t st) {
+  auto kern = k_probe_mat<NARROW, BLOOM, IDX, THREADS>;
   size_t smem = 0;
   if (BLOOM == 1) {
     smem = (size_t)t.bloom_words * 4;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ctas_per_sm = 1;
-  }
-  if (ctas_per_sm <= 0 || BLOOM == 1) {  // auto: fill every SM to the kernel's occupancy limit
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
-    ctas_per_sm = occ;
   }
   const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
-  const uint64_t ntiles = (np + tile - 1) / tile;
-  uint64_t grid = (uint64_t)di.sms * ctas_per_sm;
-  if (grid > ntiles) grid = ntiles;
+  const uint64_t grid = persistent_grid(kern, THREADS, smem, (np + tile - 1) / tile, BLOOM == 1 ? 0 : ctas_per_sm, di);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(pk, np, t.slots, t.nbuckets, t.bloom, t.bloom_words, bv, ctl,
-                                             out ? out->keys : nullptr, out ? out->vals : nullptr,
-                                             out ? out->idx : nullptr, out ? out->idx_base : 0ull, vec_ok);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(pk, np, t.slots, t.nbuckets, t.bloom, t.bloom_words, bv, ctl, out->keys,
+                                             out->vals, out->idx, out->idx_base, vec_ok);
 }
 
 void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np, const unsigned long long* bv,
@@ -386,24 +568,26 @@ void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np,
   const int bloom = t.bloom == nullptr ? 0 : (bloom_in_smem ? 1 : 2);
   const bool mat = out != nullptr;
   const bool idx = mat && out->idx != nullptr;
-#define FJ_PROBE(N, B, M, I, T) launch_probe_inst<N, B, M, I, T>(t, pk, np, bv, out, ctas_per_sm, ctl, di, st)
-#define FJ_PROBE_B(N, M, I)                               \
-  do {                                                    \
-    if (bloom == 0) FJ_PROBE(N, 0, M, I, (M ? 256 : 512));            \
-    else if (bloom == 1) FJ_PROBE(N, 1, M, I, (M ? 512 : 1024));      \
-    else FJ_PROBE(N, 2, M, I, (M ? 256 : 512));                       \
+  if (!mat) {
+#define FJ_CNT(N)                                                                       \
+  do {                                                                                  \
+    if (bloom == 0) launch_count_inst<N, 0, 512>(t, pk, np, ctas_per_sm, ctl, di, st);  \
+    else if (bloom == 1) launch_count_inst<N, 1, 1024>(t, pk, np, ctas_per_sm, ctl, di, st); \
+    else launch_count_inst<N, 2, 512>(t, pk, np, ctas_per_sm, ctl, di, st);             \
   } while (0)
-  if (t.narrow) {
-    if (!mat) FJ_PROBE_B(true, false, false);
-    else if (!idx) FJ_PROBE_B(true, true, false);
-    else FJ_PROBE_B(true, true, true);
+    if (t.narrow) FJ_CNT(true); else FJ_CNT(false);
+#undef FJ_CNT
   } else {
-    if (!mat) FJ_PROBE_B(false, false, false);
-    else if (!idx) FJ_PROBE_B(false, true, false);
-    else FJ_PROBE_B(false, true, true);
+#define FJ_MAT(N, I)                                                                               \
+  do {                                                                                             \
+    if (bloom == 0) launch_mat_inst<N, 0, I, 256>(t, pk, np, bv, out, ctas_per_sm, ctl, di, st);   \
+    else if (bloom == 1) launch_mat_inst<N, 1, I, 512>(t, pk, np, bv, out, ctas_per_sm, ctl, di, st); \
+    else launch_mat_inst<N, 2, I, 256>(t, pk, np, bv, out, ctas_per_sm, ctl, di, st);              \
+  } while (0)
+    if (t.narrow) { if (idx) FJ_MAT(true, true); else FJ_MAT(true, false); }
+    else { if (idx) FJ_MAT(false, true); else FJ_MAT(false, false); }
+#undef FJ_MAT
   }
-#undef FJ_PROBE_B
-#undef FJ_PROBE
   ++*launches;
 }
 
