@@ -60,8 +60,9 @@ struct ScatterArgs {
   void* out = nullptr;
   uint32_t* out_cursor = nullptr;
   uint64_t out_cap = 0;
-  int shift = 0;      // digit = (hash32(key) >> shift) & (fan - 1)
-  uint32_t fan = 1;   // power of two, <= 512
+  int shift = 0;      // >= 0: digit = (hash32(key) >> shift) & (fan - 1), fan a power of two
+                      // < 0 : shuffle destination = ((hash32(key) & 0xffff) * fan) >> 16, any fan
+  uint32_t fan = 1;   // <= 512
   Ctl* ctl = nullptr;
 };
 struct JoinArgs {
@@ -86,6 +87,14 @@ void launch_scatter(bool build, bool narrow, int stage, const ScatterArgs& a, co
 void launch_join(bool narrow, bool mat, const JoinArgs& a, cudaStream_t st, int* launches);
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
                           unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
+
+void launch_emit_sentinel_value(Ctl* ctl, unsigned long long value, unsigned long long n, unsigned long long* out_keys,
+                                unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
+// partition-element rows (radix_elem_bytes format) -> raw 64-bit columns
+void launch_expand(bool build, bool narrow, const void* in, uint64_t n, unsigned long long* keys, unsigned long long* vals,
+                   const DeviceInfo& di, cudaStream_t st, int* launches);
+// destination digit of a key in the multi-GPU shuffle (host mirror of the device function)
+uint32_t shuffle_dest_host(uint64_t key, uint32_t fan);
 
 // ---------------------------------------------------------------- synthetic data + utilities
 void launch_generate_g2(int side, uint64_t ny, uint64_t c, uint64_t U, uint64_t a_mod_u, uint64_t b, uint64_t seed,

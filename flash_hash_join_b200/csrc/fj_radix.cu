@@ -72,6 +72,15 @@ __device__ __forceinline__ uint32_t block_excl_scan_512(uint32_t v, uint32_t* s_
   return pre + incl - v;
 }
 
+// digit of one row.  shift >= 0: radix digit = `fan` (power of two) hash bits starting at `shift` (top bits
+// first, so consecutive passes refine a partition).  shift < 0: DESTINATION mode of the multi-GPU shuffle —
+// the low 16 hash bits range-reduced to [0, fan), fan arbitrary (<= 512): independent of the top bits that
+// the local radix passes and the table index consume afterwards.
+__host__ __device__ __forceinline__ uint32_t scatter_digit(uint32_t h, int shift, uint32_t fan) {
+  return shift >= 0 ? (h >> shift) & (fan - 1) : ((h & 0xffffu) * fan) >> 16;
+}
+uint32_t shuffle_dest_host(uint64_t key, uint32_t fan) { return scatter_digit(hash32(key), -1, fan); }
+
 // STAGE 1: input = raw 64-bit columns (keys[, vals]); STAGE 2: input = stage-1 partitions.
 template <bool BUILD, bool NARROW, int STAGE>
 __global__ void __launch_bounds__(SC_THREADS, 2)
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
           k = E::key(elem[i]);
         }
         if (ok) {
-          const uint32_t d = (hash32(k) >> shift) & (fan - 1);
+          const uint32_t d = scatter_digit(hash32(k), shift, fan);
           const uint32_t r = atomicAdd(&s_hist[d], 1u);
           dr[i] = (d << 16) | r;
         }
@@ -486,6 +495,57 @@ __global__ void __launch_bounds__(1024) k_emit_sentinel(Ctl* __restrict__ ctl, c
     out_vals[s_base + i] = v;
   }
 }
+// out-of-band key joined with an explicit (value, probe count): the multi-GPU shuffle resolves the key's
+// build row across ranks on the host
+__global__ void __launch_bounds__(1024) k_emit_sentinel_value(Ctl* __restrict__ ctl, unsigned long long value,
+                                                              unsigned long long n, unsigned long long* __restrict__ out_keys,
+                                                              unsigned long long* __restrict__ out_vals, int mat) {
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) {
+    atomicAdd(&ctl->match_count, n);
+    s_base = mat ? atomicAdd(&ctl->out_cursor, n) : 0ull;
+  }
+  __syncthreads();
+  if (!mat) return;
+  for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+    out_keys[s_base + i] = EMPTY64;
+    out_vals[s_base + i] = value;
+  }
+}
+void launch_emit_sentinel_value(Ctl* ctl, unsigned long long value, unsigned long long n, unsigned long long* out_keys,
+                                unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches) {
+  if (n == 0) return;
+  k_emit_sentinel_value<<<1, 1024, 0, st>>>(ctl, value, n, out_keys, out_vals, mat ? 1 : 0);
+  ++*launches;
+}
+
+// partition-element rows -> raw 64-bit columns (fallback of the shuffle path onto the global-table join)
+template <bool BUILD, bool NARROW>
+__global__ void __launch_bounds__(256) k_expand(const typename Elem<BUILD, NARROW>::T* __restrict__ in, uint64_t n,
+                                                unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const typename Elem<BUILD, NARROW>::T e = in[i];
+    keys[i] = Elem<BUILD, NARROW>::key(e);
+    if constexpr (BUILD) {
+      if constexpr (NARROW) vals[i] = e & 0xffffffffull;
+      else vals[i] = e.y;
+    }
+  }
+}
+void launch_expand(bool build, bool narrow, const void* in, uint64_t n, unsigned long long* keys, unsigned long long* vals,
+                   const DeviceInfo& di, cudaStream_t st, int* launches) {
+  if (n == 0) return;
+  uint64_t want = (n + 255) / 256;
+  const uint64_t cap = (uint64_t)di.sms * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+#define FJ_EX(B, N) k_expand<B, N><<<grid, 256, 0, st>>>(reinterpret_cast<const typename Elem<B, N>::T*>(in), n, keys, vals)
+  if (build) { if (narrow) FJ_EX(true, true); else FJ_EX(true, false); }
+  else { if (narrow) FJ_EX(false, true); else FJ_EX(false, false); }
+#undef FJ_EX
+  ++*launches;
+}
+
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
                           unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches) {
   k_emit_sentinel<<<1, 1024, 0, st>>>(ctl, bv, out_keys, out_vals, mat ? 1 : 0);

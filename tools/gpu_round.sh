@@ -1,0 +1,51 @@
+#!/usr/bin/env bash
+# tools/gpu_round.sh <tag> [steps...] — one gpurun call's worth of work; everything lands in gpurun_out/<tag>/.
+# steps: tests quick bench ref launches ncu_c2 ncu_c3 sanitize   (default: all but sanitize)
+set -u
+TAG=${1:-r1}
+shift || true
+STEPS=${*:-tests quick bench ref launches ncu_c2 ncu_c3}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+export FJ_OUT=$OUT
+has() { [[ " $STEPS " == *" $1 "* ]]; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,memory.total,power.limit --format=csv > "$OUT/gpu.txt" 2>&1
+nproc > "$OUT/host_cores.txt"; free -g >> "$OUT/host_cores.txt"
+
+if has tests; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
+  echo "pytest exit $?" >> "$OUT/pytest_gpu.log"
+  tail -5 "$OUT/pytest_gpu.log"
+fi
+if has quick; then
+  timeout 900 python tools/quick_bench.py C2 C3 --reps 5 > "$OUT/quick_bench.jsonl" 2> "$OUT/quick_bench.err"
+  cat "$OUT/quick_bench.jsonl"
+fi
+if has bench; then
+  timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"
+  cat "$OUT/bench.json"
+fi
+if has ref; then
+  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
+  cat "$OUT/bench_ref.json"
+fi
+if has launches; then
+  # launch list of the bench command itself (times under ncu are cold-cache/serialised: shares only)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_bench.csv" \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > "$OUT/launches_bench.log" 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$OUT/launches_c3.csv" \
+    python tools/prof_case.py C3 radix mat --reps 2 > "$OUT/launches_c3.log" 2>&1
+fi
+if has ncu_c2; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_probe -s 2 -c 1 -f -o "$OUT/c2_probe" \
+    python tools/prof_case.py C2 scalar count bloom --reps 4 > "$OUT/ncu_c2.log" 2>&1
+fi
+if has ncu_c3; then
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_scatter|k_join' -s 6 -c 6 -f -o "$OUT/c3_radix" \
+    python tools/prof_case.py C3 radix mat --reps 3 > "$OUT/ncu_c3.log" 2>&1
+fi
+if has sanitize; then
+  timeout 900 compute-sanitizer --tool memcheck python tools/prof_case.py S scalar mat bloom --reps 1 > "$OUT/memcheck.log" 2>&1
+  timeout 900 compute-sanitizer --tool racecheck python tools/prof_case.py S radix mat --reps 1 > "$OUT/racecheck.log" 2>&1
+fi
+ls -la "$OUT"
