@@ -82,6 +82,7 @@ struct RadixPlan {
   uint32_t P = 0, F1 = 0, F2 = 0;
   uint64_t cap1_b = 0, cap1_p = 0, cap2_b = 0, cap2_p = 0;
   uint32_t smax = 0, tcap = 0, chunk = 16384, max_chunks = 1;
+  bool join3 = false;  // packed rows, two passes: collision-free pipelined k_join3, else k_join
 };
 
 static uint64_t round4(uint64_t x) { return (x + 3) & ~uint64_t(3); }
@@ -118,6 +119,7 @@ struct Engine {
     cfg["smem_bloom"] = 1;
     cfg["probe_ctas_per_sm"] = 0;  // 0 = occupancy-derived
     cfg["narrow"] = 1;
+    cfg["join3"] = 1;  // packed rows, two radix passes: collision-free pipelined k_join3 (0 = k_join)
     cfg["chunk_rows"] = 1 << 24;
   }
 
@@ -203,6 +205,12 @@ void Engine::shutdown() {
 }
 
 // ---- planning ----------------------------------------------------------------------------------
+// holes that k_scatter2's 16-byte run padding adds to one output partition fed by `ntiles` input tiles:
+// each (tile, partition) run is padded by 0..pad_rows rows, (pad_rows / 2) on average
+static uint64_t pad_allow(uint64_t ntiles, uint32_t pad_rows) {
+  return pad_rows ? (uint64_t)(0.6 * pad_rows * (double)ntiles) + 16 : 0;
+}
+
 RadixPlan Engine::plan_radix(uint64_t nb, uint64_t np, bool narrow) const {
   RadixPlan pl;
   pl.narrow = narrow;
@@ -213,29 +221,52 @@ RadixPlan Engine::plan_radix(uint64_t nb, uint64_t np, bool narrow) const {
   if (smax_limit > 65532) smax_limit = 65532;  // tuple index + 1 must fit 16 bits
   const int64_t user = cfg.at("radix_sub_rows");
   if (user > 0 && (uint64_t)user < smax_limit) smax_limit = std::max<uint64_t>(64, (uint64_t)user & ~uint64_t(3));
-  uint64_t P = 16;
-  while (cap_build(nb, P) > smax_limit && P < (1u << 18)) P <<= 1;
-  if (cap_build(nb, P) > smax_limit) return pl;  // too large for two passes: not applicable
-  pl.P = (uint32_t)P;
-  int B = 0;
-  while ((1ull << B) < P) ++B;
-  pl.bits = B;
-  if (B <= 8) { pl.bits1 = B; pl.bits2 = 0; }
-  else { pl.bits1 = (B + 1) / 2; pl.bits2 = B - pl.bits1; }
-  pl.F1 = 1u << pl.bits1;
-  pl.F2 = 1u << pl.bits2;
-  pl.cap2_b = cap_build(nb, P);
-  pl.cap2_p = cap_probe(np, P);
-  pl.cap1_b = pl.bits2 ? cap_build(nb, pl.F1) + 32 : 0;
-  pl.cap1_p = pl.bits2 ? cap_probe(np, pl.F1) : 0;
-  pl.smax = (uint32_t)pl.cap2_b;
-  pl.tcap = pl.smax * 2;
-  pl.chunk = 16384;
-  pl.max_chunks = (uint32_t)((pl.cap2_p + pl.chunk - 1) / pl.chunk);
-  if (pl.max_chunks == 0) pl.max_chunks = 1;
-  if ((uint64_t)pl.P * pl.max_chunks > 0x7fffffffull) return pl;
-  pl.ok = true;
-  return pl;
+  const bool allow3 = narrow && cfg.at("join3") != 0;
+  const uint32_t tile_b = scatter_tile_rows(true, narrow), tile_p = scatter_tile_rows(false, narrow);
+  const uint32_t pad_b = scatter_pad_rows(true, narrow), pad_p = scatter_pad_rows(false, narrow);
+  for (int B = 4; B <= 18; ++B) {
+    const uint64_t P = 1ull << B;
+    RadixPlan c;
+    c.narrow = narrow;
+    c.bits = B;
+    if (B <= 8) { c.bits1 = B; c.bits2 = 0; }
+    else { c.bits1 = (B + 1) / 2; c.bits2 = B - c.bits1; }
+    // packed rows that need two passes anyway go to k_join3, which wants >= 2^14 partitions (its bitmap
+    // covers the 32 - B hash bits the passes did not consume)
+    const bool j3 = allow3 && c.bits2 > 0;
+    if (j3 && 32 - B > 18) continue;
+    c.P = (uint32_t)P;
+    c.F1 = 1u << c.bits1;
+    c.F2 = 1u << c.bits2;
+    if (c.bits2) {
+      c.cap1_b = round4(cap_build(nb, c.F1) + 32 + pad_allow(nb / tile_b + 1, pad_b));
+      c.cap1_p = round4(cap_probe(np, c.F1) + pad_allow(np / tile_p + 1, pad_p));
+      c.cap2_b = round4(cap_build(nb, P) + pad_allow(c.cap1_b / tile_b + 1, pad_b));
+      c.cap2_p = round4(cap_probe(np, P) + pad_allow(c.cap1_p / tile_p + 1, pad_p));
+    } else {
+      c.cap2_b = round4(cap_build(nb, P) + pad_allow(nb / tile_b + 1, pad_b));
+      c.cap2_p = round4(cap_probe(np, P) + pad_allow(np / tile_p + 1, pad_p));
+    }
+    c.smax = (uint32_t)std::min<uint64_t>(c.cap2_b, 0xffffffffu);
+    c.join3 = j3;
+    if (j3) {
+      uint64_t lim = join3_max_build_rows();
+      if (user > 0 && (uint64_t)user < lim) lim = std::max<uint64_t>(64, (uint64_t)user & ~uint64_t(3));
+      if (c.cap2_b > lim || join3_smem_bytes(c.smax, 32 - B) + 1024 > budget) continue;
+      c.tcap = 0;
+      c.chunk = join3_probe_chunk();
+    } else {
+      if (c.cap2_b > smax_limit) continue;
+      c.tcap = c.smax * 2;
+      c.chunk = 16384;
+    }
+    c.max_chunks = (uint32_t)((c.cap2_p + c.chunk - 1) / c.chunk);
+    if (c.max_chunks == 0) c.max_chunks = 1;
+    if ((uint64_t)c.P * c.max_chunks > 0x7fffffffull) break;
+    c.ok = true;
+    return c;
+  }
+  return pl;  // too large for two passes: not applicable
 }
 
 int Engine::choose_path(int algo, unsigned flags, uint64_t nb, bool narrow_guess, const RadixPlan& plan) const {
@@ -395,7 +426,8 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   j.ctl = d_ctl;
   j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
   j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
-  launch_join(pl.narrow, mat, j, st, &launches);
+  if (pl.join3) launch_join3(mat, j, 32 - pl.bits, di, st, &launches);
+  else launch_join(pl.narrow, mat, j, st, &launches);
   if (!pl.narrow) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));

@@ -50,12 +50,14 @@ struct ScatterArgs {
   const unsigned long long* in_keys = nullptr;
   const unsigned long long* in_vals = nullptr;
   uint64_t n = 0;
+  uint64_t row_base = 0;  // index of in_keys[0] in the caller's column (for Ctl::sentinel_row)
   // stage 2 input: the fixed-capacity partitions written by stage 1
   const void* in_part = nullptr;
   const uint32_t* in_counts = nullptr;
   uint32_t in_nparts = 0;
   uint64_t in_cap = 0;
   uint64_t n_upper = 0;  // upper bound on the rows stage 2 will see (for grid sizing)
+  bool merge = false;    // stage 2: output partition = digit only (input partitions are merged, not refined)
   // output partitions: partition p occupies [p*out_cap, p*out_cap + cursor[p])
   void* out = nullptr;
   uint32_t* out_cursor = nullptr;
@@ -82,17 +84,28 @@ struct JoinArgs {
   unsigned long long* out_vals = nullptr;
 };
 size_t radix_elem_bytes(bool build, bool narrow);
+uint32_t scatter_tile_rows(bool build, bool narrow);  // rows per tile of the pipelined scatter
+uint32_t scatter_pad_rows(bool build, bool narrow);   // max holes per (tile, partition) run
 void launch_scatter(bool build, bool narrow, int stage, const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st,
                     int* launches);
 void launch_join(bool narrow, bool mat, const JoinArgs& a, cudaStream_t st, int* launches);
+// collision-free pipelined join of packed (narrow) partitions (bitmap + rank directory over the 32 - bits
+// hash bits the radix passes did not consume).  JoinArgs::tcap / ::chunk are ignored; ::max_chunks =
+// ceil(cap_p / join3_probe_chunk()); requires join3_min_rbits() <= rbits and smax <= join3_max_build_rows()
+void launch_join3(bool mat, const JoinArgs& a, int rbits, const DeviceInfo& di, cudaStream_t st, int* launches);
+size_t join3_smem_bytes(uint32_t smax, int rbits);
+uint32_t join3_probe_chunk();
+uint32_t join3_max_build_rows();
+int join3_min_rbits();
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
                           unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
 
 void launch_emit_sentinel_value(Ctl* ctl, unsigned long long value, unsigned long long n, unsigned long long* out_keys,
                                 unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
-// partition-element rows (radix_elem_bytes format) -> raw 64-bit columns
+// partition-element rows (radix_elem_bytes format) -> raw 64-bit columns, holes dropped; *cursor (zeroed by the
+// caller) receives the number of rows written
 void launch_expand(bool build, bool narrow, const void* in, uint64_t n, unsigned long long* keys, unsigned long long* vals,
-                   const DeviceInfo& di, cudaStream_t st, int* launches);
+                   unsigned long long* cursor, const DeviceInfo& di, cudaStream_t st, int* launches);
 // destination digit of a key in the multi-GPU shuffle (host mirror of the device function)
 uint32_t shuffle_dest_host(uint64_t key, uint32_t fan);
 

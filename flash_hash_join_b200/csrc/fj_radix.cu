@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
               const typename Elem<BUILD, NARROW>::T* __restrict__ in_part,  // stage 2
               const uint32_t* __restrict__ in_counts, uint32_t in_nparts, uint64_t in_cap,
               typename Elem<BUILD, NARROW>::T* __restrict__ out, uint32_t* __restrict__ out_cursor, uint64_t out_cap,
-              int shift, uint32_t fan, Ctl* __restrict__ ctl) {
+              int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base) {
   using E = Elem<BUILD, NARROW>;
   using T = typename E::T;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
               if (!narrow_ok(k, v)) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
               elem[i] = packed;
             } else {
-              if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(in_base + e)); ok = false; }
+              if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(row_base + in_base + e)); ok = false; }
               elem[i].x = k; elem[i].y = v;
             }
           } else {
@@ -252,25 +252,340 @@ static void launch_scatter_inst(const ScatterArgs& a, const DeviceInfo& di, cuda
   if (grid == 0) return;
   kern<<<(unsigned)grid, SC_THREADS, smem, st>>>(a.in_keys, a.in_vals, a.n, reinterpret_cast<const T*>(a.in_part),
                                                  a.in_counts, a.in_nparts, a.in_cap, reinterpret_cast<T*>(a.out),
-                                                 a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl);
-}
-
-void launch_scatter(bool build, bool narrow, int stage, const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st,
-                    int* launches) {
-#define FJ_SC(B, N)                                               \
-  do {                                                            \
-    if (stage == 1) launch_scatter_inst<B, N, 1>(a, di, st);      \
-    else launch_scatter_inst<B, N, 2>(a, di, st);                 \
-  } while (0)
-  if (build) { if (narrow) FJ_SC(true, true); else FJ_SC(true, false); }
-  else { if (narrow) FJ_SC(false, true); else FJ_SC(false, false); }
-#undef FJ_SC
-  ++*launches;
+                                                 a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl, a.row_base);
 }
 
 size_t radix_elem_bytes(bool build, bool narrow) {
   return build ? (narrow ? 8 : 16) : (narrow ? 4 : 8);
 }
+
+// ================================================================================= scatter, TMA pipelined
+// k_scatter2: the production partition kernel.  Everything that touches HBM is asynchronous:
+//   in : cp.async.bulk global -> shared into a 2-deep ring of input tiles, completion on an mbarrier;
+//        the copy of tile t+2 is issued as soon as tile t has been consumed
+//   out: every (tile, partition) run is ONE cp.async.bulk shared -> global from a double-buffered staging
+//        area in which the tile has been regrouped by partition.  Bulk stores need 16-byte aligned
+//        runs, so a run is padded to a multiple of 16 bytes with all-ones elements ("holes"; an
+//        all-ones element can never be a row — see Elem below) and reservations are made in
+//        padded units.  Consumers (the next scatter pass, k_join, k_expand) skip holes.
+// The threads only ever touch shared memory: LDS row -> hash -> ATOMS rank -> STS staged element.
+// Tile size = 16 KB of OUTPUT rows (4096 / 2048 / 1024 rows for 4 / 8 / 16-byte elements); two CTAs per SM.
+constexpr int S2_THREADS = 512;
+constexpr int S2_STAGING = 16384;  // bytes per staging buffer
+constexpr int S2_FMAX = 512;
+
+template <bool BUILD, bool NARROW> struct Hole;
+template <> struct Hole<true, true> {
+  static __device__ __forceinline__ unsigned long long make() { return EMPTY64; }
+  static __device__ __forceinline__ bool is(unsigned long long e) { return (uint32_t)(e >> 32) == 0xFFFFFFFFu; }
+};
+template <> struct Hole<true, false> {  // 16-byte elements never need padding; the out-of-band key never enters
+  static __device__ __forceinline__ ulonglong2 make() { return make_ulonglong2(EMPTY64, EMPTY64); }
+  static __device__ __forceinline__ bool is(const ulonglong2& e) { return e.x == EMPTY64; }
+};
+template <> struct Hole<false, true> {
+  static __device__ __forceinline__ uint32_t make() { return 0xFFFFFFFFu; }
+  static __device__ __forceinline__ bool is(uint32_t e) { return e == 0xFFFFFFFFu; }
+};
+template <> struct Hole<false, false> {
+  static __device__ __forceinline__ unsigned long long make() { return EMPTY64; }
+  static __device__ __forceinline__ bool is(unsigned long long e) { return e == EMPTY64; }
+};
+
+template <bool BUILD, bool NARROW, int STAGE>
+__global__ void __launch_bounds__(S2_THREADS, 2)
+    k_scatter2(const unsigned long long* __restrict__ in_keys, const unsigned long long* __restrict__ in_vals,
+               uint64_t n_tiles1,                                            // stage 1: number of FULL tiles
+               const typename Elem<BUILD, NARROW>::T* __restrict__ in_part,  // stage 2
+               const uint32_t* __restrict__ in_counts, uint32_t in_nparts, uint64_t in_cap, int merge,
+               typename Elem<BUILD, NARROW>::T* __restrict__ out, uint32_t* __restrict__ out_cursor, uint64_t out_cap,
+               int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base, uint32_t stg_elems) {
+  using E = Elem<BUILD, NARROW>;
+  using T = typename E::T;
+  using H = Hole<BUILD, NARROW>;
+  constexpr int TILE = S2_STAGING / (int)sizeof(T);
+  constexpr int IPT = TILE / S2_THREADS;
+  constexpr int PADN = 16 / (int)sizeof(T) > 1 ? 16 / (int)sizeof(T) : 1;
+  constexpr int IN_ROW = STAGE == 1 ? (BUILD ? 16 : 8) : (int)sizeof(T);
+  constexpr int RING = TILE * IN_ROW;  // bytes per ring stage
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;
+  T* staging = reinterpret_cast<T*>(smem_raw + 2 * RING);
+  __shared__ uint32_t s_hist[S2_FMAX];      // rows per digit of the current tile
+  __shared__ uint32_t s_cnt[S2_FMAX];       // copy of s_hist taken by the scan
+  __shared__ uint32_t s_off[S2_FMAX];       // staging offset of the digit's (padded) run
+  __shared__ uint32_t s_tpref[S2_FMAX + 1];
+  __shared__ uint32_t s_warp[S2_THREADS / 32];
+  __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ unsigned long long s_tbase[2];  // per ring stage: input offset (elements) of the tile in flight
+  __shared__ uint32_t s_tcount[2], s_tp1[2];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint64_t ntiles;
+  if (STAGE == 1) {
+    ntiles = n_tiles1;
+  } else {
+    uint32_t t = 0;
+    if (tid < (int)in_nparts) {
+      uint64_t c = in_counts[tid];
+      if (c > in_cap) c = in_cap;
+      t = (uint32_t)((c + TILE - 1) / TILE);
+    }
+    uint32_t total;
+    const uint32_t pre = block_excl_scan_512(t, s_warp, total);
+    if (tid < (int)in_nparts) s_tpref[tid] = pre;
+    if (tid == 0) s_tpref[in_nparts] = total;
+    __syncthreads();
+    ntiles = total;
+  }
+  if (tid < S2_FMAX) s_hist[tid] = 0;
+
+  // producer (thread 0): locate tile -> (input offset, rows, source partition), publish it for the consumers
+  // and bulk-copy the tile into ring stage s
+  auto issue = [&](uint64_t tile, int s) {
+    uint64_t in_base;
+    uint32_t count, p1 = 0;
+    if (STAGE == 1) {
+      in_base = tile * TILE;
+      count = TILE;
+    } else {
+      uint32_t lo = 0, hi = in_nparts;  // largest p with s_tpref[p] <= tile
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_tpref[mid] <= (uint32_t)tile) lo = mid; else hi = mid;
+      }
+      p1 = lo;
+      uint64_t c = in_counts[p1];
+      if (c > in_cap) c = in_cap;
+      const uint64_t within = (tile - s_tpref[p1]) * (uint64_t)TILE;
+      in_base = (uint64_t)p1 * in_cap + within;
+      count = (uint32_t)((c - within) < (uint64_t)TILE ? (c - within) : TILE);
+    }
+    s_tbase[s] = in_base;
+    s_tcount[s] = count;
+    s_tp1[s] = p1;
+    unsigned char* dst = ring + s * RING;
+    if (STAGE == 1) {
+      if (BUILD) {
+        mbar_expect_tx(&s_full[s], 2u * TILE * 8u);
+        bulk_g2s(dst, in_keys + in_base, TILE * 8u, &s_full[s]);
+        bulk_g2s(dst + TILE * 8, in_vals + in_base, TILE * 8u, &s_full[s]);
+      } else {
+        mbar_expect_tx(&s_full[s], TILE * 8u);
+        bulk_g2s(dst, in_keys + in_base, TILE * 8u, &s_full[s]);
+      }
+    } else {
+      const uint32_t bytes = (count * (uint32_t)sizeof(T) + 15u) & ~15u;  // region capacity is a multiple of 16 B
+      mbar_expect_tx(&s_full[s], bytes);
+      bulk_g2s(dst, in_part + in_base, bytes, &s_full[s]);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    if (blockIdx.x + (uint64_t)gridDim.x < ntiles) issue(blockIdx.x + (uint64_t)gridDim.x, 1);
+  }
+
+  const uint32_t dpl = (fan + 31u) >> 5;  // digits per lane in the single-warp scan
+  unsigned long long sentinel_local = 0;
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    T* stg = staging + (size_t)s * stg_elems;  // TILE rows + room for the padding of `fan` runs
+    mbar_wait(&s_full[s], (it >> 1) & 1u);    // acquire: also makes s_tbase/s_tcount/s_tp1[s] visible
+    const uint64_t in_base = s_tbase[s];
+    const uint32_t count = s_tcount[s], p1 = s_tp1[s];
+
+    // ---- 1. rows out of the ring, converted; rank inside (tile, digit) from a shared-memory atomic
+    T elem[IPT];
+    uint32_t dr[IPT];
+    const unsigned char* src = ring + s * RING;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t e = i * S2_THREADS + tid;
+      dr[i] = 0xffffffffu;
+      bool ok = e < count;
+      unsigned long long k = 0;
+      if constexpr (STAGE == 1) {
+        k = reinterpret_cast<const unsigned long long*>(src)[e];
+        if constexpr (BUILD) {
+          const unsigned long long v = reinterpret_cast<const unsigned long long*>(src + TILE * 8)[e];
+          if constexpr (NARROW) {
+            if (!narrow_ok(k, v)) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
+            elem[i] = (k << 32) | (v & 0xffffffffull);
+          } else {
+            if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(row_base + in_base + e)); ok = false; }
+            elem[i].x = k; elem[i].y = v;
+          }
+        } else {
+          if constexpr (NARROW) {
+            if ((k >> 32) != 0 || (uint32_t)k == 0xFFFFFFFFu) ok = false;  // cannot match a packed build side
+            elem[i] = (uint32_t)k;
+          } else {
+            if (k == EMPTY64) { ++sentinel_local; ok = false; }
+            elem[i] = k;
+          }
+        }
+      } else {
+        elem[i] = reinterpret_cast<const T*>(src)[e];
+        if (H::is(elem[i])) ok = false;
+        k = E::key(elem[i]);
+      }
+      if (ok) {
+        const uint32_t d = scatter_digit(hash32(k), shift, fan);
+        const uint32_t r = atomicAdd(&s_hist[d], 1u);
+        dr[i] = (d << 16) | r;
+      }
+    }
+    __syncthreads();  // ring stage s fully consumed, histogram complete
+
+    // ---- 2. thread 0 refills the ring; warp 0 turns the histogram into padded staging offsets
+    if (tid == 0) {
+      const uint64_t nxt = tile + 2ull * gridDim.x;
+      if (nxt < ntiles) issue(nxt, s);
+    }
+    if (tid < (int)fan) {
+      // the staging buffer of this tile was last used two tiles ago: the bulk stores this thread issued then
+      // must have finished READING shared memory before anybody overwrites it (one group per tile and thread)
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+    if (tid < 32) {
+      uint32_t sum = 0;
+      for (uint32_t j = 0; j < dpl; ++j) {
+        const uint32_t d = lane * dpl + j;
+        if (d < fan) sum += (s_hist[d] + PADN - 1) / PADN * PADN;
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      uint32_t run = incl - sum;
+      for (uint32_t j = 0; j < dpl; ++j) {
+        const uint32_t d = lane * dpl + j;
+        if (d < fan) {
+          const uint32_t c = s_hist[d];
+          s_hist[d] = 0;
+          s_cnt[d] = c;
+          s_off[d] = run;
+          run += (c + PADN - 1) / PADN * PADN;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- 3. regroup the tile by digit in the staging buffer; the digit threads reserve the global runs
+    uint32_t my_c = 0, my_pc = 0, my_off = 0;
+    long long my_go = -1;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (dr[i] != 0xffffffffu) stg[s_off[dr[i] >> 16] + (dr[i] & 0xffffu)] = elem[i];
+    }
+    if (tid < (int)fan) {
+      my_c = s_cnt[tid];
+      my_pc = (my_c + PADN - 1) / PADN * PADN;
+      my_off = s_off[tid];
+      if (my_c) {
+        const uint32_t outp = (STAGE == 1 || merge) ? (uint32_t)tid : p1 * fan + (uint32_t)tid;
+        const uint32_t g = atomicAdd(out_cursor + outp, my_pc);
+        if ((uint64_t)g + my_pc > out_cap) atomicOr(&ctl->flags, CTL_OVERFLOW);
+        else my_go = (long long)((uint64_t)outp * out_cap + g);
+        for (uint32_t j = my_c; j < my_pc; ++j) stg[my_off + j] = H::make();  // holes pad the run to 16 bytes
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- 4. one bulk store per (tile, digit) run
+    if (tid < (int)fan) {
+      if (my_go >= 0) bulk_s2g(out + my_go, stg + my_off, my_pc * (uint32_t)sizeof(T));
+      bulk_commit();
+    }
+  }
+  if (tid < S2_FMAX) bulk_wait0();
+
+  if (!BUILD && !NARROW && STAGE == 1) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sentinel_local += __shfl_xor_sync(0xffffffffu, sentinel_local, d);
+    if ((tid & 31) == 0 && sentinel_local) atomicAdd(&ctl->sentinel_probes, sentinel_local);
+  }
+}
+
+template <bool BUILD, bool NARROW, int STAGE>
+static void launch_scatter2_inst(const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st) {
+  using T = typename Elem<BUILD, NARROW>::T;
+  constexpr int TILE = S2_STAGING / (int)sizeof(T);
+  constexpr int IN_ROW = STAGE == 1 ? (BUILD ? 16 : 8) : (int)sizeof(T);
+  auto kern = k_scatter2<BUILD, NARROW, STAGE>;
+  constexpr uint32_t PADN = 16 / sizeof(T) > 1 ? 16 / sizeof(T) : 1;
+  const uint32_t stg_elems = ((uint32_t)TILE + a.fan * (PADN - 1) + 7u) & ~7u;  // every run may carry PADN-1 holes
+  const size_t smem = 2 * (size_t)TILE * IN_ROW + 2 * (size_t)stg_elems * sizeof(T);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  uint64_t max_tiles, n_tiles1 = 0;
+  if (STAGE == 1) max_tiles = n_tiles1 = a.n / TILE;
+  else max_tiles = (a.n_upper + TILE - 1) / TILE + a.in_nparts;
+  uint64_t grid = (uint64_t)di.sms * 2;
+  if (grid > max_tiles) grid = max_tiles;
+  if (grid == 0) return;
+  kern<<<(unsigned)grid, S2_THREADS, smem, st>>>(a.in_keys, a.in_vals, n_tiles1, reinterpret_cast<const T*>(a.in_part),
+                                                 a.in_counts, a.in_nparts, a.in_cap, a.merge ? 1 : 0,
+                                                 reinterpret_cast<T*>(a.out), a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl,
+                                                 a.row_base, stg_elems);
+}
+
+// rows per tile of the pipelined scatter for one element format
+uint32_t scatter_tile_rows(bool build, bool narrow) { return (uint32_t)(S2_STAGING / radix_elem_bytes(build, narrow)); }
+uint32_t scatter_pad_rows(bool build, bool narrow) {
+  const size_t e = radix_elem_bytes(build, narrow);
+  return e >= 16 ? 0u : (uint32_t)(16 / e - 1);
+}
+
+// Stage 1: full tiles of 16-byte aligned inputs go through k_scatter2, the ragged tail (and inputs that
+// are only 8-byte aligned) through k_scatter.  Stage 2 (partition -> partition) is always k_scatter2.
+void launch_scatter(bool build, bool narrow, int stage, const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st,
+                    int* launches) {
+#define FJ_SC2(B, N, S) launch_scatter2_inst<B, N, S>(a, di, st)
+#define FJ_DISPATCH(M, S)                                              \
+  do {                                                                 \
+    if (build) { if (narrow) M(true, true, S); else M(true, false, S); } \
+    else { if (narrow) M(false, true, S); else M(false, false, S); }   \
+  } while (0)
+  if (stage == 2) {
+    FJ_DISPATCH(FJ_SC2, 2);
+    ++*launches;
+    return;
+  }
+  const uint32_t tile = scatter_tile_rows(build, narrow);
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.in_keys) & 15u) == 0 &&
+                       (!build || (reinterpret_cast<uintptr_t>(a.in_vals) & 15u) == 0);
+  const uint64_t full = aligned ? a.n / tile * tile : 0;
+  if (full) {
+    FJ_DISPATCH(FJ_SC2, 1);
+    ++*launches;
+  }
+  if (full < a.n) {
+    ScatterArgs t = a;
+    t.in_keys = a.in_keys + full;
+    t.in_vals = a.in_vals ? a.in_vals + full : nullptr;
+    t.n = a.n - full;
+    t.row_base = a.row_base + full;
+#define FJ_SC1(B, N, S) launch_scatter_inst<B, N, 1>(t, di, st)
+    FJ_DISPATCH(FJ_SC1, 1);
+#undef FJ_SC1
+    ++*launches;
+  }
+#undef FJ_DISPATCH
+#undef FJ_SC2
+}
+
 
 // ================================================================================= partition join
 // One CTA per (partition, probe chunk).  Shared memory: the partition's build tuples (TMA bulk
@@ -333,6 +648,7 @@ __global__ void __launch_bounds__(JN_THREADS, 2)
 
   // ---- build: claim a slot per tuple with 32-bit CAS
   for (uint32_t i = tid; i < nbp; i += JN_THREADS) {
+    if (Hole<true, NARROW>::is(tuples[i])) continue;  // padding written by k_scatter2
     const unsigned long long key = Elem<true, NARROW>::key(tuples[i]);
     const uint32_t g = hash32(key) * 0x9E3779B1u;
     const uint32_t fp = g & 0xffffu;
@@ -475,6 +791,277 @@ void launch_join(bool narrow, bool mat, const JoinArgs& a, cudaStream_t st, int*
   ++*launches;
 }
 
+// ================================================================================= partition join, pipelined
+// k_join3 (packed 32|32 rows, >= 2^14 partitions): collision-free join in shared memory.
+//
+// For a packed row the key is a 32-bit value and hash32 is a BIJECTION on 32-bit values; the radix passes
+// consumed the top `bits` hash bits, so inside partition p a key is identified by the remaining
+// rbits = 32 - bits hash bits ("rem").  The partition's build side is therefore a SET of rems in a universe
+// of 2^rbits (<= 2^18) values: a bitmap (<= 32 KB) answers membership exactly — no key comparison, no
+// collision chain, no divergent loop — and a rank directory (16-bit running popcount per bitmap word) maps a
+// member to the slot of its value in a dense value array:  value = vals[prefix[w] + popc(word & below(bit))].
+// Build = atomicOr (a bit that was already set is a duplicate build key -> CTL_DUP), a block scan of the word
+// popcounts, and one value store per row; probe = three shared-memory loads, branch-free.
+//
+// Persistent CTAs walk the (partition, probe chunk) items; all HBM input is prefetched one item ahead
+// with TMA bulk copies (build tuples into a staging area, probe keys into a double buffer).  Matches are
+// written in (row, warp) order so every warp store is one contiguous run; the output range of a chunk is
+// reserved with a single global atomic.
+constexpr int J3_THREADS = 512;
+constexpr int J3_WARPS = J3_THREADS / 32;
+constexpr int J3_IPT = 8;
+constexpr int J3_PCH = J3_THREADS * J3_IPT;  // probe rows per chunk
+constexpr int J3_BPT = 8;                    // build rows per thread kept in registers (smax <= J3_THREADS * J3_BPT)
+
+template <bool MAT>
+__global__ void __launch_bounds__(J3_THREADS, 2)
+    k_join3(const unsigned long long* __restrict__ build, const uint32_t* __restrict__ bcnt, uint64_t cap_b,
+            const uint32_t* __restrict__ probe, const uint32_t* __restrict__ pcnt, uint64_t cap_p, uint32_t smax,
+            int rbits, uint32_t max_chunks, uint64_t nitems, Ctl* __restrict__ ctl,
+            unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_vals) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t nwords = 1u << (rbits - 5);
+  unsigned long long* staging = reinterpret_cast<unsigned long long*>(smem_raw);                 // smax tuples
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw + (size_t)smax * 8);                    // nwords
+  uint16_t* prefix = reinterpret_cast<uint16_t*>(smem_raw + (size_t)smax * 8 + (size_t)nwords * 4);  // nwords
+  uint32_t* vals = reinterpret_cast<uint32_t*>(smem_raw + (size_t)smax * 8 + (size_t)nwords * 6);    // smax
+  uint32_t* pbuf = vals + smax;                                                                   // 2 x J3_PCH
+  __shared__ __align__(8) uint64_t s_bar_t, s_bar_p[2];
+  __shared__ uint32_t s_nb[2], s_np[2];
+  __shared__ uint32_t s_wsum[J3_WARPS];
+  __shared__ uint32_t s_cnt[J3_IPT * J3_WARPS];
+  __shared__ unsigned long long s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rmask = (1u << rbits) - 1u;
+
+  auto item_meta = [&](uint64_t idx, uint32_t& p, uint32_t& nbp, uint32_t& npc, uint64_t& pstart) {
+    p = (uint32_t)(idx / max_chunks);
+    const uint32_t c = (uint32_t)(idx - (uint64_t)p * max_chunks);
+    uint64_t nb = bcnt[p];
+    if (nb > cap_b) nb = cap_b;  // region overflowed: CTL_OVERFLOW already raised by the scatter
+    uint64_t np = pcnt[p];
+    if (np > cap_p) np = cap_p;
+    pstart = (uint64_t)c * J3_PCH;
+    npc = pstart < np ? (uint32_t)((np - pstart) < (uint64_t)J3_PCH ? (np - pstart) : J3_PCH) : 0u;
+    nbp = (uint32_t)nb;
+    if (nbp > smax) {
+      atomicOr(&ctl->flags, CTL_OVERFLOW);
+      nbp = 0;
+    }
+    if (nbp == 0 || npc == 0) nbp = npc = 0;
+  };
+  auto bulk_in = [&](void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+      bulk_g2s(static_cast<unsigned char*>(dst) + off, static_cast<const unsigned char*>(src) + off, n, bar);
+    }
+  };
+  auto issue_tuples = [&](uint64_t idx, uint32_t k) {  // thread 0
+    uint32_t p, nbp, npc;
+    uint64_t pstart;
+    item_meta(idx, p, nbp, npc, pstart);
+    s_nb[k & 1] = nbp;
+    bulk_in(staging, build + (uint64_t)p * cap_b, (nbp * 8u + 15u) & ~15u, &s_bar_t);
+  };
+  auto issue_probe = [&](uint64_t idx, uint32_t k) {  // thread 0
+    uint32_t p, nbp, npc;
+    uint64_t pstart;
+    item_meta(idx, p, nbp, npc, pstart);
+    s_np[k & 1] = npc;
+    bulk_in(pbuf + (size_t)(k & 1) * J3_PCH, probe + (uint64_t)p * cap_p + pstart, (npc * 4u + 15u) & ~15u, &s_bar_p[k & 1]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&s_bar_t, 1);
+    mbar_init(&s_bar_p[0], 1);
+    mbar_init(&s_bar_p[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < nitems) {
+    issue_tuples(blockIdx.x, 0);
+    issue_probe(blockIdx.x, 0);
+  }
+  __syncthreads();
+
+  unsigned long long local_count = 0;
+  uint32_t k = 0;
+  for (uint64_t idx = blockIdx.x; idx < nitems; idx += gridDim.x, ++k) {
+    const uint64_t nxt = idx + gridDim.x;
+    if (tid == 0 && nxt < nitems) issue_probe(nxt, k + 1);  // that buffer was released by the barrier ending item k-1
+    const uint32_t nbp = s_nb[k & 1], npc = s_np[k & 1];
+
+    // ---- A. clear the bitmap while the tuples land
+    if (nbp) {
+      uint4* bm4 = reinterpret_cast<uint4*>(bitmap);
+      for (uint32_t i = tid; i < nwords / 4; i += J3_THREADS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    mbar_wait(&s_bar_t, k & 1u);
+    __syncthreads();
+
+    if (nbp) {  // block-uniform
+      // ---- B. set the member bits; keep (rem, value) of this thread's rows in registers
+      uint32_t rem[J3_BPT], bval[J3_BPT];
+#pragma unroll
+      for (int j = 0; j < J3_BPT; ++j) {
+        const uint32_t i = j * J3_THREADS + tid;
+        rem[j] = 0xFFFFFFFFu;
+        if (i < nbp) {
+          const unsigned long long t = staging[i];
+          const uint32_t key = (uint32_t)(t >> 32);
+          if (key != 0xFFFFFFFFu) {  // not padding written by k_scatter2
+            rem[j] = hash32(key) & rmask;
+            bval[j] = (uint32_t)t;
+            const uint32_t bit = 1u << (rem[j] & 31u);
+            const uint32_t old = atomicOr(bitmap + (rem[j] >> 5), bit);
+            if (old & bit) atomicOr(&ctl->flags, CTL_DUP);  // same key twice (hash32 is a bijection)
+          }
+        }
+      }
+      __syncthreads();
+      // ---- C. rank directory: running popcount before every bitmap word
+      {
+        const uint32_t wpt = nwords / J3_THREADS;  // words per thread: 1 .. 16 (nwords is a power of two >= 512)
+        uint32_t sum = 0;
+        for (uint32_t w = 0; w < wpt; ++w) sum += __popc(bitmap[tid * wpt + w]);
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+          const uint32_t v = lane < J3_WARPS ? s_wsum[lane] : 0u;
+          uint32_t in2 = v;
+#pragma unroll
+          for (int d = 1; d < J3_WARPS; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, in2, d);
+            if (lane >= d) in2 += o;
+          }
+          if (lane < J3_WARPS) s_wsum[lane] = in2 - v;
+        }
+        __syncthreads();
+        uint32_t run = s_wsum[warp] + incl - sum;
+        for (uint32_t w = 0; w < wpt; ++w) {
+          prefix[tid * wpt + w] = (uint16_t)run;
+          run += __popc(bitmap[tid * wpt + w]);
+        }
+      }
+      __syncthreads();
+      // ---- D. place the values by rank
+#pragma unroll
+      for (int j = 0; j < J3_BPT; ++j) {
+        if (rem[j] != 0xFFFFFFFFu) {
+          const uint32_t w = rem[j] >> 5;
+          const uint32_t r = prefix[w] + __popc(bitmap[w] & ((1u << (rem[j] & 31u)) - 1u));
+          vals[r] = bval[j];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && nxt < nitems) issue_tuples(nxt, k + 1);  // staging is free again
+
+    // ---- probe: membership bit, then the value by rank.  No loops, no key comparison.
+    mbar_wait(&s_bar_p[k & 1], (k >> 1) & 1u);
+    const uint32_t* pk = pbuf + (size_t)(k & 1) * J3_PCH;
+    uint32_t key[J3_IPT], val[J3_IPT];
+    uint32_t hitmask = 0;
+    if (npc) {
+#pragma unroll
+      for (int i = 0; i < J3_IPT; ++i) {
+        const uint32_t r = i * J3_THREADS + tid;
+        key[i] = r < npc ? pk[r] : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int i = 0; i < J3_IPT; ++i) {
+        const uint32_t rm = hash32(key[i]) & rmask;
+        const uint32_t w = rm >> 5, sh = rm & 31u;
+        const uint32_t word = bitmap[w];
+        const bool hit = (key[i] != 0xFFFFFFFFu) & ((word >> sh) & 1u);  // 0xFFFFFFFF: hole / past the end
+        val[i] = 0;
+        if (MAT && hit) val[i] = vals[prefix[w] + __popc(word & ((1u << sh) - 1u))];
+        hitmask |= hit ? (1u << i) : 0u;
+      }
+    }
+    if (!MAT) {
+      local_count += __popc(hitmask);
+    } else if (npc) {  // block-uniform
+      uint32_t rank[J3_IPT];
+#pragma unroll
+      for (int i = 0; i < J3_IPT; ++i) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> i) & 1u);
+        rank[i] = __popc(bal & lanemask_lt());
+        if (lane == 0) s_cnt[i * J3_WARPS + warp] = __popc(bal);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        constexpr int PER = J3_IPT * J3_WARPS / 32;
+        uint32_t c[PER];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { c[u] = s_cnt[lane * PER + u]; sum += c[u]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { s_cnt[lane * PER + u] = run; run += c[u]; }
+        if (lane == 31) {
+          s_base = incl ? atomicAdd(&ctl->out_cursor, (unsigned long long)incl) : 0ull;
+          local_count += incl;
+        }
+      }
+      __syncthreads();
+      const unsigned long long base = s_base;
+#pragma unroll
+      for (int i = 0; i < J3_IPT; ++i) {
+        if ((hitmask >> i) & 1u) {
+          const unsigned long long pos = base + s_cnt[i * J3_WARPS + warp] + rank[i];
+          st_stream(out_keys + pos, (unsigned long long)key[i]);
+          st_stream(out_vals + pos, (unsigned long long)val[i]);
+        }
+      }
+    }
+    __syncthreads();  // pbuf[k & 1], s_cnt, s_base, the bitmap and vals are reused by the next items
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
+  if (lane == 0 && local_count) atomicAdd(&ctl->match_count, local_count);
+}
+
+size_t join3_smem_bytes(uint32_t smax, int rbits) {
+  return (size_t)smax * 12 + (size_t)(1u << (rbits - 5)) * 6 + 2 * (size_t)J3_PCH * 4;
+}
+uint32_t join3_probe_chunk() { return J3_PCH; }
+uint32_t join3_max_build_rows() { return J3_THREADS * J3_BPT; }
+int join3_min_rbits() { return 14; }  // bitmap words >= J3_THREADS
+
+void launch_join3(bool mat, const JoinArgs& a, int rbits, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  const size_t smem = join3_smem_bytes(a.smax, rbits);
+  const uint64_t nitems = (uint64_t)a.nparts * a.max_chunks;
+  if (nitems == 0) return;
+  uint64_t grid = (uint64_t)di.sms * 2;
+  if (grid > nitems) grid = nitems;
+#define FJ_J3(M)                                                                                              \
+  do {                                                                                                        \
+    auto kern = k_join3<M>;                                                                                   \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+    kern<<<(unsigned)grid, J3_THREADS, smem, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b, \
+                                                   reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.smax, \
+                                                   rbits, a.max_chunks, nitems, a.ctl, a.out_keys, a.out_vals); \
+  } while (0)
+  if (mat) FJ_J3(true); else FJ_J3(false);
+#undef FJ_J3
+  ++*launches;
+}
+
 // probe rows whose key is the out-of-band sentinel (wide path only)
 __global__ void __launch_bounds__(1024) k_emit_sentinel(Ctl* __restrict__ ctl, const unsigned long long* __restrict__ bv,
                                                         unsigned long long* __restrict__ out_keys,
@@ -519,27 +1106,41 @@ void launch_emit_sentinel_value(Ctl* ctl, unsigned long long value, unsigned lon
   ++*launches;
 }
 
-// partition-element rows -> raw 64-bit columns (fallback of the shuffle path onto the global-table join)
+// partition-element rows -> raw 64-bit columns, holes dropped (fallback of the shuffle path onto the
+// global-table join).  *cursor receives the number of rows written.
 template <bool BUILD, bool NARROW>
 __global__ void __launch_bounds__(256) k_expand(const typename Elem<BUILD, NARROW>::T* __restrict__ in, uint64_t n,
-                                                unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+                                                unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
+                                                unsigned long long* __restrict__ cursor) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const typename Elem<BUILD, NARROW>::T e = in[i];
-    keys[i] = Elem<BUILD, NARROW>::key(e);
-    if constexpr (BUILD) {
-      if constexpr (NARROW) vals[i] = e & 0xffffffffull;
-      else vals[i] = e.y;
+  const uint64_t n_round = (n + 31) & ~uint64_t(31);
+  const unsigned lane = threadIdx.x & 31;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    typename Elem<BUILD, NARROW>::T e = Hole<BUILD, NARROW>::make();
+    if (i < n) e = in[i];
+    const bool ok = !Hole<BUILD, NARROW>::is(e);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    unsigned long long base = 0;
+    if (lane == 0 && bal) base = atomicAdd(cursor, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) {
+      const unsigned long long pos = base + __popc(bal & lanemask_lt());
+      keys[pos] = Elem<BUILD, NARROW>::key(e);
+      if constexpr (BUILD) {
+        if constexpr (NARROW) vals[pos] = e & 0xffffffffull;
+        else vals[pos] = e.y;
+      }
     }
   }
 }
 void launch_expand(bool build, bool narrow, const void* in, uint64_t n, unsigned long long* keys, unsigned long long* vals,
-                   const DeviceInfo& di, cudaStream_t st, int* launches) {
+                   unsigned long long* cursor, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (n == 0) return;
   uint64_t want = (n + 255) / 256;
   const uint64_t cap = (uint64_t)di.sms * 16;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-#define FJ_EX(B, N) k_expand<B, N><<<grid, 256, 0, st>>>(reinterpret_cast<const typename Elem<B, N>::T*>(in), n, keys, vals)
+#define FJ_EX(B, N) \
+  k_expand<B, N><<<grid, 256, 0, st>>>(reinterpret_cast<const typename Elem<B, N>::T*>(in), n, keys, vals, cursor)
   if (build) { if (narrow) FJ_EX(true, true); else FJ_EX(true, false); }
   else { if (narrow) FJ_EX(false, true); else FJ_EX(false, false); }
 #undef FJ_EX

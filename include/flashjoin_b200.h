@@ -124,7 +124,7 @@ FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values,
  * hash_join.cpp:38, :79, :99, :302, :393, :576) ------------------------------------------------
  * keys: "load_pct" (table load factor, %), "load_pct_auto" (1: small tables drop to 25 %), "bloom_bits_per_key", "adaptive_table_l2_pct",
  *       "radix_sub_rows" (target build rows per shared-memory partition), "radix_optimistic",
- *       "smem_bloom" (0/1), "probe_ctas_per_sm", "chunk_rows" (host-input pipelining chunk). */
+ *       "smem_bloom" (0/1), "join3" (0/1: collision-free pipelined partition join for packed rows), "probe_ctas_per_sm", "chunk_rows" (host-input pipelining chunk). */
 FJ_API fj_status fj_config_set(const char* key, int64_t value);
 FJ_API fj_status fj_config_get(const char* key, int64_t* value);
 
