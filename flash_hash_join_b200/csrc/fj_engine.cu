@@ -231,6 +231,7 @@ RadixPlan Engine::plan_radix(uint64_t nb, uint64_t np, bool narrow) const {
     c.bits = B;
     if (B <= 8) { c.bits1 = B; c.bits2 = 0; }
     else { c.bits1 = (B + 1) / 2; c.bits2 = B - c.bits1; }
+    if (c.bits1 > 8) break;  // one scatter pass fans out to at most 256 partitions
     // packed rows that need two passes anyway go to k_join3, which wants >= 2^14 partitions (its bitmap
     // covers the 32 - B hash bits the passes did not consume)
     const bool j3 = allow3 && c.bits2 > 0;

@@ -64,7 +64,7 @@ struct ScatterArgs {
   uint64_t out_cap = 0;
   int shift = 0;      // >= 0: digit = (hash32(key) >> shift) & (fan - 1), fan a power of two
                       // < 0 : shuffle destination = ((hash32(key) & 0xffff) * fan) >> 16, any fan
-  uint32_t fan = 1;   // <= 512
+  uint32_t fan = 1;   // <= 256
   Ctl* ctl = nullptr;
 };
 struct JoinArgs {

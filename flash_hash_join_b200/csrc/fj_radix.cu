@@ -272,7 +272,7 @@ size_t radix_elem_bytes(bool build, bool narrow) {
 // Tile size = 16 KB of OUTPUT rows (4096 / 2048 / 1024 rows for 4 / 8 / 16-byte elements); two CTAs per SM.
 constexpr int S2_THREADS = 512;
 constexpr int S2_STAGING = 16384;  // bytes per staging buffer
-constexpr int S2_FMAX = 512;
+constexpr int S2_FMAX = 256;  // max fan-out of one pass (digits fit 8 bits)
 
 template <bool BUILD, bool NARROW> struct Hole;
 template <> struct Hole<true, true> {
@@ -292,6 +292,8 @@ template <> struct Hole<false, false> {
   static __device__ __forceinline__ bool is(unsigned long long e) { return e == EMPTY64; }
 };
 
+constexpr int S2_CHUNKS = S2_STAGING / 16 + S2_FMAX;  // 16-byte chunks of one staging buffer, padding included
+
 template <bool BUILD, bool NARROW, int STAGE>
 __global__ void __launch_bounds__(S2_THREADS, 2)
     k_scatter2(const unsigned long long* __restrict__ in_keys, const unsigned long long* __restrict__ in_vals,
@@ -305,20 +307,24 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
   using H = Hole<BUILD, NARROW>;
   constexpr int TILE = S2_STAGING / (int)sizeof(T);
   constexpr int IPT = TILE / S2_THREADS;
-  constexpr int PADN = 16 / (int)sizeof(T) > 1 ? 16 / (int)sizeof(T) : 1;
+  constexpr int PADN = 16 / (int)sizeof(T) > 1 ? 16 / (int)sizeof(T) : 1;  // rows per 16-byte chunk
   constexpr int IN_ROW = STAGE == 1 ? (BUILD ? 16 : 8) : (int)sizeof(T);
   constexpr int RING = TILE * IN_ROW;  // bytes per ring stage
+  constexpr int POISON = 0x7fffffff;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;
   T* staging = reinterpret_cast<T*>(smem_raw + 2 * RING);
-  __shared__ uint32_t s_hist[S2_FMAX];      // rows per digit of the current tile
-  __shared__ uint32_t s_cnt[S2_FMAX];       // copy of s_hist taken by the scan
-  __shared__ uint32_t s_off[S2_FMAX];       // staging offset of the digit's (padded) run
+  __shared__ uint32_t s_hist[S2_FMAX];          // rows per digit of the current tile
+  __shared__ uint32_t s_cnt[S2_FMAX];           // copy of s_hist taken by the scan
+  __shared__ uint32_t s_off[S2_FMAX];           // staging offset (rows) of the digit's padded run
+  __shared__ int s_delta[2][S2_FMAX];           // per staging buffer: global chunk index - staging chunk index
+  __shared__ uint8_t s_cdig[2][S2_CHUNKS];      // per staging buffer: digit of every 16-byte chunk
+  __shared__ uint32_t s_nchunk[2];
   __shared__ uint32_t s_tpref[S2_FMAX + 1];
   __shared__ uint32_t s_warp[S2_THREADS / 32];
   __shared__ __align__(8) uint64_t s_full[2];
-  __shared__ unsigned long long s_tbase[2];  // per ring stage: input offset (elements) of the tile in flight
+  __shared__ unsigned long long s_tbase[2];     // per ring stage: input offset (elements) of the tile in flight
   __shared__ uint32_t s_tcount[2], s_tp1[2];
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -393,8 +399,22 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
     if (blockIdx.x + (uint64_t)gridDim.x < ntiles) issue(blockIdx.x + (uint64_t)gridDim.x, 1);
   }
 
+  // step 4: copy one staged tile out, 16 bytes per thread and iteration; the chunks of a run are contiguous
+  // both in the staging buffer and in global memory, so a warp writes (a few) contiguous pieces
+  auto copy_out = [&](int sb) {
+    const uint4* src16 = reinterpret_cast<const uint4*>(staging + (size_t)sb * stg_elems);
+    uint4* out16 = reinterpret_cast<uint4*>(out);
+    const uint32_t nchunk = s_nchunk[sb];
+    for (uint32_t c = tid; c < nchunk; c += S2_THREADS) {
+      const int dl = s_delta[sb][s_cdig[sb][c]];
+      if (dl != POISON) out16[(long long)dl + (long long)c] = src16[c];
+    }
+  };
+
   const uint32_t dpl = (fan + 31u) >> 5;  // digits per lane in the single-warp scan
   unsigned long long sentinel_local = 0;
+  // digit threads (tid < fan): the run reserved for this thread's digit in the tile staged last
+  uint32_t my_g = 0, my_pc = 0, my_off = 0, my_outp = 0;
   uint32_t it = 0;
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int s = it & 1;
@@ -444,18 +464,24 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         dr[i] = (d << 16) | r;
       }
     }
-    __syncthreads();  // ring stage s fully consumed, histogram complete
+    // the reservation made for the previous tile has long returned: publish where its runs go
+    if (it > 0 && tid < (int)fan) {
+      int dl = POISON;
+      if (my_pc) {
+        if ((uint64_t)my_g + my_pc > out_cap) atomicOr(&ctl->flags, CTL_OVERFLOW);
+        else dl = (int)((long long)(((uint64_t)my_outp * out_cap + my_g) / PADN) - (long long)(my_off / PADN));
+      }
+      s_delta[s ^ 1][tid] = dl;
+    }
+    __syncthreads();  // ring stage s consumed, histogram complete, previous tile staged and its s_delta published
 
-    // ---- 2. thread 0 refills the ring; warp 0 turns the histogram into padded staging offsets
+    // ---- 4 (of the PREVIOUS tile): copy it out.  Deferred to here so that the latency of the reserving
+    // atomicAdd (issued in step 3) is covered by step 1 of this tile.  Thread 0 refills the ring first.
     if (tid == 0) {
       const uint64_t nxt = tile + 2ull * gridDim.x;
       if (nxt < ntiles) issue(nxt, s);
     }
-    if (tid < (int)fan) {
-      // the staging buffer of this tile was last used two tiles ago: the bulk stores this thread issued then
-      // must have finished READING shared memory before anybody overwrites it (one group per tile and thread)
-      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    }
+    // ---- 2. warp 0 turns the histogram into padded staging offsets while the other warps copy out
     if (tid < 32) {
       uint32_t sum = 0;
       for (uint32_t j = 0; j < dpl; ++j) {
@@ -479,38 +505,42 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
           run += (c + PADN - 1) / PADN * PADN;
         }
       }
+      if (lane == 31) s_nchunk[s] = incl / PADN;
     }
+    if (it > 0) copy_out(s ^ 1);
     __syncthreads();
 
     // ---- 3. regroup the tile by digit in the staging buffer; the digit threads reserve the global runs
-    uint32_t my_c = 0, my_pc = 0, my_off = 0;
-    long long my_go = -1;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       if (dr[i] != 0xffffffffu) stg[s_off[dr[i] >> 16] + (dr[i] & 0xffffu)] = elem[i];
     }
     if (tid < (int)fan) {
-      my_c = s_cnt[tid];
+      const uint32_t my_c = s_cnt[tid];
       my_pc = (my_c + PADN - 1) / PADN * PADN;
       my_off = s_off[tid];
       if (my_c) {
-        const uint32_t outp = (STAGE == 1 || merge) ? (uint32_t)tid : p1 * fan + (uint32_t)tid;
-        const uint32_t g = atomicAdd(out_cursor + outp, my_pc);
-        if ((uint64_t)g + my_pc > out_cap) atomicOr(&ctl->flags, CTL_OVERFLOW);
-        else my_go = (long long)((uint64_t)outp * out_cap + g);
+        my_outp = (STAGE == 1 || merge) ? (uint32_t)tid : p1 * fan + (uint32_t)tid;
+        my_g = atomicAdd(out_cursor + my_outp, my_pc);  // consumed after step 1 of the next tile
         for (uint32_t j = my_c; j < my_pc; ++j) stg[my_off + j] = H::make();  // holes pad the run to 16 bytes
+        for (uint32_t c = my_off / PADN; c < (my_off + my_pc) / PADN; ++c) s_cdig[s][c] = (uint8_t)tid;
       }
     }
-    fence_proxy_async();
-    __syncthreads();
-
-    // ---- 4. one bulk store per (tile, digit) run
-    if (tid < (int)fan) {
-      if (my_go >= 0) bulk_s2g(out + my_go, stg + my_off, my_pc * (uint32_t)sizeof(T));
-      bulk_commit();
-    }
   }
-  if (tid < S2_FMAX) bulk_wait0();
+  // drain: the last tile staged by this CTA
+  if (it > 0) {
+    const int sb = (it - 1) & 1;
+    if (tid < (int)fan) {
+      int dl = POISON;
+      if (my_pc) {
+        if ((uint64_t)my_g + my_pc > out_cap) atomicOr(&ctl->flags, CTL_OVERFLOW);
+        else dl = (int)((long long)(((uint64_t)my_outp * out_cap + my_g) / PADN) - (long long)(my_off / PADN));
+      }
+      s_delta[sb][tid] = dl;
+    }
+    __syncthreads();
+    copy_out(sb);
+  }
 
   if (!BUILD && !NARROW && STAGE == 1) {
 #pragma unroll
@@ -921,11 +951,22 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
         }
       }
       __syncthreads();
-      // ---- C. rank directory: running popcount before every bitmap word
+      // ---- C. rank directory: running popcount before every bitmap word.  Thread t owns the wpt consecutive
+      // words [t * wpt, (t + 1) * wpt); with wpt == 8 (2^17 hash values per partition, the 1e8-row case) they
+      // are read as two 128-bit loads and the eight 16-bit prefixes leave as one 128-bit store.
       {
         const uint32_t wpt = nwords / J3_THREADS;  // words per thread: 1 .. 16 (nwords is a power of two >= 512)
+        uint32_t pc[8];
         uint32_t sum = 0;
-        for (uint32_t w = 0; w < wpt; ++w) sum += __popc(bitmap[tid * wpt + w]);
+        if (wpt == 8) {
+          const uint4 a = reinterpret_cast<const uint4*>(bitmap)[tid * 2], b = reinterpret_cast<const uint4*>(bitmap)[tid * 2 + 1];
+          pc[0] = __popc(a.x); pc[1] = __popc(a.y); pc[2] = __popc(a.z); pc[3] = __popc(a.w);
+          pc[4] = __popc(b.x); pc[5] = __popc(b.y); pc[6] = __popc(b.z); pc[7] = __popc(b.w);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += pc[w];
+        } else {
+          for (uint32_t w = 0; w < wpt; ++w) sum += __popc(bitmap[tid * wpt + w]);
+        }
         uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -946,9 +987,17 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
         }
         __syncthreads();
         uint32_t run = s_wsum[warp] + incl - sum;
-        for (uint32_t w = 0; w < wpt; ++w) {
-          prefix[tid * wpt + w] = (uint16_t)run;
-          run += __popc(bitmap[tid * wpt + w]);
+        if (wpt == 8) {
+          uint32_t q[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { q[w] = run; run += pc[w]; }
+          reinterpret_cast<uint4*>(prefix)[tid] =
+              make_uint4(q[0] | (q[1] << 16), q[2] | (q[3] << 16), q[4] | (q[5] << 16), q[6] | (q[7] << 16));
+        } else {
+          for (uint32_t w = 0; w < wpt; ++w) {
+            prefix[tid * wpt + w] = (uint16_t)run;
+            run += __popc(bitmap[tid * wpt + w]);
+          }
         }
       }
       __syncthreads();

@@ -41,7 +41,7 @@ if has ncu_c2; then
     python tools/prof_case.py C2 scalar count bloom --reps 4 > "$OUT/ncu_c2.log" 2>&1
 fi
 if has ncu_c3; then
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_scatter|k_join' -s 6 -c 6 -f -o "$OUT/c3_radix" \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_scatter2|k_join" -s 5 -c 5 -f -o "$OUT/c3_radix" \
     python tools/prof_case.py C3 radix mat --reps 3 > "$OUT/ncu_c3.log" 2>&1
 fi
 if has sanitize; then
