@@ -269,9 +269,8 @@ size_t radix_elem_bytes(bool build, bool narrow) {
 //        all-ones element can never be a row — see Elem below) and reservations are made in
 //        padded units.  Consumers (the next scatter pass, k_join, k_expand) skip holes.
 // The threads only ever touch shared memory: LDS row -> hash -> ATOMS rank -> STS staged element.
-// Tile size = 16 KB of OUTPUT rows (4096 / 2048 / 1024 rows for 4 / 8 / 16-byte elements); two CTAs per SM.
+// Tile = 4096 rows (2048 for 16-byte elements): 8 (4) rows per thread; two CTAs per SM.
 constexpr int S2_THREADS = 512;
-constexpr int S2_STAGING = 16384;  // bytes per staging buffer
 constexpr int S2_FMAX = 256;  // max fan-out of one pass (digits fit 8 bits)
 
 template <bool BUILD, bool NARROW> struct Hole;
@@ -292,7 +291,8 @@ template <> struct Hole<false, false> {
   static __device__ __forceinline__ bool is(unsigned long long e) { return e == EMPTY64; }
 };
 
-constexpr int S2_CHUNKS = S2_STAGING / 16 + S2_FMAX;  // 16-byte chunks of one staging buffer, padding included
+template <class T> struct S2Tile { static constexpr int ROWS = sizeof(T) == 16 ? 2048 : 4096; };
+constexpr int S2_CHUNKS = 2048 + S2_FMAX;  // 16-byte chunks of the staging buffer (<= 32 KB of rows), padding included
 
 template <bool BUILD, bool NARROW, int STAGE>
 __global__ void __launch_bounds__(S2_THREADS, 2)
@@ -301,25 +301,25 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
                const typename Elem<BUILD, NARROW>::T* __restrict__ in_part,  // stage 2
                const uint32_t* __restrict__ in_counts, uint32_t in_nparts, uint64_t in_cap, int merge,
                typename Elem<BUILD, NARROW>::T* __restrict__ out, uint32_t* __restrict__ out_cursor, uint64_t out_cap,
-               int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base, uint32_t stg_elems) {
+               int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base) {
   using E = Elem<BUILD, NARROW>;
   using T = typename E::T;
   using H = Hole<BUILD, NARROW>;
-  constexpr int TILE = S2_STAGING / (int)sizeof(T);
+  constexpr int TILE = S2Tile<T>::ROWS;
   constexpr int IPT = TILE / S2_THREADS;
   constexpr int PADN = 16 / (int)sizeof(T) > 1 ? 16 / (int)sizeof(T) : 1;  // rows per 16-byte chunk
-  constexpr int IN_ROW = STAGE == 1 ? (BUILD ? 16 : 8) : (int)sizeof(T);
-  constexpr int RING = TILE * IN_ROW;  // bytes per ring stage
+  constexpr int IN_ROW = STAGE == 1 ? 8 : (int)sizeof(T);                  // stage 1: the ring holds the KEYS only
+  constexpr int RING = TILE * IN_ROW;                                       // bytes per ring stage
   constexpr int POISON = 0x7fffffff;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;
-  T* staging = reinterpret_cast<T*>(smem_raw + 2 * RING);
+  T* stg = reinterpret_cast<T*>(smem_raw + 2 * RING);  // TILE rows + room for the padding of `fan` runs
   __shared__ uint32_t s_hist[S2_FMAX];          // rows per digit of the current tile
   __shared__ uint32_t s_cnt[S2_FMAX];           // copy of s_hist taken by the scan
   __shared__ uint32_t s_off[S2_FMAX];           // staging offset (rows) of the digit's padded run
-  __shared__ int s_delta[2][S2_FMAX];           // per staging buffer: global chunk index - staging chunk index
-  __shared__ uint8_t s_cdig[2][S2_CHUNKS];      // per staging buffer: digit of every 16-byte chunk
+  __shared__ int s_delta[S2_FMAX];              // global chunk index - staging chunk index of the staged tile
+  __shared__ uint8_t s_cdig[S2_CHUNKS];         // digit of every 16-byte chunk of the staged tile
   __shared__ uint32_t s_nchunk[2];
   __shared__ uint32_t s_tpref[S2_FMAX + 1];
   __shared__ uint32_t s_warp[S2_THREADS / 32];
@@ -373,14 +373,8 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
     s_tp1[s] = p1;
     unsigned char* dst = ring + s * RING;
     if (STAGE == 1) {
-      if (BUILD) {
-        mbar_expect_tx(&s_full[s], 2u * TILE * 8u);
-        bulk_g2s(dst, in_keys + in_base, TILE * 8u, &s_full[s]);
-        bulk_g2s(dst + TILE * 8, in_vals + in_base, TILE * 8u, &s_full[s]);
-      } else {
-        mbar_expect_tx(&s_full[s], TILE * 8u);
-        bulk_g2s(dst, in_keys + in_base, TILE * 8u, &s_full[s]);
-      }
+      mbar_expect_tx(&s_full[s], TILE * 8u);
+      bulk_g2s(dst, in_keys + in_base, TILE * 8u, &s_full[s]);
     } else {
       const uint32_t bytes = (count * (uint32_t)sizeof(T) + 15u) & ~15u;  // region capacity is a multiple of 16 B
       mbar_expect_tx(&s_full[s], bytes);
@@ -399,14 +393,13 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
     if (blockIdx.x + (uint64_t)gridDim.x < ntiles) issue(blockIdx.x + (uint64_t)gridDim.x, 1);
   }
 
-  // step 4: copy one staged tile out, 16 bytes per thread and iteration; the chunks of a run are contiguous
+  // step 4: copy the staged tile out, 16 bytes per thread and iteration; the chunks of a run are contiguous
   // both in the staging buffer and in global memory, so a warp writes (a few) contiguous pieces
-  auto copy_out = [&](int sb) {
-    const uint4* src16 = reinterpret_cast<const uint4*>(staging + (size_t)sb * stg_elems);
+  auto copy_out = [&](uint32_t nchunk) {
+    const uint4* src16 = reinterpret_cast<const uint4*>(stg);
     uint4* out16 = reinterpret_cast<uint4*>(out);
-    const uint32_t nchunk = s_nchunk[sb];
     for (uint32_t c = tid; c < nchunk; c += S2_THREADS) {
-      const int dl = s_delta[sb][s_cdig[sb][c]];
+      const int dl = s_delta[s_cdig[c]];
       if (dl != POISON) out16[(long long)dl + (long long)c] = src16[c];
     }
   };
@@ -418,15 +411,20 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
   uint32_t it = 0;
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int s = it & 1;
-    T* stg = staging + (size_t)s * stg_elems;  // TILE rows + room for the padding of `fan` runs
-    mbar_wait(&s_full[s], (it >> 1) & 1u);    // acquire: also makes s_tbase/s_tcount/s_tp1[s] visible
+    mbar_wait(&s_full[s], (it >> 1) & 1u);  // acquire: also makes s_tbase/s_tcount/s_tp1[s] visible
     const uint64_t in_base = s_tbase[s];
     const uint32_t count = s_tcount[s], p1 = s_tp1[s];
 
-    // ---- 1. rows out of the ring, converted; rank inside (tile, digit) from a shared-memory atomic
+    // ---- 1. rows out of the ring; rank inside (tile, digit) from a shared-memory atomic.  Stage-1 build
+    // values are only needed when the row is staged (step 3): they come straight from HBM into registers.
     T elem[IPT];
     uint32_t dr[IPT];
+    unsigned long long bval[(STAGE == 1 && BUILD) ? IPT : 1];
     const unsigned char* src = ring + s * RING;
+    if constexpr (STAGE == 1 && BUILD) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) bval[i] = ld_stream1(in_vals + in_base + i * S2_THREADS + tid);
+    }
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t e = i * S2_THREADS + tid;
@@ -436,13 +434,12 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
       if constexpr (STAGE == 1) {
         k = reinterpret_cast<const unsigned long long*>(src)[e];
         if constexpr (BUILD) {
-          const unsigned long long v = reinterpret_cast<const unsigned long long*>(src + TILE * 8)[e];
           if constexpr (NARROW) {
-            if (!narrow_ok(k, v)) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
-            elem[i] = (k << 32) | (v & 0xffffffffull);
+            if ((k >> 32) != 0 || (uint32_t)k == 0xFFFFFFFFu) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
+            elem[i] = k << 32;
           } else {
             if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(row_base + in_base + e)); ok = false; }
-            elem[i].x = k; elem[i].y = v;
+            elem[i].x = k;
           }
         } else {
           if constexpr (NARROW) {
@@ -471,7 +468,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         if ((uint64_t)my_g + my_pc > out_cap) atomicOr(&ctl->flags, CTL_OVERFLOW);
         else dl = (int)((long long)(((uint64_t)my_outp * out_cap + my_g) / PADN) - (long long)(my_off / PADN));
       }
-      s_delta[s ^ 1][tid] = dl;
+      s_delta[tid] = dl;
     }
     __syncthreads();  // ring stage s consumed, histogram complete, previous tile staged and its s_delta published
 
@@ -507,12 +504,20 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
       }
       if (lane == 31) s_nchunk[s] = incl / PADN;
     }
-    if (it > 0) copy_out(s ^ 1);
+    if (it > 0) copy_out(s_nchunk[s ^ 1]);
     __syncthreads();
 
     // ---- 3. regroup the tile by digit in the staging buffer; the digit threads reserve the global runs
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
+      if constexpr (STAGE == 1 && BUILD) {
+        if constexpr (NARROW) {
+          if ((bval[i] >> 32) != 0 && dr[i] != 0xffffffffu) atomicOr(&ctl->flags, CTL_NEED_WIDE);  // attempt is abandoned
+          elem[i] |= bval[i] & 0xffffffffull;
+        } else {
+          elem[i].y = bval[i];
+        }
+      }
       if (dr[i] != 0xffffffffu) stg[s_off[dr[i] >> 16] + (dr[i] & 0xffffu)] = elem[i];
     }
     if (tid < (int)fan) {
@@ -523,23 +528,22 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         my_outp = (STAGE == 1 || merge) ? (uint32_t)tid : p1 * fan + (uint32_t)tid;
         my_g = atomicAdd(out_cursor + my_outp, my_pc);  // consumed after step 1 of the next tile
         for (uint32_t j = my_c; j < my_pc; ++j) stg[my_off + j] = H::make();  // holes pad the run to 16 bytes
-        for (uint32_t c = my_off / PADN; c < (my_off + my_pc) / PADN; ++c) s_cdig[s][c] = (uint8_t)tid;
+        for (uint32_t c = my_off / PADN; c < (my_off + my_pc) / PADN; ++c) s_cdig[c] = (uint8_t)tid;
       }
     }
   }
   // drain: the last tile staged by this CTA
   if (it > 0) {
-    const int sb = (it - 1) & 1;
     if (tid < (int)fan) {
       int dl = POISON;
       if (my_pc) {
         if ((uint64_t)my_g + my_pc > out_cap) atomicOr(&ctl->flags, CTL_OVERFLOW);
         else dl = (int)((long long)(((uint64_t)my_outp * out_cap + my_g) / PADN) - (long long)(my_off / PADN));
       }
-      s_delta[sb][tid] = dl;
+      s_delta[tid] = dl;
     }
     __syncthreads();
-    copy_out(sb);
+    copy_out(s_nchunk[(it - 1) & 1]);
   }
 
   if (!BUILD && !NARROW && STAGE == 1) {
@@ -552,12 +556,12 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
 template <bool BUILD, bool NARROW, int STAGE>
 static void launch_scatter2_inst(const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st) {
   using T = typename Elem<BUILD, NARROW>::T;
-  constexpr int TILE = S2_STAGING / (int)sizeof(T);
-  constexpr int IN_ROW = STAGE == 1 ? (BUILD ? 16 : 8) : (int)sizeof(T);
+  constexpr int TILE = S2Tile<T>::ROWS;
+  constexpr int IN_ROW = STAGE == 1 ? 8 : (int)sizeof(T);
   auto kern = k_scatter2<BUILD, NARROW, STAGE>;
   constexpr uint32_t PADN = 16 / sizeof(T) > 1 ? 16 / sizeof(T) : 1;
   const uint32_t stg_elems = ((uint32_t)TILE + a.fan * (PADN - 1) + 7u) & ~7u;  // every run may carry PADN-1 holes
-  const size_t smem = 2 * (size_t)TILE * IN_ROW + 2 * (size_t)stg_elems * sizeof(T);
+  const size_t smem = 2 * (size_t)TILE * IN_ROW + (size_t)stg_elems * sizeof(T);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   uint64_t max_tiles, n_tiles1 = 0;
   if (STAGE == 1) max_tiles = n_tiles1 = a.n / TILE;
@@ -568,11 +572,11 @@ static void launch_scatter2_inst(const ScatterArgs& a, const DeviceInfo& di, cud
   kern<<<(unsigned)grid, S2_THREADS, smem, st>>>(a.in_keys, a.in_vals, n_tiles1, reinterpret_cast<const T*>(a.in_part),
                                                  a.in_counts, a.in_nparts, a.in_cap, a.merge ? 1 : 0,
                                                  reinterpret_cast<T*>(a.out), a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl,
-                                                 a.row_base, stg_elems);
+                                                 a.row_base);
 }
 
 // rows per tile of the pipelined scatter for one element format
-uint32_t scatter_tile_rows(bool build, bool narrow) { return (uint32_t)(S2_STAGING / radix_elem_bytes(build, narrow)); }
+uint32_t scatter_tile_rows(bool build, bool narrow) { return radix_elem_bytes(build, narrow) == 16 ? 2048u : 4096u; }
 uint32_t scatter_pad_rows(bool build, bool narrow) {
   const size_t e = radix_elem_bytes(build, narrow);
   return e >= 16 ? 0u : (uint32_t)(16 / e - 1);
