@@ -200,26 +200,29 @@ __device__ __forceinline__ bool probe_home(unsigned long long key, uint32_t b, u
 constexpr int PROBE_KPT = 8;   // probe keys per thread per tile (4 x 128-bit loads)
 constexpr int PROBE_QCAP = 64; // per-warp survivor queue (Bloom variants), entries
 
-// load one tile of probe keys: 128-bit coalesced loads when aligned and full, guarded otherwise
+// load one tile of probe keys: 128-bit coalesced loads when aligned and full, guarded otherwise.
+// Returns the mask of valid key slots (0xff for a full tile).
 template <int THREADS>
-__device__ __forceinline__ void load_tile(const unsigned long long* __restrict__ pk, uint64_t np, uint64_t tbase, bool vec,
-                                          unsigned long long (&key)[PROBE_KPT], bool (&valid)[PROBE_KPT]) {
+__device__ __forceinline__ uint32_t load_tile(const unsigned long long* __restrict__ pk, uint64_t np, uint64_t tbase, bool vec,
+                                              unsigned long long (&key)[PROBE_KPT]) {
   const int tid = threadIdx.x;
   if (vec) {
 #pragma unroll
     for (int r = 0; r < PROBE_KPT / 2; ++r) {
       const uint64_t e = tbase + 2ull * ((uint64_t)r * THREADS + tid);
       ld_stream2(pk + e, key[2 * r], key[2 * r + 1]);
-      valid[2 * r] = valid[2 * r + 1] = true;
     }
-  } else {
-#pragma unroll
-    for (int q = 0; q < PROBE_KPT; ++q) {
-      const uint64_t e = tbase + (uint64_t)q * THREADS + tid;
-      valid[q] = e < np;
-      key[q] = valid[q] ? ld_stream1(pk + e) : 0ull;
-    }
+    return 0xffu;
   }
+  uint32_t valid = 0;
+#pragma unroll
+  for (int q = 0; q < PROBE_KPT; ++q) {
+    const uint64_t e = tbase + (uint64_t)q * THREADS + tid;
+    const bool ok = e < np;
+    key[q] = ok ? ld_stream1(pk + e) : 0ull;
+    valid |= ok ? (1u << q) : 0u;
+  }
+  return valid;
 }
 
 // stage the whole Bloom filter in shared memory with TMA bulk copies (cp.async.bulk + mbarrier)
@@ -278,23 +281,9 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
 
   uint32_t cnt = 0, qh = 0, qt = 0;
   const uint64_t ntiles = (np + TILE - 1) / TILE;
-  // register double buffering: the next tile's keys are requested before the current tile is
-  // processed, so the HBM latency of the key stream overlaps the filter / table work
-  unsigned long long nkey[PROBE_KPT];
-  bool nvalid[PROBE_KPT];
-  if (blockIdx.x < ntiles) {
-    const uint64_t tb0 = (uint64_t)blockIdx.x * TILE;
-    load_tile<THREADS>(pk, np, tb0, vec_ok && tb0 + TILE <= np, nkey, nvalid);
-  }
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    unsigned long long key[PROBE_KPT];
-    bool valid[PROBE_KPT];
-#pragma unroll
-    for (int q = 0; q < PROBE_KPT; ++q) { key[q] = nkey[q]; valid[q] = nvalid[q]; }
-    if (tile + gridDim.x < ntiles) {
-      const uint64_t tbn = (tile + gridDim.x) * TILE;
-      load_tile<THREADS>(pk, np, tbn, vec_ok && tbn + TILE <= np, nkey, nvalid);
-    }
+
+  // one tile: dense branch-free stage over all 8 keys of the thread, then the survivors go to the warp queue
+  auto do_tile = [&](const unsigned long long (&key)[PROBE_KPT], const uint32_t valid) {
     uint32_t surv = 0;  // bit q set: key[q] needs (more) table work
     if (BLOOM == 0) {
 #pragma unroll
@@ -309,18 +298,19 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
         for (int j = 0; j < 4; ++j) {
           const int q = half * 4 + j;
           const unsigned long long k = key[q];
+          const bool vq = (valid >> q) & 1u;
           bool hit, more;
           if (NARROW) {
             const uint32_t k32 = (uint32_t)k;
-            const bool ok = valid[q] & ((k >> 32) == 0) & (k32 != 0xFFFFFFFFu);
+            const bool ok = vq & ((k >> 32) == 0) & (k32 != 0xFFFFFFFFu);
             hit = ok & (((uint32_t)(s[j][0] >> 32) == k32) | ((uint32_t)(s[j][1] >> 32) == k32) |
                         ((uint32_t)(s[j][2] >> 32) == k32) | ((uint32_t)(s[j][3] >> 32) == k32));
             more = ok & !hit & ((uint32_t)(s[j][3] >> 32) != 0xFFFFFFFFu);
           } else {
-            const bool ok = valid[q] & (k != EMPTY64);
+            const bool ok = vq & (k != EMPTY64);
             hit = ok & ((s[j][0] == k) | (s[j][2] == k));
             more = ok & !hit & (s[j][2] != EMPTY64);
-            hit |= valid[q] & (k == EMPTY64) & sent_present;
+            hit |= vq & (k == EMPTY64) & sent_present;
           }
           cnt += hit ? 1u : 0u;
           surv |= more ? (1u << q) : 0u;
@@ -330,17 +320,21 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
       uint32_t x[PROBE_KPT], w[PROBE_KPT];
 #pragma unroll
       for (int q = 0; q < PROBE_KPT; ++q) {  // all filter words requested before any is tested
-        x[q] = bloom_hash(key[q]);
+        // packed table: a key with a non-zero high word cannot be present, so only the low word is hashed
+        // (the build side hashes the same way: its high words are zero)
+        x[q] = NARROW ? bloom_hash((uint32_t)key[q]) : bloom_hash(key[q]);
         const uint32_t wi = bloom_word(x[q], bloom_words);
         w[q] = (BLOOM == 1) ? sbloom[wi] : __ldg(bloom + wi);
       }
 #pragma unroll
       for (int q = 0; q < PROBE_KPT; ++q) {
         const uint32_t m = bloom_mask(x[q]);
-        bool pass = valid[q] & ((~w[q] & m) == 0u);
-        if (!NARROW) pass |= valid[q] & (key[q] == EMPTY64);  // the out-of-band key is not in the filter
+        bool pass = (~w[q] & m) == 0u;
+        if (NARROW) pass &= (key[q] >> 32) == 0;
+        else pass |= key[q] == EMPTY64;  // the out-of-band key is not in the filter
         surv |= pass ? (1u << q) : 0u;
       }
+      surv &= valid;
     }
     // ---- compact the tile's survivors into the warp queue (one scan per tile)
     const uint32_t c = __popc(surv);
@@ -351,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
       if (lane >= d) incl += o;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) continue;  // warp-uniform
+    if (total == 0) return;  // warp-uniform
     if (qt - qh + total <= (uint32_t)PROBE_QCAP) {
       uint32_t pos = qt + incl - c;
 #pragma unroll
@@ -373,6 +367,28 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
         if ((surv >> q) & 1u) cnt += lookup(key[q], SKIP) ? 1u : 0u;
       }
     }
+  };
+
+  // register double buffering, unrolled by two so that the buffers never have to be copied: the next
+  // tile's keys are requested before the current tile is processed, so the HBM latency of the key
+  // stream overlaps the filter / table work
+  unsigned long long ka[PROBE_KPT], kb[PROBE_KPT];
+  uint32_t va = 0, vb = 0;
+  auto fetch = [&](uint64_t tile, unsigned long long (&k)[PROBE_KPT]) -> uint32_t {
+    const uint64_t tb = tile * TILE;
+    return load_tile<THREADS>(pk, np, tb, vec_ok && tb + TILE <= np, k);
+  };
+  uint64_t tile = blockIdx.x;
+  if (tile < ntiles) va = fetch(tile, ka);
+  while (tile < ntiles) {
+    const uint64_t t1 = tile + gridDim.x;
+    if (t1 < ntiles) vb = fetch(t1, kb);
+    do_tile(ka, va);
+    if (t1 >= ntiles) break;
+    const uint64_t t2 = t1 + gridDim.x;
+    if (t2 < ntiles) va = fetch(t2, ka);
+    do_tile(kb, vb);
+    tile = t2;
   }
   // drain the remainder (< 32 survivors)
   __syncwarp();
@@ -417,7 +433,9 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 3)
     unsigned long long key[PROBE_KPT];
     bool valid[PROBE_KPT];
     const bool vec = vec_ok && tbase + TILE <= np;
-    load_tile<THREADS>(pk, np, tbase, vec, key, valid);
+    const uint32_t vmask = load_tile<THREADS>(pk, np, tbase, vec, key);
+#pragma unroll
+    for (int q = 0; q < PROBE_KPT; ++q) valid[q] = (vmask >> q) & 1u;
 
     using val_t = typename std::conditional<NARROW, uint32_t, unsigned long long>::type;
     val_t val[PROBE_KPT];
