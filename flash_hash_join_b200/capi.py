@@ -184,3 +184,47 @@ def generate_g2(side: str, N: int, ny: int, match_pct: int, seed: int, start: in
     vals = DeviceArray(count) if side == "build" else None
     check(lib().fj_generate_g2(0 if side == "build" else 1, N, ny, match_pct, seed, start, count, keys.ptr, vals.ptr if vals else None))
     return (keys, vals) if vals is not None else keys
+
+
+# ---- multi-GPU (one process per GPU) -----------------------------------------------------------------
+def comm_unique_id() -> bytes:
+    buf = (C.c_ubyte * 128)()
+    check(lib().fj_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(rank: int, world: int, ident: bytes | None = None) -> None:
+    """fj_comm_init.  `ident` is the 128-byte NCCL id produced by rank 0 (comm_unique_id) and carried to the
+    other ranks by the caller (torch.distributed, MPI, a file ...); a single-rank communicator makes its own."""
+    if ident is None:
+        if world != 1:
+            raise ValueError("ident is required when world > 1")
+        ident = comm_unique_id()
+    check(lib().fj_comm_init(rank, world, ident))
+
+
+def comm_destroy() -> None:
+    check(lib().fj_comm_destroy())
+
+
+def join_dist(mode: int, algo: int, flags: int, root: int, build_keys, build_values, probe_keys):
+    """fj_join_dist_u64 on this rank's slices (numpy or DeviceArray).  Returns (global matches, local matches,
+    seconds, stats dict)."""
+    keep, ptrs, sizes, dev = [], [], [], []
+    for x in (build_keys, build_values, probe_keys):
+        r = _ptr(x)
+        ptrs.append(r[0]); sizes.append(r[1]); dev.append(r[2])
+        if len(r) > 3:
+            keep.append(r[3])
+    if len(set(dev)) != 1:
+        raise ValueError("inputs must be all host arrays or all DeviceArray")
+    if sizes[0] != sizes[1]:
+        raise ValueError("build_values and build_keys differ in length")
+    if dev[0]:
+        flags |= FLAG_DEVICE_INPUTS
+    g, l = C.c_uint64(0), C.c_uint64(0)
+    sec = C.c_double(0.0)
+    st = Stats()
+    check(lib().fj_join_dist_u64(mode, algo, flags, root, ptrs[0], ptrs[1], sizes[0], ptrs[2], sizes[2], C.byref(g), C.byref(l),
+                                 C.byref(sec), C.byref(st)))
+    return int(g.value), int(l.value), float(sec.value), st.as_dict()

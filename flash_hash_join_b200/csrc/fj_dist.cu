@@ -124,4 +124,16 @@ fj_status_t dist_alltoallv_bytes(DistState& d, const void* send, const uint64_t*
   return 0;
 }
 
+fj_status_t dist_exchange(DistState& d, const DistMsg* sends, size_t n_sends, const DistMsg* recvs, size_t n_recvs,
+                          cudaStream_t st) {
+  ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);
+  FJ_NCCL(g_api.GroupStart());
+  for (size_t i = 0; i < n_sends; ++i)
+    if (sends[i].bytes) FJ_NCCL(g_api.Send(sends[i].ptr, sends[i].bytes, ncclUint8, sends[i].peer, comm, st));
+  for (size_t i = 0; i < n_recvs; ++i)
+    if (recvs[i].bytes) FJ_NCCL(g_api.Recv(recvs[i].ptr, recvs[i].bytes, ncclUint8, recvs[i].peer, comm, st));
+  FJ_NCCL(g_api.GroupEnd());
+  return 0;
+}
+
 }  // namespace fj

@@ -31,4 +31,11 @@ fj_status_t dist_allgather_u64(DistState& d, const void* send, void* recv, size_
 fj_status_t dist_alltoallv_bytes(DistState& d, const void* send, const uint64_t* send_offs, const uint64_t* send_counts,
                                  void* recv, const uint64_t* recv_offs, const uint64_t* recv_counts, cudaStream_t st);
 
+// grouped point-to-point exchange: every message of `sends` is ncclSend to its peer, every message of `recvs`
+// ncclRecv from its peer, all inside one ncclGroupStart/End.  Messages between the same pair of ranks are
+// matched in list order.
+struct DistMsg { int peer; void* ptr; uint64_t bytes; };
+fj_status_t dist_exchange(DistState& d, const DistMsg* sends, size_t n_sends, const DistMsg* recvs, size_t n_recvs,
+                          cudaStream_t st);
+
 }  // namespace fj

@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/flashjoin_b200.h"
 #include "fj_dist.h"
@@ -100,7 +101,7 @@ struct Engine {
   bool inited = false;
   DeviceInfo di;
   cudaStream_t st = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[12] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases
   Ctl* h_ctl = nullptr;  // pinned
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
   DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush;
@@ -121,6 +122,8 @@ struct Engine {
     cfg["narrow"] = 1;
     cfg["join3"] = 1;  // packed rows, two radix passes: collision-free pipelined k_join3 (0 = k_join)
     cfg["chunk_rows"] = 1 << 24;
+    cfg["shuffle_virtual_ranks"] = 1;  // > 1: every rank owns that many shuffle destinations (exercises the
+                                       // multi-destination scatter / exchange layout on few GPUs)
   }
 
   fj_status init(int device);
@@ -130,9 +133,16 @@ struct Engine {
   fj_status attempt_scalar(unsigned flags, bool narrow, bool exact, const unsigned long long* bk,
                            const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
                            uint64_t idx_base, fj_stats* s);
+  // flat != nullptr: both sides are already in partition-element format (rows received from the multi-GPU
+  // shuffle, holes included): flat->b / flat->p replace bk,bv / pk and every pass is a stage-2 pass
+  struct FlatInput { const void* b; uint64_t nb; const void* p; uint64_t np; };
   fj_status attempt_radix(unsigned flags, const RadixPlan& pl, const unsigned long long* bk,
                           const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
-                          fj_stats* s);
+                          fj_stats* s, const FlatInput* flat = nullptr);
+  fj_status join_shuffle(int algo, unsigned jflags, const unsigned long long* d_bk, const unsigned long long* d_bv,
+                         uint64_t nb, const unsigned long long* d_pk, uint64_t np, fj_stats* s, uint64_t* total);
+  fj_status finish_attempt(unsigned flags, fj_stats* s);
+  DevBuf send_b, send_p, recv_b, recv_p, shuf_cur, shuf_meta, exp_bk, exp_bv, exp_pk, all_bk, all_bv;
   fj_status join_device(int algo, unsigned flags, const unsigned long long* bk, const unsigned long long* bv,
                         uint64_t nb, const unsigned long long* pk, uint64_t np, uint64_t idx_base, fj_stats* s);
   fj_status join(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb, const uint64_t* pk,
@@ -193,7 +203,8 @@ void Engine::shutdown() {
   dist_destroy(dist);
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
-                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &dist_scratch})
+                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &dist_scratch, &send_b, &send_p, &recv_b,
+                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv})
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
@@ -366,7 +377,7 @@ fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const 
 // ---- one attempt on the radix path -------------------------------------------------------------
 fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsigned long long* bk,
                                 const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
-                                fj_stats* s) {
+                                fj_stats* s, const FlatInput* flat) {
   const bool mat = flags & FJ_FLAG_MATERIALIZE;
   const bool two = pl.bits2 > 0;
   const size_t tb = radix_elem_bytes(true, pl.narrow), tp = radix_elem_bytes(false, pl.narrow);
@@ -376,9 +387,9 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   }
   FJ_TRY(part_b_b.ensure((size_t)pl.P * pl.cap2_b * tb));
   FJ_TRY(part_b_p.ensure((size_t)pl.P * pl.cap2_p * tp));
-  // cursor layout: [A build F1][A probe F1][B build P][B probe P]
+  // cursor layout: [A build F1][A probe F1][B build P][B probe P][flat build count][flat probe count]
   const size_t ncur = 2 * (size_t)pl.F1 + 2 * (size_t)pl.P;
-  FJ_TRY(cursors.ensure(ncur * 4));
+  FJ_TRY(cursors.ensure((ncur + 2) * 4));
   uint32_t* cur_a_b = cursors.as<uint32_t>();
   uint32_t* cur_a_p = cur_a_b + pl.F1;
   uint32_t* cur_b_b = cur_a_p + pl.F1;
@@ -394,27 +405,42 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
 
   ScatterArgs a;
   a.ctl = d_ctl;
+  int stage = 1;
+  if (flat) {  // rows that arrived from the shuffle: one flat "partition" per side
+    if (flat->nb > 0xffffffffull || flat->np > 0xffffffffull)
+      return set_err(FJ_ERR_BAD_ARG, "more than 2^32 - 1 rows on one rank after the shuffle");
+    uint32_t* flat_cnt = cur_b_p + pl.P;
+    const uint32_t hc[2] = {(uint32_t)flat->nb, (uint32_t)flat->np};
+    FJ_CUDA(cudaMemcpyAsync(flat_cnt, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+    stage = 2;
+    a.in_nparts = 1;
+  }
+  auto first_pass = [&](bool build, void* out, uint32_t* cur, uint64_t cap, int shift, uint32_t fan) {
+    if (flat) {
+      a.in_part = build ? flat->b : flat->p;
+      a.in_counts = cur_b_p + pl.P + (build ? 0 : 1);
+      a.in_cap = a.n_upper = build ? flat->nb : flat->np;
+    } else {
+      a.in_keys = build ? bk : pk;
+      a.in_vals = build ? bv : nullptr;
+      a.n = build ? nb : np;
+    }
+    a.out = out; a.out_cursor = cur; a.out_cap = cap; a.shift = shift; a.fan = fan;
+    if (!flat || a.in_cap) launch_scatter(build, pl.narrow, stage, a, di, st, &launches);
+  };
   if (!two) {
-    a.in_keys = bk; a.in_vals = bv; a.n = nb;
-    a.out = part_b_b.p; a.out_cursor = cur_b_b; a.out_cap = pl.cap2_b; a.shift = 32 - pl.bits; a.fan = pl.P;
-    launch_scatter(true, pl.narrow, 1, a, di, st, &launches);
-    a.in_keys = pk; a.in_vals = nullptr; a.n = np;
-    a.out = part_b_p.p; a.out_cursor = cur_b_p; a.out_cap = pl.cap2_p;
-    launch_scatter(false, pl.narrow, 1, a, di, st, &launches);
+    first_pass(true, part_b_b.p, cur_b_b, pl.cap2_b, 32 - pl.bits, pl.P);
+    first_pass(false, part_b_p.p, cur_b_p, pl.cap2_p, 32 - pl.bits, pl.P);
   } else {
-    a.in_keys = bk; a.in_vals = bv; a.n = nb;
-    a.out = part_a_b.p; a.out_cursor = cur_a_b; a.out_cap = pl.cap1_b; a.shift = 32 - pl.bits1; a.fan = pl.F1;
-    launch_scatter(true, pl.narrow, 1, a, di, st, &launches);
-    a.in_keys = pk; a.in_vals = nullptr; a.n = np;
-    a.out = part_a_p.p; a.out_cursor = cur_a_p; a.out_cap = pl.cap1_p;
-    launch_scatter(false, pl.narrow, 1, a, di, st, &launches);
+    first_pass(true, part_a_b.p, cur_a_b, pl.cap1_b, 32 - pl.bits1, pl.F1);
+    first_pass(false, part_a_p.p, cur_a_p, pl.cap1_p, 32 - pl.bits1, pl.F1);
     ScatterArgs b;
     b.ctl = d_ctl;
     b.shift = 32 - pl.bits; b.fan = pl.F2; b.in_nparts = pl.F1;
-    b.in_part = part_a_b.p; b.in_counts = cur_a_b; b.in_cap = pl.cap1_b; b.n_upper = nb;
+    b.in_part = part_a_b.p; b.in_counts = cur_a_b; b.in_cap = pl.cap1_b; b.n_upper = flat ? flat->nb : nb;
     b.out = part_b_b.p; b.out_cursor = cur_b_b; b.out_cap = pl.cap2_b;
     launch_scatter(true, pl.narrow, 2, b, di, st, &launches);
-    b.in_part = part_a_p.p; b.in_counts = cur_a_p; b.in_cap = pl.cap1_p; b.n_upper = np;
+    b.in_part = part_a_p.p; b.in_counts = cur_a_p; b.in_cap = pl.cap1_p; b.n_upper = flat ? flat->np : np;
     b.out = part_b_p.p; b.out_cursor = cur_b_p; b.out_cap = pl.cap2_p;
     launch_scatter(false, pl.narrow, 2, b, di, st, &launches);
   }
@@ -429,7 +455,7 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
   if (pl.join3) launch_join3(mat, j, 32 - pl.bits, di, st, &launches);
   else launch_join(pl.narrow, mat, j, st, &launches);
-  if (!pl.narrow) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
+  if (!pl.narrow && !flat) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   FJ_CUDA(cudaStreamSynchronize(st));
@@ -446,6 +472,19 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   s->dedup_exact = 0;
   s->radix_bits1 = pl.bits1;
   s->radix_bits2 = pl.bits2;
+  return FJ_OK;
+}
+
+fj_status Engine::finish_attempt(unsigned flags, fj_stats* s) {
+  s->matches = h_ctl->match_count;
+  if (flags & FJ_FLAG_MATERIALIZE) {
+    if (h_ctl->out_cursor != h_ctl->match_count)
+      return set_err(FJ_ERR_STATE, "internal: pair cursor %llu != match count %llu", (unsigned long long)h_ctl->out_cursor,
+                     (unsigned long long)h_ctl->match_count);
+    pairs_valid = true;
+    pairs_n = h_ctl->match_count;
+    pairs_idx = (flags & FJ_FLAG_PROBE_IDX) != 0;
+  }
   return FJ_OK;
 }
 
@@ -478,16 +517,7 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
     if ((f & CTL_NEED_WIDE) && narrow) { narrow = false; continue; }
     if ((f & CTL_OVERFLOW) && path == FJ_ALGO_RADIX) { path = FJ_ALGO_SCALAR; continue; }
     if ((f & CTL_DUP) && !exact) { exact = true; narrow = false; path = FJ_ALGO_SCALAR; continue; }
-    s->matches = h_ctl->match_count;
-    if (flags & FJ_FLAG_MATERIALIZE) {
-      if (h_ctl->out_cursor != h_ctl->match_count)
-        return set_err(FJ_ERR_STATE, "internal: pair cursor %llu != match count %llu", (unsigned long long)h_ctl->out_cursor,
-                       (unsigned long long)h_ctl->match_count);
-      pairs_valid = true;
-      pairs_n = h_ctl->match_count;
-      pairs_idx = (flags & FJ_FLAG_PROBE_IDX) != 0;
-    }
-    return FJ_OK;
+    return finish_attempt(flags, s);
   }
   return set_err(FJ_ERR_STATE, "internal: join did not converge after 5 attempts (flags %u)", h_ctl->flags);
 }
@@ -534,6 +564,258 @@ fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint6
   if (out_seconds) *out_seconds = s.device_s;
   if (stats) *stats = s;
   return FJ_OK;
+}
+
+// ---- SHUFFLE (large build side, BASELINE.json configs[2] at G > 1 and configs[4]) ---------------
+// Every rank holds a slice of BOTH sides.  Rows are hash-partitioned by destination rank with the same
+// pipelined scatter kernel the local radix passes use (destination digit = low 16 hash bits range-reduced,
+// independent of the top bits the local passes consume), already narrowed to the packed partition format
+// when the data allows (12 instead of 24 bytes per build+probe row pair cross NVLink), exchanged with one
+// grouped ncclSend/ncclRecv all-to-all-v, and joined locally on the receiving rank straight from the
+// received partition-format rows.  Equal keys meet on exactly one rank, so local results simply add up.
+fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long long* d_bk, const unsigned long long* d_bv,
+                               uint64_t nb, const unsigned long long* d_pk, uint64_t np, fj_stats* s, uint64_t* total) {
+  const int W = dist.world, R = dist.rank;
+  int V = (int)std::max<int64_t>(1, cfg["shuffle_virtual_ranks"]);
+  if (W * V > 256) V = std::max(1, 256 / W);
+  if (W > 256) return set_err(FJ_ERR_BAD_ARG, "shuffle supports at most 256 ranks");
+  const uint32_t F = (uint32_t)(W * V);
+  const bool mat = jflags & FJ_FLAG_MATERIALIZE;
+  bool narrow = !(jflags & FJ_FLAG_FORCE_WIDE) && cfg["narrow"] != 0;
+  Ctl* d_ctl = ctl.as<Ctl>();
+  pairs_valid = false;
+  const size_t M = 8 + 2 * (size_t)F;  // 64-bit words of per-rank metadata
+  std::vector<uint64_t> meta(M), all(M * (size_t)W);
+  FJ_TRY(shuf_meta.ensure((M + M * W) * 8));
+  uint64_t* d_meta = shuf_meta.as<uint64_t>();
+  double comm_ms = 0.0, part_ms = 0.0;
+
+  for (int attempt = 1; attempt <= 3; ++attempt) {
+    // ---- 1. scatter the local rows by destination
+    const size_t tb = radix_elem_bytes(true, narrow), tp = radix_elem_bytes(false, narrow);
+    const uint64_t cap_sb = round4(nb + (uint64_t)scatter_pad_rows(true, narrow) * (nb / scatter_tile_rows(true, narrow) + 1) + 16);
+    const uint64_t cap_sp = round4(np + (uint64_t)scatter_pad_rows(false, narrow) * (np / scatter_tile_rows(false, narrow) + 1) + 16);
+    FJ_TRY(send_b.ensure((size_t)F * cap_sb * tb));
+    FJ_TRY(send_p.ensure((size_t)F * cap_sp * tp));
+    FJ_TRY(shuf_cur.ensure(2 * (size_t)F * 4));
+    uint32_t* cur_sb = shuf_cur.as<uint32_t>();
+    uint32_t* cur_sp = cur_sb + F;
+    int launches = 0;
+    FJ_CUDA(cudaEventRecord(ev[8], st));
+    launch_init_ctl(d_ctl, st);
+    ++launches;
+    FJ_CUDA(cudaMemsetAsync(shuf_cur.p, 0, 2 * (size_t)F * 4, st));
+    ScatterArgs a;
+    a.ctl = d_ctl; a.shift = -1; a.fan = F;
+    if (nb) {
+      a.in_keys = d_bk; a.in_vals = d_bv; a.n = nb; a.out = send_b.p; a.out_cursor = cur_sb; a.out_cap = cap_sb;
+      launch_scatter(true, narrow, 1, a, di, st, &launches);
+    }
+    if (np) {
+      a.in_keys = d_pk; a.in_vals = nullptr; a.n = np; a.out = send_p.p; a.out_cursor = cur_sp; a.out_cap = cap_sp;
+      launch_scatter(false, narrow, 1, a, di, st, &launches);
+    }
+    FJ_CUDA(cudaEventRecord(ev[9], st));
+    std::vector<uint32_t> h_cur(2 * (size_t)F);
+    FJ_CUDA(cudaMemcpyAsync(h_cur.data(), shuf_cur.p, 2 * (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    FJ_CUDA(cudaGetLastError());
+    part_ms += ms(8, 9);
+    s->kernel_launches += launches;
+    // the out-of-band key (wide rows only): first build row that carries it, and its value
+    const unsigned long long srow = h_ctl->sentinel_row;
+    unsigned long long sval = 0;
+    if (!narrow && srow != EMPTY64) FJ_CUDA(cudaMemcpy(&sval, d_bv + srow, 8, cudaMemcpyDeviceToHost));
+    const unsigned long long my_sent_probes = narrow ? 0ull : h_ctl->sentinel_probes;
+
+    // ---- 2. everybody learns everybody's flags and send counts
+    meta[0] = h_ctl->flags;
+    meta[1] = (narrow || srow == EMPTY64) ? EMPTY64 : (((uint64_t)R << 40) | srow);  // global keep-first order: (rank, row)
+    meta[2] = sval;
+    meta[3] = my_sent_probes;
+    meta[4] = nb;
+    meta[5] = np;
+    meta[6] = meta[7] = 0;
+    for (uint32_t d = 0; d < F; ++d) { meta[8 + d] = h_cur[d]; meta[8 + F + d] = h_cur[F + d]; }
+    FJ_CUDA(cudaEventRecord(ev[10], st));
+    FJ_CUDA(cudaMemcpyAsync(d_meta, meta.data(), M * 8, cudaMemcpyHostToDevice, st));
+    FJ_TRY(dist_allgather_u64(dist, d_meta, d_meta + M, M, st));
+    FJ_CUDA(cudaMemcpyAsync(all.data(), d_meta + M, M * W * 8, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    unsigned any = 0;
+    for (int r = 0; r < W; ++r) any |= (unsigned)all[(size_t)r * M];
+    if ((any & CTL_NEED_WIDE) && narrow) {  // some rank holds a row that does not fit 32|32: everybody re-runs wide
+      FJ_CUDA(cudaEventRecord(ev[11], st));
+      FJ_CUDA(cudaEventSynchronize(ev[11]));
+      comm_ms += ms(10, 11);
+      narrow = false;
+      continue;
+    }
+    if (any & CTL_OVERFLOW) return set_err(FJ_ERR_STATE, "internal: shuffle send region overflowed");
+    s->attempts = attempt;
+
+    // ---- 3. all-to-all-v of the partition-format rows
+    uint64_t nb_recv = 0, np_recv = 0;
+    std::vector<DistMsg> sends, recvs;
+    for (uint32_t d = 0; d < F; ++d) {
+      const int peer = (int)(d / V);
+      sends.push_back({peer, send_b.as<char>() + (size_t)d * cap_sb * tb, (uint64_t)h_cur[d] * tb});
+    }
+    for (uint32_t d = 0; d < F; ++d) {
+      const int peer = (int)(d / V);
+      sends.push_back({peer, send_p.as<char>() + (size_t)d * cap_sp * tp, (uint64_t)h_cur[F + d] * tp});
+    }
+    for (int r = 0; r < W; ++r)
+      for (int v = 0; v < V; ++v) nb_recv += all[(size_t)r * M + 8 + (size_t)R * V + v];
+    for (int r = 0; r < W; ++r)
+      for (int v = 0; v < V; ++v) np_recv += all[(size_t)r * M + 8 + F + (size_t)R * V + v];
+    FJ_TRY(recv_b.ensure(nb_recv * tb + 64));
+    FJ_TRY(recv_p.ensure(np_recv * tp + 64));
+    {
+      uint64_t ob = 0, op = 0;
+      for (int r = 0; r < W; ++r)
+        for (int v = 0; v < V; ++v) {
+          const uint64_t c = all[(size_t)r * M + 8 + (size_t)R * V + v];
+          recvs.push_back({r, recv_b.as<char>() + ob * tb, c * tb});
+          ob += c;
+        }
+      for (int r = 0; r < W; ++r)
+        for (int v = 0; v < V; ++v) {
+          const uint64_t c = all[(size_t)r * M + 8 + F + (size_t)R * V + v];
+          recvs.push_back({r, recv_p.as<char>() + op * tp, c * tp});
+          op += c;
+        }
+    }
+    FJ_TRY(dist_exchange(dist, sends.data(), sends.size(), recvs.data(), recvs.size(), st));
+    FJ_CUDA(cudaEventRecord(ev[11], st));
+    FJ_CUDA(cudaEventSynchronize(ev[11]));
+    comm_ms += ms(10, 11);
+    s->h2d_bytes += 0;
+
+    // the out-of-band key, resolved globally: the value of the first build row (rank-major) that carries it
+    bool sent_exists = false;
+    unsigned long long sent_val = 0;
+    {
+      uint64_t best = EMPTY64;
+      for (int r = 0; r < W; ++r) {
+        const uint64_t key = all[(size_t)r * M + 1];
+        if (key < best) { best = key; sent_val = all[(size_t)r * M + 2]; sent_exists = true; }
+      }
+    }
+
+    // ---- 4. local join of the received rows
+    FJ_TRY(ensure_out(jflags, np_recv + my_sent_probes + 1));
+    bool ran = false;
+    if (nb_recv && np_recv) {
+      RadixPlan plan = plan_radix(nb_recv, np_recv, narrow);
+      int path = (algo == FJ_ALGO_SCALAR || !plan.ok) ? FJ_ALGO_SCALAR : FJ_ALGO_RADIX;
+      for (int local = 0; local < 2 && !ran; ++local) {
+        if (path == FJ_ALGO_RADIX) {
+          const FlatInput fl{recv_b.p, nb_recv, recv_p.p, np_recv};
+          FJ_TRY(attempt_radix(jflags, plan, nullptr, nullptr, 0, nullptr, 0, s, &fl));
+          if (h_ctl->flags & CTL_OVERFLOW) { path = FJ_ALGO_SCALAR; continue; }  // skewed partition: global table instead
+          ran = true;
+        } else {
+          // partition-format rows -> plain columns (holes dropped), then the global-table path
+          FJ_TRY(exp_bk.ensure(nb_recv * 8));
+          FJ_TRY(exp_bv.ensure(nb_recv * 8));
+          FJ_TRY(exp_pk.ensure(np_recv * 8));
+          unsigned long long* d_cnt2 = reinterpret_cast<unsigned long long*>(d_meta);
+          int l2 = 0;
+          FJ_CUDA(cudaMemsetAsync(d_cnt2, 0, 16, st));
+          launch_expand(true, narrow, recv_b.p, nb_recv, exp_bk.as<unsigned long long>(), exp_bv.as<unsigned long long>(), d_cnt2,
+                        di, st, &l2);
+          launch_expand(false, narrow, recv_p.p, np_recv, exp_pk.as<unsigned long long>(), nullptr, d_cnt2 + 1, di, st, &l2);
+          unsigned long long h_cnt2[2] = {0, 0};
+          FJ_CUDA(cudaMemcpyAsync(h_cnt2, d_cnt2, 16, cudaMemcpyDeviceToHost, st));
+          FJ_CUDA(cudaStreamSynchronize(st));
+          s->kernel_launches += l2;
+          if (h_cnt2[0] && h_cnt2[1]) {
+            FJ_TRY(attempt_scalar(jflags & ~FJ_FLAG_PROBE_IDX, narrow, false, exp_bk.as<unsigned long long>(),
+                                  exp_bv.as<unsigned long long>(), h_cnt2[0], exp_pk.as<unsigned long long>(), h_cnt2[1], 0, s));
+            ran = true;
+          }
+          break;
+        }
+      }
+    }
+    if (!ran) {  // nothing to join on this rank: still a defined control block (the collectives below need every rank)
+      int l3 = 0;
+      launch_init_ctl(d_ctl, st);
+      ++l3;
+      s->kernel_launches += l3;
+      s->path = FJ_ALGO_RADIX;
+      s->narrow = narrow ? 1 : 0;
+    }
+    if (sent_exists && my_sent_probes) {
+      int l4 = 0;
+      launch_emit_sentinel_value(d_ctl, sent_val, my_sent_probes, out_keys.as<unsigned long long>(), out_vals.as<unsigned long long>(),
+                                 mat, st, &l4);
+      s->kernel_launches += l4;
+    }
+    FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    FJ_CUDA(cudaGetLastError());
+
+    // ---- 5. duplicates anywhere?  keep-first is defined on the GLOBAL build order (rank-major), which the
+    // shuffle does not preserve: gather the whole build side on every rank and run the exact local join of
+    // the rank's own probe rows against it.  Slow, rare (every BASELINE.json config has unique build keys).
+    uint64_t flag2[2] = {(uint64_t)((h_ctl->flags & CTL_DUP) ? 1 : 0), 0};
+    std::vector<uint64_t> all2(2 * (size_t)W);
+    FJ_CUDA(cudaEventRecord(ev[10], st));
+    FJ_CUDA(cudaMemcpyAsync(d_meta, flag2, 16, cudaMemcpyHostToDevice, st));
+    FJ_TRY(dist_allgather_u64(dist, d_meta, d_meta + 2, 2, st));
+    FJ_CUDA(cudaMemcpyAsync(all2.data(), d_meta + 2, 16 * (size_t)W, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaEventRecord(ev[11], st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    comm_ms += ms(10, 11);
+    bool any_dup = false;
+    for (int r = 0; r < W; ++r) any_dup |= all2[2 * (size_t)r] != 0;
+    if (any_dup) {
+      uint64_t nb_all = 0, my_off = 0;
+      for (int r = 0; r < W; ++r) { if (r == R) my_off = nb_all; nb_all += all[(size_t)r * M + 4]; }
+      FJ_TRY(all_bk.ensure(std::max<uint64_t>(nb_all, 1) * 8));
+      FJ_TRY(all_bv.ensure(std::max<uint64_t>(nb_all, 1) * 8));
+      FJ_CUDA(cudaEventRecord(ev[10], st));
+      if (nb) {
+        FJ_CUDA(cudaMemcpyAsync(all_bk.as<unsigned long long>() + my_off, d_bk, nb * 8, cudaMemcpyDeviceToDevice, st));
+        FJ_CUDA(cudaMemcpyAsync(all_bv.as<unsigned long long>() + my_off, d_bv, nb * 8, cudaMemcpyDeviceToDevice, st));
+      }
+      uint64_t off = 0;
+      for (int r = 0; r < W; ++r) {
+        const uint64_t c = all[(size_t)r * M + 4];
+        if (c) {
+          FJ_TRY(dist_broadcast_u64(dist, all_bk.as<unsigned long long>() + off, c, r, st));
+          FJ_TRY(dist_broadcast_u64(dist, all_bv.as<unsigned long long>() + off, c, r, st));
+        }
+        off += c;
+      }
+      FJ_CUDA(cudaEventRecord(ev[11], st));
+      FJ_CUDA(cudaEventSynchronize(ev[11]));
+      comm_ms += ms(10, 11);
+      FJ_TRY(join_device(FJ_ALGO_SCALAR, jflags, all_bk.as<unsigned long long>(), all_bv.as<unsigned long long>(), nb_all, d_pk, np,
+                         0, s));
+    } else {
+      FJ_TRY(finish_attempt(jflags, s));
+    }
+
+    // ---- 6. global count
+    uint64_t cnt2[2] = {s->matches, 0};
+    FJ_CUDA(cudaEventRecord(ev[10], st));
+    FJ_CUDA(cudaMemcpyAsync(d_meta, cnt2, 16, cudaMemcpyHostToDevice, st));
+    FJ_TRY(dist_allreduce_sum_u64(dist, d_meta, d_meta + 2, 1, st));
+    unsigned long long tot = 0;
+    FJ_CUDA(cudaMemcpyAsync(&tot, d_meta + 2, 8, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaEventRecord(ev[11], st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    comm_ms += ms(10, 11);
+    *total = tot;
+    s->comm_s += comm_ms * 1e-3;
+    s->partition_s += part_ms * 1e-3;
+    return FJ_OK;
+  }
+  return set_err(FJ_ERR_STATE, "internal: shuffle join did not converge");
 }
 
 // ---- multi-GPU drivers (one process per GPU) ---------------------------------------------------
@@ -606,7 +888,37 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
     s.device_s += s.comm_s;
     *out_global = total;
   } else {
-    return set_err(FJ_ERR_STATE, "FJ_DIST_SHUFFLE is not implemented in this build");
+    if ((nb && (!bk || !bv))) return set_err(FJ_ERR_BAD_ARG, "NULL build pointer with non-zero length");
+    if (flags & FJ_FLAG_PROBE_IDX) return set_err(FJ_ERR_BAD_ARG, "FJ_FLAG_PROBE_IDX is not available in shuffle mode (rows move between ranks)");
+    const unsigned long long *d_bk, *d_bv, *d_pk;
+    if (dev_in) {
+      d_bk = reinterpret_cast<const unsigned long long*>(bk);
+      d_bv = reinterpret_cast<const unsigned long long*>(bv);
+      d_pk = reinterpret_cast<const unsigned long long*>(pk);
+    } else {
+      FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
+      FJ_TRY(in_bv.ensure(std::max<size_t>(nb, 1) * 8));
+      FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
+      const double th = now_s();
+      if (nb) {
+        FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyHostToDevice, st));
+        FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyHostToDevice, st));
+      }
+      if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+      FJ_CUDA(cudaStreamSynchronize(st));
+      s.h2d_s = now_s() - th;
+      s.h2d_bytes = (uint64_t)(2 * nb + np) * 8;
+      d_bk = in_bk.as<unsigned long long>();
+      d_bv = in_bv.as<unsigned long long>();
+      d_pk = in_pk.as<unsigned long long>();
+    }
+    FJ_CUDA(cudaEventRecord(ev[4], st));
+    uint64_t tot = 0;
+    FJ_TRY(join_shuffle(algo, jflags, d_bk, d_bv, nb, d_pk, np, &s, &tot));
+    FJ_CUDA(cudaEventRecord(ev[5], st));
+    FJ_CUDA(cudaEventSynchronize(ev[5]));
+    s.device_s = ms(4, 5) * 1e-3;  // whole distributed join on this rank, exchange included
+    *out_global = tot;
   }
   if (out_local) *out_local = s.matches;
   s.wall_s = now_s() - t0;

@@ -153,11 +153,16 @@ FJ_API fj_status fj_timer_stop(double* seconds);
  * No reference counterpart (hash_join.cpp is single-process, std::thread only).  The caller
  * distributes a 128-byte NCCL unique id produced by rank 0 (any transport: torch.distributed,
  * MPI, a file) and every rank calls fj_comm_init.
- *   fj_join_dist_u64, FJ_DIST_BROADCAST: build side given on rank `root` (nb may be 0 elsewhere) is
- *     ncclBroadcast to all ranks, each rank builds locally and probes ITS OWN probe slice
- *     (pk/np are rank-local); counts are summed with ncclAllReduce.  *out_matches = global count.
+ *   fj_join_dist_u64, FJ_DIST_BROADCAST: the build side lives on rank `root` (every rank passes the same
+ *     nb; bk/bv are only read on root and may be NULL elsewhere) and is ncclBroadcast to all ranks, each
+ *     rank builds locally and probes ITS OWN probe slice (pk/np are rank-local); counts are summed with
+ *     ncclAllReduce.  *out_matches_global = global count, *out_matches_local = this rank's.
  *   FJ_DIST_SHUFFLE: every rank passes its slice of BOTH sides; rows are hash-partitioned by
- *     destination rank, exchanged with grouped ncclSend/ncclRecv (all-to-all-v) and joined locally. */
+ *     destination rank (already narrowed to the packed partition format when the data allows),
+ *     exchanged with one grouped ncclSend/ncclRecv all-to-all-v and joined locally from the received
+ *     rows.  Duplicate build keys anywhere fall back to gathering the build side on every rank
+ *     (keep-first is defined on the rank-major global row order).  Materialized pairs stay on the
+ *     rank that produced them (fj_pairs_*).  FJ_FLAG_PROBE_IDX is not available in this mode. */
 enum { FJ_DIST_BROADCAST = 0, FJ_DIST_SHUFFLE = 1 };
 FJ_API fj_status fj_comm_unique_id(void* id128);
 FJ_API fj_status fj_comm_init(int rank, int world, const void* id128);

@@ -362,3 +362,91 @@ def test_c3_full_size_golden(fj, golden_cases):
     assert n == c["count"]
     n, _ = fj.hash_join_count(bk, bv, pk)
     assert n == c["count"]
+
+
+# ------------------------------------------------------------------------------------------------ shuffle (1 GPU)
+@pytest.fixture(scope="module")
+def comm1(capi):
+    """A single-rank communicator: the whole FJ_DIST_SHUFFLE machinery (destination scatter, self send/recv,
+    join from received partition-format rows) runs on one GPU; `shuffle_virtual_ranks` > 1 gives the rank
+    several destinations so that the multi-destination layout is exercised too."""
+    capi.check(capi.lib().fj_init(0))
+    capi.comm_init(0, 1)
+    yield capi
+    capi.config_set(shuffle_virtual_ranks=1)
+    capi.comm_destroy()
+
+
+def _shuffle_check(capi, bk, bv, pk, algos=None, expect=None):
+    n0, k0, v0 = expect if expect is not None else O.np_join(bk, bv, pk)
+    sp0 = O.sorted_pairs(k0, v0)
+    for algo in algos or (capi.ALGO_ADAPTIVE, capi.ALGO_SCALAR, capi.ALGO_RADIX):
+        for flags in (0, capi.FLAG_MATERIALIZE):
+            g, l, sec, st = capi.join_dist(capi.DIST_SHUFFLE, algo, flags, 0, bk, bv, pk)
+            assert g == l == n0, (algo, flags, g, l, n0, st)
+            if flags & capi.FLAG_MATERIALIZE:
+                assert np.array_equal(O.sorted_pairs(*capi.pairs()), sp0), (algo, st)
+    return st
+
+
+@pytest.mark.parametrize("virtual", [1, 4, 7])
+def test_shuffle_single_rank(comm1, virtual):
+    capi = comm1
+    capi.config_set(shuffle_virtual_ranks=virtual)
+    bk, bv, pk = g1(300_000, 60_000, 90)
+    st = _shuffle_check(capi, bk, bv, pk)
+    assert st["narrow"] == 1
+    # empty sides
+    e = np.empty(0, dtype=np.uint64)
+    for a, b, c in ((e, e, pk), (bk, bv, e), (e, e, e)):
+        g, l, _, _ = capi.join_dist(capi.DIST_SHUFFLE, capi.ALGO_ADAPTIVE, capi.FLAG_MATERIALIZE, 0, a, b, c)
+        assert g == 0 and capi.pairs()[0].size == 0
+    # rows that do not fit the packed format: the narrow attempt is abandoned on every rank
+    bv2 = bv.copy(); bv2[17] = 2**45
+    st = _shuffle_check(capi, bk, bv2, pk)
+    assert st["narrow"] == 0 and st["attempts"] == 2
+    # 64-bit keys incl. the out-of-band key 2^64-1 and key 0
+    E = 2**64 - 1
+    rng = np.random.default_rng(3)
+    wk = np.unique(np.concatenate([rng.integers(0, E, 40_000, dtype=np.uint64), np.array([0, E, 2**32], dtype=np.uint64)]))
+    wv = rng.integers(0, E, wk.size, dtype=np.uint64)
+    wp = np.concatenate([rng.choice(wk, 100_000), rng.integers(0, E, 50_000, dtype=np.uint64), np.array([E, E, 0], dtype=np.uint64)])
+    _shuffle_check(capi, wk, wv, wp)
+
+
+def test_shuffle_duplicate_build_keys_and_skew(comm1):
+    capi = comm1
+    capi.config_set(shuffle_virtual_ranks=4)
+    rng = np.random.default_rng(9)
+    bk = rng.integers(0, 5000, 60_000).astype(np.uint64)
+    bv = np.arange(60_000, dtype=np.uint64)
+    pk = rng.integers(0, 6000, 200_000).astype(np.uint64)
+    st = _shuffle_check(capi, bk, bv, pk, expect=O.join("radix", False, True, bk, bv, pk))
+    assert st["dedup_exact"] == 1
+    # all probe rows carry one key: one destination / one partition receives everything
+    bk = np.arange(1, 50_001, dtype=np.uint64)
+    _shuffle_check(capi, bk, bk * np.uint64(7), np.full(500_000, 4242, dtype=np.uint64))
+
+
+def test_shuffle_large_two_pass(comm1):
+    """Enough rows that the local join after the exchange takes two radix passes + k_join3."""
+    capi = comm1
+    capi.config_set(shuffle_virtual_ranks=2)
+    bk, bv, pk = g2(4_000_000, 4_000_000, 90)
+    g, l, sec, st = capi.join_dist(capi.DIST_SHUFFLE, capi.ALGO_ADAPTIVE, capi.FLAG_MATERIALIZE, 0, bk, bv, pk)
+    n0, k0, v0 = O.np_join(bk, bv, pk)
+    assert g == n0 and st["path"] == "radix" and st["radix_bits2"] > 0
+    assert np.array_equal(O.sorted_pairs(*capi.pairs()), O.sorted_pairs(k0, v0))
+
+
+def test_shuffle_dest_mirror(capi):
+    """flash_hash_join_b200.dist.shuffle_dest (numpy) is the device destination function: every key lands on
+    exactly one rank, so per-destination oracle joins add up to the global join."""
+    from flash_hash_join_b200.dist import shuffle_dest
+
+    bk, bv, pk = g1(200_000, 50_000, 90)
+    world = 4
+    db, dp = shuffle_dest(bk, world), shuffle_dest(pk, world)
+    total = sum(O.np_join(bk[db == r], bv[db == r], pk[dp == r])[0] for r in range(world))
+    assert total == O.np_join(bk, bv, pk)[0]
+    assert db.min() >= 0 and db.max() < world and np.bincount(db, minlength=world).min() > 0.2 * bk.size / world
