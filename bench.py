@@ -8,6 +8,9 @@ Workload (config.workload): BASELINE.json configs[1] — `flash_join_bloom` join
 rows vs y = 1e5 build rows, ~10 % probe match rate, per GPU (weak scaling: every GPU gets its own
 1e8-row probe slice; the 1e5-row build side lives on rank 0 and is ncclBroadcast inside the step).
 One "step" = one whole join: table clear + build + (broadcast) + probe + count (+ all-reduce).
+`--config C3` (flash_join_radix materialize, 1e8 x 1e8) is the large-build workload: at N > 1 both sides
+are split over the GPUs and joined with the NCCL all-to-all shuffle (strong scaling).  A default N = 1 run
+also times C3 and reports it under "other_configs" (the headline line stays C2).
 
   value      probe rows / second, whole job, inputs resident in HBM, device time (CUDA events on the
              engine's stream, bracketed by barrier + synchronize, max over ranks)
@@ -181,6 +184,7 @@ def main() -> None:
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the additional C3 measurement of a default N=1 run")
     ap.add_argument("--_cpu_worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3 and not args._cpu_worker and args.impl == "ours":
@@ -232,25 +236,8 @@ def main() -> None:
         dist.broadcast_object_list(ident, src=0)
         capi.check(L.fj_comm_init(rank, world, ident[0]))
 
-    N, ny, pct = w["N"], w["ny"], w["pct"]
-    n_total = N * world
-    algo = {"adaptive": capi.ALGO_ADAPTIVE, "scalar": capi.ALGO_SCALAR, "radix": capi.ALGO_RADIX}[w["algo"]]
-    flags = (capi.FLAG_BLOOM if w["bloom"] else 0) | (capi.FLAG_MATERIALIZE if w["mat"] else 0)
-    # inputs resident in HBM: every rank its own probe slice; the build side on every rank (used by rank 0 only when world > 1)
-    d_bk, d_bv = capi.generate_g2("build", n_total, ny, pct, SEED, 0, ny)
-    d_pk = capi.generate_g2("probe", n_total, ny, pct, SEED, rank * N, N)
-
-    def step_device():
-        n = C.c_uint64(0)
-        nl = C.c_uint64(0)
-        sec = C.c_double(0)
-        st = capi.Stats()
-        if world == 1:
-            capi.check(L.fj_join_u64(algo, flags | capi.FLAG_DEVICE_INPUTS, d_bk.ptr, d_bv.ptr, ny, d_pk.ptr, N, C.byref(n), C.byref(sec), C.byref(st)))
-        else:
-            capi.check(L.fj_join_dist_u64(capi.DIST_BROADCAST, algo, flags | capi.FLAG_DEVICE_INPUTS, 0, d_bk.ptr, d_bv.ptr, ny, d_pk.ptr, N,
-                                          C.byref(n), C.byref(nl), C.byref(sec), C.byref(st)))
-        return n.value, st
+    sampler = ClockSampler(local)
+    sampler.start()
 
     def barrier():
         capi.check(L.fj_device_synchronize())
@@ -266,81 +253,140 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        matches, _ = step_device()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
-    barrier()
-    capi.check(L.fj_timer_start())
-    launches = 0
-    probe_s, device_s, phases = [], [], {"clear_s": 0.0, "build_s": 0.0, "partition_s": 0.0, "probe_s": 0.0, "comm_s": 0.0}
-    for _ in range(args.steps):
-        matches, st = step_device()
-        launches += st.kernel_launches
-        probe_s.append(st.probe_s)
-        device_s.append(st.device_s)
-        for k in phases:
-            phases[k] += getattr(st, k)
-    t = C.c_double(0)
-    capi.check(L.fj_timer_stop(C.byref(t)))
-    barrier()
-    clocks = sampler.stop()
-    elapsed = max_over_ranks(t.value)
-    value = n_total * args.steps / elapsed
-    last = st.as_dict()
+    def measure(cfg_name: str, steps: int, warmup: int, want_e2e: bool) -> dict:
+        from flash_hash_join_b200.dist import row_slice
 
-    # roofline of the dominant kernel
-    peak, peak_src = measured_peak()
-    dom_s = statistics.mean(probe_s)
-    if w["mat"]:
-        alg_bytes_kernel = 8.0 * N + 16.0 * matches / world  # probe keys read + pairs written
-    else:
-        alg_bytes_kernel = 8.0 * N  # 8 B per probe row; build-side bytes belong to the build kernel
-    achieved = alg_bytes_kernel / dom_s * 1e-9
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text()).get(args.config, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_join (smem partition join)" if last["path"] == "radix" else "k_probe", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_kernel, "kernel_ms": dom_s * 1e3,
-                "whole_step_frac": (last["algorithmic_bytes"] / (elapsed / args.steps) * 1e-9) / peak}
+        w = WORKLOADS[cfg_name]
+        ny, pct = w["ny"], w["pct"]
+        shuffle = world > 1 and w["algo"] == "radix"  # large build side: both sides split, all-to-all shuffle
+        if shuffle:  # strong scaling: the named workload is split over the GPUs
+            n_total = w["N"]
+            p0, p1 = row_slice(n_total, world, rank)
+            b0, b1 = row_slice(ny, world, rank)
+            N = p1 - p0
+        else:        # weak scaling: every GPU gets its own probe slice of the named size, the build side is replicated
+            N = w["N"]
+            n_total = N * world
+            p0, b0, b1 = rank * N, 0, ny
+        nb_local = b1 - b0
+        algo = {"adaptive": capi.ALGO_ADAPTIVE, "scalar": capi.ALGO_SCALAR, "radix": capi.ALGO_RADIX}[w["algo"]]
+        flags = (capi.FLAG_BLOOM if w["bloom"] else 0) | (capi.FLAG_MATERIALIZE if w["mat"] else 0)
+        mode = capi.DIST_SHUFFLE if shuffle else capi.DIST_BROADCAST
+        # inputs resident in HBM
+        d_bk, d_bv = capi.generate_g2("build", n_total, ny, pct, SEED, b0, nb_local)
+        d_pk = capi.generate_g2("probe", n_total, ny, pct, SEED, p0, N)
 
-    # e2e: host (pinned) buffers through the reference-facing call
-    e2e = None
-    if not args.no_e2e:
-        h_bk, h_bv, h_pk = flash_join.pinned_empty(ny), flash_join.pinned_empty(ny), flash_join.pinned_empty(N)
-        capi.check(L.fj_memcpy_d2h(h_bk.ctypes.data, d_bk.ptr, ny * 8))
-        capi.check(L.fj_memcpy_d2h(h_bv.ctypes.data, d_bv.ptr, ny * 8))
-        capi.check(L.fj_memcpy_d2h(h_pk.ctypes.data, d_pk.ptr, N * 8))
-        e_steps = max(3, min(args.steps, 10))
-
-        def step_host():
-            if world == 1:
-                n, _sec = getattr(flash_join, w["entry"])(h_bk, h_bv, h_pk)  # the call a flash_join user makes
-                return n
+        def step_device():
             n = C.c_uint64(0)
-            capi.check(L.fj_join_dist_u64(capi.DIST_BROADCAST, algo, flags, 0, h_bk.ctypes.data, h_bv.ctypes.data, ny, h_pk.ctypes.data, N,
-                                          C.byref(n), None, None, None))
-            return n.value
+            nl = C.c_uint64(0)
+            sec = C.c_double(0)
+            st = capi.Stats()
+            if world == 1:
+                capi.check(L.fj_join_u64(algo, flags | capi.FLAG_DEVICE_INPUTS, d_bk.ptr, d_bv.ptr, ny, d_pk.ptr, N, C.byref(n), C.byref(sec), C.byref(st)))
+            else:
+                capi.check(L.fj_join_dist_u64(mode, algo, flags | capi.FLAG_DEVICE_INPUTS, 0, d_bk.ptr, d_bv.ptr, nb_local, d_pk.ptr, N,
+                                              C.byref(n), C.byref(nl), C.byref(sec), C.byref(st)))
+            return n.value, st
 
-        step_host()
+        for _ in range(warmup):
+            matches, _ = step_device()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            m2 = step_host()
-        capi.check(L.fj_device_synchronize())
-        dt = max_over_ranks(time.perf_counter() - t0)
+        capi.check(L.fj_timer_start())
+        launches = 0
+        dom_s = []
+        phases = {"clear_s": 0.0, "build_s": 0.0, "partition_s": 0.0, "probe_s": 0.0, "comm_s": 0.0}
+        for _ in range(steps):
+            matches, st = step_device()
+            launches += st.kernel_launches
+            dom_s.append(st.probe_s)
+            for k in phases:
+                phases[k] += getattr(st, k)
+        t = C.c_double(0)
+        capi.check(L.fj_timer_stop(C.byref(t)))
         barrier()
-        assert m2 == matches, (m2, matches)
-        e2e = {"value": n_total * e_steps / dt, "unit": "rows/s", "h2d_bytes_per_step": (2 * ny + N) * 8, "d2h_bytes_per_step": 48,
-               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "host_memory": "pinned (flash_join.pinned_empty)",
-               "api": f"flash_join.{w['entry']}" if world == 1 else "fj_join_dist_u64 (C ABI, host buffers)"}
-        del h_bk, h_bv, h_pk
+        elapsed = max_over_ranks(t.value)
+        value = n_total * steps / elapsed
+        last = st.as_dict()
+
+        # roofline of the dominant kernel (the probe / partition-join kernel of the step)
+        peak, peak_src = measured_peak()
+        kern_s = statistics.mean(dom_s)
+        if w["mat"]:
+            alg_bytes_kernel = 8.0 * N + 16.0 * last["matches"]  # probe keys read + pairs written by this rank
+        else:
+            alg_bytes_kernel = 8.0 * N  # 8 B per probe row; build-side bytes belong to the build kernel
+        achieved = alg_bytes_kernel / kern_s * 1e-9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(cfg_name, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        alg_step = (16.0 * ny + 8.0 * n_total + 16.0 * matches) if w["mat"] else 8.0 * (ny + n_total)
+        roofline = {"bound": "hbm", "kernel": "k_join3 (shared-memory partition join)" if last["path"] == "radix" else "k_probe_count",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes_kernel, "kernel_ms": kern_s * 1e3,
+                    "whole_step_frac": (alg_step / (elapsed / steps) * 1e-9) / (peak * world),
+                    "whole_step_algorithmic_bytes": alg_step}
+
+        # e2e: host (pinned) buffers through the reference-facing call
+        e2e = None
+        if want_e2e:
+            h_bk, h_bv, h_pk = flash_join.pinned_empty(nb_local), flash_join.pinned_empty(nb_local), flash_join.pinned_empty(N)
+            capi.check(L.fj_memcpy_d2h(h_bk.ctypes.data, d_bk.ptr, nb_local * 8))
+            capi.check(L.fj_memcpy_d2h(h_bv.ctypes.data, d_bv.ptr, nb_local * 8))
+            capi.check(L.fj_memcpy_d2h(h_pk.ctypes.data, d_pk.ptr, N * 8))
+            e_steps = max(3, min(steps, 10))
+
+            def step_host():
+                if world == 1:
+                    n, _sec = getattr(flash_join, w["entry"])(h_bk, h_bv, h_pk)  # the call a flash_join user makes
+                    return n
+                n = C.c_uint64(0)
+                capi.check(L.fj_join_dist_u64(mode, algo, flags, 0, h_bk.ctypes.data, h_bv.ctypes.data, nb_local, h_pk.ctypes.data, N,
+                                              C.byref(n), None, None, None))
+                return n.value
+
+            step_host()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                m2 = step_host()
+            capi.check(L.fj_device_synchronize())
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            assert m2 == matches, (m2, matches)
+            e2e = {"value": n_total * e_steps / dt, "unit": "rows/s", "h2d_bytes_per_step": (2 * nb_local + N) * 8, "d2h_bytes_per_step": 48,
+                   "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "host_memory": "pinned (flash_join.pinned_empty)",
+                   "api": f"flash_join.{w['entry']}" if world == 1 else "fj_join_dist_u64 (C ABI, host buffers)",
+                   "note": "result pairs of a materialize call stay in HBM (fj_pairs_fetch is a separate call); the count is read back"}
+            del h_bk, h_bv, h_pk
+        for x in (d_bk, d_bv, d_pk):
+            x.free()
+        if shuffle:
+            par = f"both sides split over {world} GPUs, rows hash-partitioned by destination, NCCL all-to-all-v, local radix join, count ncclAllReduce"
+        elif world > 1:
+            par = f"build side ncclBroadcast from rank 0, probe side split over {world} GPUs, count ncclAllReduce"
+        else:
+            par = "single GPU"
+        return {"w": w, "N": N, "n_total": n_total, "value": value, "elapsed": elapsed, "steps": steps, "matches": matches, "last": last,
+                "launches": launches, "roofline": roofline, "e2e": e2e, "scaling": "strong" if shuffle else "weak", "parallelism": par,
+                "phases": {k: v / steps * 1e3 for k, v in phases.items()}}
+
+    m = measure(args.config, args.steps, args.warmup, not args.no_e2e)
+    w, matches = m["w"], m["matches"]
+    other = None
+    if world == 1 and args.config == "C2" and not args.no_other:
+        try:
+            o = measure("C3", 5, 3, False)
+            other = {"C3": {"workload": o["w"]["desc"], "value": o["value"], "unit": "rows/s", "ms_per_step": o["elapsed"] / o["steps"] * 1e3,
+                            "matches": o["matches"], "path": o["last"]["path"], "radix_bits": [o["last"]["radix_bits1"], o["last"]["radix_bits2"]],
+                            "narrow_rows": bool(o["last"]["narrow"]), "phases_ms_per_step": o["phases"], "roofline": o["roofline"],
+                            "gpu_launches": o["launches"]}}
+        except Exception as e:  # never lose the headline line
+            other = {"C3": {"error": str(e)[:300]}}
+    clocks = sampler.stop()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -354,16 +400,18 @@ def main() -> None:
             cpu = {"value": None, "unit": "rows/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)[:200]}
 
     if rank == 0:
+        last = m["last"]
         line = {
-            "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "metric": metric, "value": m["value"], "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["elapsed"] / args.steps * 1e3, "higher_is_better": True, "scaling": m["scaling"], "vs_baseline": None, "dtype": "u64",
             "data": f"synthetic (G2 counter-based h2o join shape, seed {SEED}; generated in HBM)",
-            "config": {"workload": w["desc"], "entry_point": w["entry"], "rows_probe_per_gpu": N, "rows_build": ny, "match_pct": pct,
-                       "l2": f"inputs {8 * N / 1e6:.0f} MB per step > 126 MB L2 (no flush needed); table and Bloom filter are rebuilt every step",
-                       "parallelism": "single GPU" if world == 1 else f"build side ncclBroadcast from rank 0, probe side split over {world} GPUs, count ncclAllReduce",
-                       "path": last["path"], "narrow_slots": bool(last["narrow"]), "bloom": last["bloom_kind"]},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "matches": matches, "phases_ms_per_step": {k: v / args.steps * 1e3 for k, v in phases.items()},
+            "config": {"workload": w["desc"], "entry_point": w["entry"], "rows_probe_per_gpu": m["N"], "rows_probe_total": m["n_total"],
+                       "rows_build": w["ny"], "match_pct": w["pct"],
+                       "l2": f"inputs {8 * m['N'] / 1e6:.0f} MB per step > 126 MB L2 (no flush needed); table / partitions are rebuilt every step",
+                       "parallelism": m["parallelism"], "path": last["path"], "narrow_slots": bool(last["narrow"]), "bloom": last["bloom_kind"]},
+            "clocks": dict(clocks, window="sampled every 100 ms from before warm-up to the end of the e2e loop"),
+            "e2e": m["e2e"], "gpu_launches": m["launches"], "roofline": m["roofline"], "cpu_baseline": cpu,
+            "matches": matches, "phases_ms_per_step": m["phases"], "other_configs": other,
         }
         print(json.dumps(line))
     if dist is not None:

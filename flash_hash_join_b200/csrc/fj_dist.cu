@@ -102,6 +102,15 @@ fj_status_t dist_broadcast_u64(DistState& d, void* buf, size_t count, int root, 
   FJ_NCCL(g_api.Broadcast(buf, buf, count, ncclUint64, root, reinterpret_cast<ncclComm_t>(d.comm), st));
   return 0;
 }
+fj_status_t dist_broadcast2_u64(DistState& d, const void* send_a, void* recv_a, const void* send_b, void* recv_b, size_t count,
+                                int root, cudaStream_t st) {
+  ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);
+  FJ_NCCL(g_api.GroupStart());
+  FJ_NCCL(g_api.Broadcast(send_a, recv_a, count, ncclUint64, root, comm, st));
+  FJ_NCCL(g_api.Broadcast(send_b, recv_b, count, ncclUint64, root, comm, st));
+  FJ_NCCL(g_api.GroupEnd());
+  return 0;
+}
 fj_status_t dist_allreduce_sum_u64(DistState& d, const void* send, void* recv, size_t count, cudaStream_t st) {
   FJ_NCCL(g_api.AllReduce(send, recv, count, ncclUint64, ncclSum, reinterpret_cast<ncclComm_t>(d.comm), st));
   return 0;

@@ -25,6 +25,9 @@ fj_status_t dist_init(DistState& d, int rank, int world, const void* id128);
 void dist_destroy(DistState& d);
 // collectives on 64-bit words
 fj_status_t dist_broadcast_u64(DistState& d, void* buf, size_t count, int root, cudaStream_t st);
+// two broadcasts in one NCCL group (one launch): root sends from send_a / send_b, everybody receives in recv_a / recv_b
+fj_status_t dist_broadcast2_u64(DistState& d, const void* send_a, void* recv_a, const void* send_b, void* recv_b, size_t count,
+                                int root, cudaStream_t st);
 fj_status_t dist_allreduce_sum_u64(DistState& d, const void* send, void* recv, size_t count, cudaStream_t st);
 fj_status_t dist_allgather_u64(DistState& d, const void* send, void* recv, size_t count_per_rank, cudaStream_t st);
 // all-to-all-v of bytes: rank r sends send_counts[r] bytes from send + send_offs[r], receives recv_counts[r] at recv + recv_offs[r]

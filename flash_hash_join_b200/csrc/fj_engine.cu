@@ -850,12 +850,10 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
     FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
     FJ_TRY(in_bv.ensure(std::max<size_t>(nb, 1) * 8));
     const double th = now_s();
+    const void *src_bk = in_bk.p, *src_bv = in_bv.p;  // what root broadcasts from
     if (dev_in) {
       d_pk = reinterpret_cast<const unsigned long long*>(pk);
-      if (is_root && nb) {
-        FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyDeviceToDevice, st));
-        FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyDeviceToDevice, st));
-      }
+      if (is_root) { src_bk = bk; src_bv = bv; }  // straight out of the caller's HBM arrays
     } else {
       FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
       if (is_root && nb) {
@@ -868,18 +866,19 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
       s.h2d_bytes = (uint64_t)((is_root ? 2 * nb : 0) + np) * 8;
       d_pk = in_pk.as<unsigned long long>();
     }
-    // broadcast the raw build rows
+    // broadcast the raw build rows (keys and values in one NCCL group)
     FJ_CUDA(cudaEventRecord(ev[4], st));
-    if (nb) {
-      FJ_TRY(dist_broadcast_u64(dist, in_bk.p, nb, root, st));
-      FJ_TRY(dist_broadcast_u64(dist, in_bv.p, nb, root, st));
-    }
+    if (nb) FJ_TRY(dist_broadcast2_u64(dist, src_bk, in_bk.p, src_bv, in_bv.p, nb, root, st));
     FJ_CUDA(cudaEventRecord(ev[5], st));
     FJ_TRY(join_device(algo, jflags, in_bk.as<unsigned long long>(), in_bv.as<unsigned long long>(), nb, d_pk, np, 0, &s));
-    // global count
+    // global count: all-reduce straight from the control block the probe kernel wrote
     FJ_CUDA(cudaEventRecord(ev[0], st));
-    FJ_CUDA(cudaMemcpyAsync(d_cnt, &s.matches, 8, cudaMemcpyHostToDevice, st));
-    FJ_TRY(dist_allreduce_sum_u64(dist, d_cnt, d_cnt + 1, 1, st));
+    const void* cnt_src = &ctl.as<Ctl>()->match_count;
+    if (nb == 0 || np == 0) {  // no kernel ran on this rank
+      FJ_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+      cnt_src = d_cnt;
+    }
+    FJ_TRY(dist_allreduce_sum_u64(dist, cnt_src, d_cnt + 1, 1, st));
     unsigned long long total = 0;
     FJ_CUDA(cudaMemcpyAsync(&total, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
     FJ_CUDA(cudaEventRecord(ev[1], st));
