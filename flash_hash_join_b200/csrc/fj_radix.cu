@@ -294,7 +294,7 @@ template <> struct Hole<false, false> {
 template <class T> struct S2Tile { static constexpr int ROWS = sizeof(T) == 16 ? 2048 : 4096; };
 constexpr int S2_CHUNKS = 2048 + S2_FMAX;  // 16-byte chunks of the staging buffer (<= 32 KB of rows), padding included
 
-template <bool BUILD, bool NARROW, int STAGE>
+template <bool BUILD, bool NARROW, int STAGE, bool DEST>
 __global__ void __launch_bounds__(S2_THREADS, 2)
     k_scatter2(const unsigned long long* __restrict__ in_keys, const unsigned long long* __restrict__ in_vals,
                uint64_t n_tiles1,                                            // stage 1: number of FULL tiles
@@ -315,9 +315,9 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;
   T* stg = reinterpret_cast<T*>(smem_raw + 2 * RING);  // TILE rows + room for the padding of `fan` runs
-  __shared__ uint32_t s_hist[S2_FMAX];          // rows per digit of the current tile
+  __shared__ uint32_t s_hist[S2_FMAX + 1];      // rows per digit of the current tile; [fan] = bin of the dropped rows
   __shared__ uint32_t s_cnt[S2_FMAX];           // copy of s_hist taken by the scan
-  __shared__ uint32_t s_off[S2_FMAX];           // staging offset (rows) of the digit's padded run
+  __shared__ uint32_t s_off[S2_FMAX + 1];       // staging offset (rows) of the digit's padded run; [fan] = spare slot
   __shared__ int s_delta[S2_FMAX];              // global chunk index - staging chunk index of the staged tile
   __shared__ uint8_t s_cdig[S2_CHUNKS];         // digit of every 16-byte chunk of the staged tile
   __shared__ uint32_t s_nchunk[2];
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
     __syncthreads();
     ntiles = total;
   }
-  if (tid < S2_FMAX) s_hist[tid] = 0;
+  if (tid <= S2_FMAX) s_hist[tid] = 0;
 
   // producer (thread 0): locate tile -> (input offset, rows, source partition), publish it for the consumers
   // and bulk-copy the tile into ring stage s
@@ -425,41 +425,55 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
 #pragma unroll
       for (int i = 0; i < IPT; ++i) bval[i] = ld_stream1(in_vals + in_base + i * S2_THREADS + tid);
     }
+    // Branch-free on purpose: a dropped row (hole, past the end, out-of-band key) is ranked into the spare bin
+    // s_hist[fan] instead of being skipped, so the 8 rows of a thread are 8 independent instruction streams.
+    bool bad = false;                          // packed build: a row that does not fit 32|32
+    unsigned long long sent_row = EMPTY64;     // wide build: first row with the out-of-band key
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t e = i * S2_THREADS + tid;
-      dr[i] = 0xffffffffu;
       bool ok = e < count;
       unsigned long long k = 0;
       if constexpr (STAGE == 1) {
         k = reinterpret_cast<const unsigned long long*>(src)[e];
         if constexpr (BUILD) {
           if constexpr (NARROW) {
-            if ((k >> 32) != 0 || (uint32_t)k == 0xFFFFFFFFu) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
+            const bool fits = ((k >> 32) == 0) & ((uint32_t)k != 0xFFFFFFFFu);
+            bad |= ok & !fits;
+            ok &= fits;
             elem[i] = k << 32;
           } else {
-            if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(row_base + in_base + e)); ok = false; }
+            const bool oob = k == EMPTY64;
+            sent_row = (ok & oob & (sent_row == EMPTY64)) ? (unsigned long long)(row_base + in_base + e) : sent_row;
+            ok &= !oob;
             elem[i].x = k;
           }
         } else {
           if constexpr (NARROW) {
-            if ((k >> 32) != 0 || (uint32_t)k == 0xFFFFFFFFu) ok = false;  // cannot match a packed build side
+            ok &= ((k >> 32) == 0) & ((uint32_t)k != 0xFFFFFFFFu);  // else: cannot match a packed build side
             elem[i] = (uint32_t)k;
           } else {
-            if (k == EMPTY64) { ++sentinel_local; ok = false; }
+            const bool oob = k == EMPTY64;
+            sentinel_local += (ok & oob) ? 1ull : 0ull;
+            ok &= !oob;
             elem[i] = k;
           }
         }
       } else {
         elem[i] = reinterpret_cast<const T*>(src)[e];
-        if (H::is(elem[i])) ok = false;
+        ok &= !H::is(elem[i]);
         k = E::key(elem[i]);
       }
-      if (ok) {
-        const uint32_t d = scatter_digit(hash32(k), shift, fan);
-        const uint32_t r = atomicAdd(&s_hist[d], 1u);
-        dr[i] = (d << 16) | r;
-      }
+      const uint32_t h = hash32(k);
+      const uint32_t d = ok ? (DEST ? ((h & 0xffffu) * fan) >> 16 : (h >> shift) & (fan - 1)) : fan;
+      const uint32_t r = atomicAdd(&s_hist[d], 1u);
+      dr[i] = ok ? ((d << 16) | r) : (fan << 16);  // dropped rows are staged into one spare slot
+    }
+    if constexpr (STAGE == 1 && BUILD && NARROW) {
+      if (bad) atomicOr(&ctl->flags, CTL_NEED_WIDE);  // the attempt is abandoned by the host
+    }
+    if constexpr (STAGE == 1 && BUILD && !NARROW) {
+      if (sent_row != EMPTY64) atomicMin(&ctl->sentinel_row, sent_row);
     }
     // the reservation made for the previous tile has long returned: publish where its runs go
     if (it > 0 && tid < (int)fan) {
@@ -502,23 +516,31 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
           run += (c + PADN - 1) / PADN * PADN;
         }
       }
-      if (lane == 31) s_nchunk[s] = incl / PADN;
+      if (lane == 31) {
+        s_nchunk[s] = incl / PADN;
+        s_hist[fan] = 0;
+        s_off[fan] = ((uint32_t)TILE + fan * (PADN - 1) + 7u) & ~7u;  // first row past the staged tile
+      }
     }
     if (it > 0) copy_out(s_nchunk[s ^ 1]);
     __syncthreads();
 
     // ---- 3. regroup the tile by digit in the staging buffer; the digit threads reserve the global runs
+    bool bad3 = false;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       if constexpr (STAGE == 1 && BUILD) {
         if constexpr (NARROW) {
-          if ((bval[i] >> 32) != 0 && dr[i] != 0xffffffffu) atomicOr(&ctl->flags, CTL_NEED_WIDE);  // attempt is abandoned
+          bad3 |= ((bval[i] >> 32) != 0) & ((dr[i] >> 16) != fan);
           elem[i] |= bval[i] & 0xffffffffull;
         } else {
           elem[i].y = bval[i];
         }
       }
-      if (dr[i] != 0xffffffffu) stg[s_off[dr[i] >> 16] + (dr[i] & 0xffffu)] = elem[i];
+      stg[s_off[dr[i] >> 16] + (dr[i] & 0xffffu)] = elem[i];
+    }
+    if constexpr (STAGE == 1 && BUILD && NARROW) {
+      if (bad3) atomicOr(&ctl->flags, CTL_NEED_WIDE);
     }
     if (tid < (int)fan) {
       const uint32_t my_c = s_cnt[tid];
@@ -553,15 +575,15 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
   }
 }
 
-template <bool BUILD, bool NARROW, int STAGE>
+template <bool BUILD, bool NARROW, int STAGE, bool DEST>
 static void launch_scatter2_inst(const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st) {
   using T = typename Elem<BUILD, NARROW>::T;
   constexpr int TILE = S2Tile<T>::ROWS;
   constexpr int IN_ROW = STAGE == 1 ? 8 : (int)sizeof(T);
-  auto kern = k_scatter2<BUILD, NARROW, STAGE>;
+  auto kern = k_scatter2<BUILD, NARROW, STAGE, DEST>;
   constexpr uint32_t PADN = 16 / sizeof(T) > 1 ? 16 / sizeof(T) : 1;
   const uint32_t stg_elems = ((uint32_t)TILE + a.fan * (PADN - 1) + 7u) & ~7u;  // every run may carry PADN-1 holes
-  const size_t smem = 2 * (size_t)TILE * IN_ROW + (size_t)stg_elems * sizeof(T);
+  const size_t smem = 2 * (size_t)TILE * IN_ROW + ((size_t)stg_elems + 1) * sizeof(T);  // + the spare slot of dropped rows
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   uint64_t max_tiles, n_tiles1 = 0;
   if (STAGE == 1) max_tiles = n_tiles1 = a.n / TILE;
@@ -586,7 +608,11 @@ uint32_t scatter_pad_rows(bool build, bool narrow) {
 // are only 8-byte aligned) through k_scatter.  Stage 2 (partition -> partition) is always k_scatter2.
 void launch_scatter(bool build, bool narrow, int stage, const ScatterArgs& a, const DeviceInfo& di, cudaStream_t st,
                     int* launches) {
-#define FJ_SC2(B, N, S) launch_scatter2_inst<B, N, S>(a, di, st)
+#define FJ_SC2(B, N, S)                                               \
+  do {                                                                \
+    if (S == 1 && a.shift < 0) launch_scatter2_inst<B, N, 1, true>(a, di, st); \
+    else launch_scatter2_inst<B, N, S, false>(a, di, st);             \
+  } while (0)
 #define FJ_DISPATCH(M, S)                                              \
   do {                                                                 \
     if (build) { if (narrow) M(true, true, S); else M(true, false, S); } \
@@ -936,24 +962,29 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
     __syncthreads();
 
     if (nbp) {  // block-uniform
-      // ---- B. set the member bits; keep (rem, value) of this thread's rows in registers
+      // ---- B. set the member bits; keep (rem, value) of this thread's rows in registers.  Branch-free: a
+      // row that is padding or past the end ORs a zero into word 0, so the rows of a thread are independent
+      // instruction streams instead of a chain of divergent regions.
       uint32_t rem[J3_BPT], bval[J3_BPT];
+      bool dup = false;
 #pragma unroll
       for (int j = 0; j < J3_BPT; ++j) {
-        const uint32_t i = j * J3_THREADS + tid;
         rem[j] = 0xFFFFFFFFu;
-        if (i < nbp) {
-          const unsigned long long t = staging[i];
+        bval[j] = 0;
+        if (j * J3_THREADS < (int)nbp) {  // block-uniform: whole slots past the partition cost nothing
+          const uint32_t i = j * J3_THREADS + tid;
+          const unsigned long long t = staging[i < nbp ? i : 0];
           const uint32_t key = (uint32_t)(t >> 32);
-          if (key != 0xFFFFFFFFu) {  // not padding written by k_scatter2
-            rem[j] = hash32(key) & rmask;
-            bval[j] = (uint32_t)t;
-            const uint32_t bit = 1u << (rem[j] & 31u);
-            const uint32_t old = atomicOr(bitmap + (rem[j] >> 5), bit);
-            if (old & bit) atomicOr(&ctl->flags, CTL_DUP);  // same key twice (hash32 is a bijection)
-          }
+          const bool ok = (i < nbp) & (key != 0xFFFFFFFFu);  // 0xFFFFFFFF: padding written by k_scatter2
+          const uint32_t rm = hash32(key) & rmask;
+          rem[j] = ok ? rm : 0xFFFFFFFFu;
+          bval[j] = (uint32_t)t;
+          const uint32_t bit = ok ? (1u << (rm & 31u)) : 0u;
+          const uint32_t old = atomicOr(bitmap + (ok ? (rm >> 5) : (uint32_t)lane), bit);  // dropped rows OR a zero
+          dup |= (old & bit) != 0u;  // same key twice (hash32 is a bijection on 32-bit keys)
         }
       }
+      if (dup) atomicOr(&ctl->flags, CTL_DUP);
       __syncthreads();
       // ---- C. rank directory: running popcount before every bitmap word.  Thread t owns the wpt consecutive
       // words [t * wpt, (t + 1) * wpt); with wpt == 8 (2^17 hash values per partition, the 1e8-row case) they
@@ -1008,10 +1039,11 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
       // ---- D. place the values by rank
 #pragma unroll
       for (int j = 0; j < J3_BPT; ++j) {
-        if (rem[j] != 0xFFFFFFFFu) {
-          const uint32_t w = rem[j] >> 5;
+        if (j * J3_THREADS < (int)nbp) {
+          const bool ok = rem[j] != 0xFFFFFFFFu;
+          const uint32_t w = ok ? (rem[j] >> 5) : (uint32_t)lane;
           const uint32_t r = prefix[w] + __popc(bitmap[w] & ((1u << (rem[j] & 31u)) - 1u));
-          vals[r] = bval[j];
+          if (ok) vals[r] = bval[j];
         }
       }
     }
@@ -1031,12 +1063,14 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
       }
 #pragma unroll
       for (int i = 0; i < J3_IPT; ++i) {
+        val[i] = 0;
+        if (i * J3_THREADS >= (int)npc) continue;  // block-uniform
         const uint32_t rm = hash32(key[i]) & rmask;
         const uint32_t w = rm >> 5, sh = rm & 31u;
         const uint32_t word = bitmap[w];
         const bool hit = (key[i] != 0xFFFFFFFFu) & ((word >> sh) & 1u);  // 0xFFFFFFFF: hole / past the end
-        val[i] = 0;
-        if (MAT && hit) val[i] = vals[prefix[w] + __popc(word & ((1u << sh) - 1u))];
+        // unconditional: for a miss the rank is still <= the partition's row count, i.e. inside vals[0..smax]
+        val[i] = MAT ? vals[prefix[w] + __popc(word & ((1u << sh) - 1u))] : 0u;
         hitmask |= hit ? (1u << i) : 0u;
       }
     }
