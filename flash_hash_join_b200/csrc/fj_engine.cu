@@ -341,10 +341,8 @@ fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const 
   int launches = 0;
   Ctl* d_ctl = ctl.as<Ctl>();
   FJ_CUDA(cudaEventRecord(ev[0], st));
-  launch_init_ctl(d_ctl, st);
+  launch_prepare(d_ctl, t.slots, table_bytes, t.bloom, t.bloom ? bloom_bytes : 0, di, st);  // ctl + empty table + filter
   ++launches;
-  FJ_CUDA(cudaMemsetAsync(t.slots, 0xff, table_bytes, st));
-  if (t.bloom) FJ_CUDA(cudaMemsetAsync(t.bloom, 0, bloom_bytes, st));
   FJ_CUDA(cudaEventRecord(ev[1], st));
   launch_build(t, bk, bv, nb, exact ? 1 : 0, d_ctl, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[2], st));
@@ -398,9 +396,8 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   int launches = 0;
 
   FJ_CUDA(cudaEventRecord(ev[0], st));
-  launch_init_ctl(d_ctl, st);
+  launch_prepare(d_ctl, nullptr, 0, cursors.p, ncur * 4, di, st);  // ctl + partition cursors
   ++launches;
-  FJ_CUDA(cudaMemsetAsync(cursors.p, 0, ncur * 4, st));
   FJ_CUDA(cudaEventRecord(ev[1], st));
 
   ScatterArgs a;

@@ -33,6 +33,10 @@ struct ProbeOut {
 };
 
 void launch_init_ctl(Ctl* ctl, cudaStream_t st);
+// control block reset + `ones` filled with 0xFF (empty table) + `zeros` cleared, in one launch; sizes are
+// rounded up to 16 bytes (either region may be empty)
+void launch_prepare(Ctl* ctl, void* ones, size_t ones_bytes, void* zeros, size_t zeros_bytes, const DeviceInfo& di,
+                    cudaStream_t st);
 // build kernels: mode 0 = fast (CAS on key, plain value store, raises CTL_DUP on duplicates),
 //                mode 1 = exact keep-first (wide only: value word holds min row index, then fix-up)
 void launch_build(const TableView& t, const unsigned long long* bk, const unsigned long long* bv, uint64_t nb,

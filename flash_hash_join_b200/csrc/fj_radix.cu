@@ -395,10 +395,15 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
 
   // step 4: copy the staged tile out, 16 bytes per thread and iteration; the chunks of a run are contiguous
   // both in the staging buffer and in global memory, so a warp writes (a few) contiguous pieces
-  auto copy_out = [&](uint32_t nchunk) {
+  // Inside the tile loop warp 0 does not take part: it turns the next histogram into staging offsets meanwhile
+  // (step 2), which used to make it the straggler of the barrier that follows.
+  auto copy_out = [&](uint32_t nchunk, bool with_warp0) {
     const uint4* src16 = reinterpret_cast<const uint4*>(stg);
     uint4* out16 = reinterpret_cast<uint4*>(out);
-    for (uint32_t c = tid; c < nchunk; c += S2_THREADS) {
+    if (!with_warp0 && tid < 32) return;
+    const uint32_t first = with_warp0 ? (uint32_t)tid : (uint32_t)tid - 32u;
+    const uint32_t step = with_warp0 ? (uint32_t)S2_THREADS : (uint32_t)S2_THREADS - 32u;
+    for (uint32_t c = first; c < nchunk; c += step) {
       const int dl = s_delta[s_cdig[c]];
       if (dl != POISON) out16[(long long)dl + (long long)c] = src16[c];
     }
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         s_off[fan] = ((uint32_t)TILE + fan * (PADN - 1) + 7u) & ~7u;  // first row past the staged tile
       }
     }
-    if (it > 0) copy_out(s_nchunk[s ^ 1]);
+    if (it > 0) copy_out(s_nchunk[s ^ 1], false);
     __syncthreads();
 
     // ---- 3. regroup the tile by digit in the staging buffer; the digit threads reserve the global runs
@@ -537,7 +542,10 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
           elem[i].y = bval[i];
         }
       }
-      stg[s_off[dr[i] >> 16] + (dr[i] & 0xffffu)] = elem[i];
+      const uint32_t pos = s_off[dr[i] >> 16] + (dr[i] & 0xffffu);
+      stg[pos] = elem[i];
+      s_cdig[pos / PADN] = (uint8_t)(dr[i] >> 16);  // digit of the 16-byte chunk (every row of the chunk writes the same
+                                                     // byte; a dropped row writes past the staged chunks)
     }
     if constexpr (STAGE == 1 && BUILD && NARROW) {
       if (bad3) atomicOr(&ctl->flags, CTL_NEED_WIDE);
@@ -550,7 +558,6 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         my_outp = (STAGE == 1 || merge) ? (uint32_t)tid : p1 * fan + (uint32_t)tid;
         my_g = atomicAdd(out_cursor + my_outp, my_pc);  // consumed after step 1 of the next tile
         for (uint32_t j = my_c; j < my_pc; ++j) stg[my_off + j] = H::make();  // holes pad the run to 16 bytes
-        for (uint32_t c = my_off / PADN; c < (my_off + my_pc) / PADN; ++c) s_cdig[c] = (uint8_t)tid;
       }
     }
   }
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
       s_delta[tid] = dl;
     }
     __syncthreads();
-    copy_out(s_nchunk[(it - 1) & 1]);
+    copy_out(s_nchunk[(it - 1) & 1], true);
   }
 
   if (!BUILD && !NARROW && STAGE == 1) {
@@ -864,9 +871,8 @@ void launch_join(bool narrow, bool mat, const JoinArgs& a, cudaStream_t st, int*
 // popcounts, and one value store per row; probe = three shared-memory loads, branch-free.
 //
 // Persistent CTAs walk the (partition, probe chunk) items; all HBM input is prefetched one item ahead
-// with TMA bulk copies (build tuples into a staging area, probe keys into a double buffer).  Matches are
-// written in (row, warp) order so every warp store is one contiguous run; the output range of a chunk is
-// reserved with a single global atomic.
+// with TMA bulk copies (build tuples into a staging area, probe keys into a double buffer).  Every warp
+// reserves the output range of its own matches with one global atomic and writes it as contiguous runs.
 constexpr int J3_THREADS = 512;
 constexpr int J3_WARPS = J3_THREADS / 32;
 constexpr int J3_IPT = 8;
@@ -889,8 +895,6 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
   __shared__ __align__(8) uint64_t s_bar_t, s_bar_p[2];
   __shared__ uint32_t s_nb[2], s_np[2];
   __shared__ uint32_t s_wsum[J3_WARPS];
-  __shared__ uint32_t s_cnt[J3_IPT * J3_WARPS];
-  __shared__ unsigned long long s_base;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rmask = (1u << rbits) - 1u;
@@ -1010,18 +1014,11 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
         }
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-          const uint32_t v = lane < J3_WARPS ? s_wsum[lane] : 0u;
-          uint32_t in2 = v;
-#pragma unroll
-          for (int d = 1; d < J3_WARPS; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, in2, d);
-            if (lane >= d) in2 += o;
-          }
-          if (lane < J3_WARPS) s_wsum[lane] = in2 - v;
-        }
-        __syncthreads();
-        uint32_t run = s_wsum[warp] + incl - sum;
+        // every warp sums the totals of the warps before it itself (one REDUX) instead of waiting for a
+        // second barrier behind a single scanning warp
+        static_assert(J3_WARPS <= 32, "one lane per warp total");
+        const uint32_t wpre = __reduce_add_sync(0xffffffffu, lane < warp ? s_wsum[lane] : 0u);
+        uint32_t run = wpre + incl - sum;
         if (wpt == 8) {
           uint32_t q[8];
 #pragma unroll
@@ -1077,46 +1074,33 @@ __global__ void __launch_bounds__(J3_THREADS, 2)
     if (!MAT) {
       local_count += __popc(hitmask);
     } else if (npc) {  // block-uniform
-      uint32_t rank[J3_IPT];
+      // Every warp reserves the output range of its own matches (<= 256 pairs: 2 KB per column, written as 8
+      // contiguous runs) with one global atomic: no block-wide scan and no barrier between probing and storing.
+      uint32_t off[J3_IPT];
+      uint32_t wtot = 0;
 #pragma unroll
       for (int i = 0; i < J3_IPT; ++i) {
         const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> i) & 1u);
-        rank[i] = __popc(bal & lanemask_lt());
-        if (lane == 0) s_cnt[i * J3_WARPS + warp] = __popc(bal);
+        off[i] = wtot + __popc(bal & lanemask_lt());
+        wtot += __popc(bal);
       }
-      __syncthreads();
-      if (warp == 0) {
-        constexpr int PER = J3_IPT * J3_WARPS / 32;
-        uint32_t c[PER];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int u = 0; u < PER; ++u) { c[u] = s_cnt[lane * PER + u]; sum += c[u]; }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
-        }
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int u = 0; u < PER; ++u) { s_cnt[lane * PER + u] = run; run += c[u]; }
-        if (lane == 31) {
-          s_base = incl ? atomicAdd(&ctl->out_cursor, (unsigned long long)incl) : 0ull;
-          local_count += incl;
-        }
+      unsigned long long base = 0;
+      if (lane == 0 && wtot) {
+        base = atomicAdd(&ctl->out_cursor, (unsigned long long)wtot);
+        local_count += wtot;
       }
-      __syncthreads();
-      const unsigned long long base = s_base;
+      base = __shfl_sync(0xffffffffu, base, 0);
+      unsigned long long* ok = out_keys + base;
+      unsigned long long* ov = out_vals + base;
 #pragma unroll
       for (int i = 0; i < J3_IPT; ++i) {
         if ((hitmask >> i) & 1u) {
-          const unsigned long long pos = base + s_cnt[i * J3_WARPS + warp] + rank[i];
-          st_stream(out_keys + pos, (unsigned long long)key[i]);
-          st_stream(out_vals + pos, (unsigned long long)val[i]);
+          st_stream(ok + off[i], (unsigned long long)key[i]);
+          st_stream(ov + off[i], (unsigned long long)val[i]);
         }
       }
     }
-    __syncthreads();  // pbuf[k & 1], s_cnt, s_base, the bitmap and vals are reused by the next items
+    __syncthreads();  // pbuf[k & 1], the bitmap and vals are reused by the next items
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);

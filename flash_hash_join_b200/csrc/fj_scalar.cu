@@ -13,6 +13,7 @@
 //   narrow: 4 packed words per bucket, word = key32 << 32 | value32, EMPTY = ~0
 //   wide  : 2 slots per bucket, slot = {key64, value64}, EMPTY key = ~0 (that key value itself is
 //           kept out of band in Ctl::sentinel_row)
+#include <algorithm>
 #include <cstdio>
 #include <type_traits>
 
@@ -30,6 +31,36 @@ __global__ void k_init_ctl(Ctl* ctl) {
   ctl->pad = 0;
 }
 void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ctl); }
+
+// One launch instead of {k_init_ctl, cudaMemsetAsync(table), cudaMemsetAsync(bloom | cursors)}: the control
+// block, a 16-byte-granular region filled with all-ones (the empty table, FlashHashTable ctor :98-110) and a
+// 16-byte-granular region of zeros (the Bloom filter, or the partition cursors of the radix path).
+__global__ void __launch_bounds__(512) k_prepare(Ctl* __restrict__ ctl, uint4* __restrict__ ones, uint64_t n_ones,
+                                                 uint4* __restrict__ zeros, uint64_t n_zeros) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t == 0) {
+    ctl->match_count = 0;
+    ctl->out_cursor = 0;
+    ctl->sentinel_row = EMPTY64;
+    ctl->sentinel_probes = 0;
+    ctl->flags = 0;
+    ctl->pad = 0;
+  }
+  const uint4 f = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0u, 0u, 0u, 0u);
+  for (uint64_t i = t; i < n_ones; i += stride) ones[i] = f;
+  for (uint64_t i = t; i < n_zeros; i += stride) zeros[i] = z;
+}
+// ones_bytes / zeros_bytes are rounded UP to 16 bytes: the buffers behind them come from the engine's arena,
+// whose allocations are 256-byte granular
+void launch_prepare(Ctl* ctl, void* ones, size_t ones_bytes, void* zeros, size_t zeros_bytes, const DeviceInfo& di,
+                    cudaStream_t st) {
+  const uint64_t n1 = (ones_bytes + 15) / 16, n0 = (zeros_bytes + 15) / 16;
+  const uint64_t want = (std::max(n1, n0) + 511) / 512;
+  const uint64_t cap = (uint64_t)di.sms * 8;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+  k_prepare<<<grid, 512, 0, st>>>(ctl, static_cast<uint4*>(ones), n1, static_cast<uint4*>(zeros), n0);
+}
 
 // =================================================================================== build
 // MODE 0: fast path.  MODE 1: exact keep-first (wide only) — the value word accumulates the
@@ -225,7 +256,9 @@ __device__ __forceinline__ uint32_t load_tile(const unsigned long long* __restri
   return valid;
 }
 
-// stage the whole Bloom filter in shared memory with TMA bulk copies (cp.async.bulk + mbarrier)
+// stage the whole Bloom filter in shared memory with TMA bulk copies (cp.async.bulk + mbarrier).  Only issues
+// the copies: the caller waits on `bar` (phase 0) right before the first filter word is read, so the first
+// tile of probe keys is already in flight while the filter lands.
 __device__ __forceinline__ void stage_bloom(unsigned char* smem_dst, const uint32_t* __restrict__ bloom, uint32_t bloom_words,
                                             uint64_t* bar) {
   if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -238,7 +271,6 @@ __device__ __forceinline__ void stage_bloom(unsigned char* smem_dst, const uint3
       bulk_g2s(smem_dst + off, reinterpret_cast<const unsigned char*>(bloom) + off, n, bar);
     }
   }
-  mbar_wait(bar, 0);
 }
 
 // ------------------------------------------------------------------------------------ count
@@ -380,6 +412,7 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 2)
   };
   uint64_t tile = blockIdx.x;
   if (tile < ntiles) va = fetch(tile, ka);
+  if (BLOOM == 1) mbar_wait(&s_bar, 0);
   while (tile < ntiles) {
     const uint64_t t1 = tile + gridDim.x;
     if (t1 < ntiles) vb = fetch(t1, kb);
@@ -418,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, BLOOM == 1 ? 1 : 3)
   const uint32_t* sbloom = reinterpret_cast<const uint32_t*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (BLOOM == 1) stage_bloom(smem_raw, bloom, bloom_words, &s_bar);
+  if (BLOOM == 1) { stage_bloom(smem_raw, bloom, bloom_words, &s_bar); mbar_wait(&s_bar, 0); }
   bool sent_present = false;
   unsigned long long sent_value = 0;
   if (!NARROW) {

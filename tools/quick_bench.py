@@ -59,6 +59,8 @@ def main():
         else:
             run(f"{c} radix mat", R, M, d, a.reps, N)
             run(f"{c} radix count", R, 0, d, a.reps, N)
+            run(f"{c} radix mat 2^16 parts", R, M, d, a.reps, N, {"radix_sub_rows": 2400})
+            capi.config_set(radix_sub_rows=0)
             run(f"{c} radix mat wide", R, M | W, d, a.reps, N)
             run(f"{c} scalar count", S, 0, d, max(1, a.reps // 2), N)
             run(f"{c} scalar mat", S, M, d, max(1, a.reps // 2), N)
