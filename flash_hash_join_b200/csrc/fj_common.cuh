@@ -20,11 +20,16 @@ struct Ctl {
   unsigned long long sentinel_probes;  // radix path: probe rows whose key == EMPTY64 (joined out of band)
   unsigned int flags;               // CTL_* bits raised by kernels
   unsigned int pad;
+  // dense-key-domain paths (direct addressing instead of hashing)
+  unsigned long long max_key;       // largest build key the stage-1 scatter staged
+  unsigned long long dense_rows;    // build rows stored into the direct-address regions
+  unsigned long long dense_slots;   // non-empty direct-address slots afterwards (< dense_rows <=> duplicate build keys)
 };
 enum : unsigned {
   CTL_NEED_WIDE = 1u,  // a build key or value does not fit the packed 32|32 slot
   CTL_DUP = 2u,        // duplicate build keys seen: keep-first needs the exact path
   CTL_OVERFLOW = 4u,   // an optimistic fixed-capacity partition buffer overflowed
+  CTL_NOT_DENSE = 8u,  // a build key (or value) lies outside the optimistic dense key domain
 };
 
 // ---- hashing -----------------------------------------------------------------------------------

@@ -122,6 +122,9 @@ struct Engine {
     cfg["narrow"] = 1;
     cfg["join3"] = 1;  // packed rows, two radix passes: collision-free pipelined k_join3 (0 = k_join)
     cfg["chunk_rows"] = 1 << 24;
+    cfg["dense"] = 1;               // optimistic dense-key-domain fast paths (exact bitmap count, direct-address radix join)
+    cfg["dense_min_rows"] = 1 << 20;  // radix: smallest build side that takes the direct-address join
+    cfg["dense_group_mb"] = 16;     // radix: direct-address regions kept L2 resident per pipeline stage (3 stages)
     cfg["shuffle_virtual_ranks"] = 1;  // > 1: every rank owns that many shuffle destinations (exercises the
                                        // multi-destination scatter / exchange layout on few GPUs)
   }
@@ -133,6 +136,16 @@ struct Engine {
   fj_status attempt_scalar(unsigned flags, bool narrow, bool exact, const unsigned long long* bk,
                            const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
                            uint64_t idx_base, fj_stats* s);
+  // dense key domain, radix path: one scatter pass by the low key bits + direct-address join in L2 (k_djoin)
+  struct DensePlan { bool ok = false; uint64_t klimit = 0, rstride = 0, cap_b = 0, cap_p = 0; };
+  DensePlan plan_dense(unsigned flags, uint64_t nb, uint64_t np) const;
+  fj_status attempt_dense(unsigned flags, const DensePlan& dp, const unsigned long long* bk, const unsigned long long* bv,
+                          uint64_t nb, const unsigned long long* pk, uint64_t np, fj_stats* s);
+  DevBuf direct;
+  // dense key domain, count only: exact membership bitmap in shared memory instead of table + filter
+  uint64_t dense_bitmap_bits(uint64_t nb) const;
+  fj_status attempt_scalar_dense(uint64_t dbits, const unsigned long long* bk, uint64_t nb, const unsigned long long* pk,
+                                 uint64_t np, fj_stats* s);
   // flat != nullptr: both sides are already in partition-element format (rows received from the multi-GPU
   // shuffle, holes included): flat->b / flat->p replace bk,bv / pk and every pass is a stage-2 pass
   struct FlatInput { const void* b; uint64_t nb; const void* p; uint64_t np; };
@@ -203,7 +216,7 @@ void Engine::shutdown() {
   dist_destroy(dist);
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
-                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &dist_scratch, &send_b, &send_p, &recv_b,
+                    &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &direct, &dist_scratch, &send_b, &send_p, &recv_b,
                     &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv})
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
@@ -372,6 +385,50 @@ fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const 
   return FJ_OK;
 }
 
+// ---- dense key domain, count only (global-table path) -----------------------------------------
+// Optimistic key bound: the next power of two above 2*nb (h2o keys are 1..1.1*nb, 1..1.9*nb at 10 % match),
+// clipped to what fits shared memory; 0 = not applicable.
+uint64_t Engine::dense_bitmap_bits(uint64_t nb) const {
+  if (!cfg.at("dense") || !cfg.at("narrow") || nb == 0) return 0;
+  uint64_t d = 256;
+  while (d < 2 * nb) d <<= 1;
+  const uint64_t lim = (uint64_t)probe_smem_bitmap_limit_bytes(di) * 8;
+  if (d > lim) d = lim & ~uint64_t(127);
+  return d >= nb + 1 ? d : 0;
+}
+
+fj_status Engine::attempt_scalar_dense(uint64_t dbits, const unsigned long long* bk, uint64_t nb,
+                                       const unsigned long long* pk, uint64_t np, fj_stats* s) {
+  const size_t bytes = dbits / 8;
+  FJ_TRY(bloom.ensure(bytes));
+  Ctl* d_ctl = ctl.as<Ctl>();
+  int launches = 0;
+  FJ_CUDA(cudaEventRecord(ev[0], st));
+  launch_prepare(d_ctl, nullptr, 0, bloom.p, bytes, di, st);
+  ++launches;
+  FJ_CUDA(cudaEventRecord(ev[1], st));
+  launch_build_bitmap(bloom.as<uint32_t>(), dbits, bk, nb, d_ctl, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[2], st));
+  launch_probe_count_dense(pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  FJ_CUDA(cudaGetLastError());
+  s->clear_s += ms(0, 1) * 1e-3;
+  s->build_s += ms(1, 2) * 1e-3;
+  s->probe_s += ms(2, 3) * 1e-3;
+  s->device_s += ms(0, 3) * 1e-3;
+  s->kernel_launches += launches;
+  s->table_bytes = bytes;
+  s->path = FJ_ALGO_SCALAR;
+  s->narrow = 1;
+  s->bloom_kind = 3;
+  s->dense = 1;
+  s->dedup_exact = 0;
+  s->radix_bits1 = s->radix_bits2 = 0;
+  return FJ_OK;
+}
+
 // ---- one attempt on the radix path -------------------------------------------------------------
 fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsigned long long* bk,
                                 const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
@@ -472,6 +529,87 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   return FJ_OK;
 }
 
+// ---- one attempt on the dense-key-domain radix path ---------------------------------------------
+// Optimistic: every build key < klimit = 2^(ceil(log2 nb) + 1) (h2o ids are 1..1.1*nb) and every build value
+// < 2^32 - 1.  ONE scatter pass by the low 8 key bits (k_scatter2 with DomainArgs::ident), then k_djoin.
+static uint64_t round8(uint64_t x) { return (x + 7) & ~uint64_t(7); }
+Engine::DensePlan Engine::plan_dense(unsigned flags, uint64_t nb, uint64_t np) const {
+  DensePlan dp;
+  if (!cfg.at("dense") || !cfg.at("narrow") || (flags & (FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX))) return dp;
+  if (nb < (uint64_t)std::max<int64_t>(cfg.at("dense_min_rows"), 1024) || nb > (1ull << 31)) return dp;
+  uint64_t k = 1024;
+  while (k < 2 * nb) k <<= 1;
+  if (k > 0xFFFFFFFFull) k = 0xFFFFFFFFull;
+  const uint32_t F = djoin_fan();
+  const uint32_t tile_b = scatter_tile_rows(true, true), tile_p = scatter_tile_rows(false, true);
+  const uint32_t pad_b = scatter_pad_rows(true, true), pad_p = scatter_pad_rows(false, true);
+  dp.klimit = k;
+  dp.rstride = round4((k + F - 1) / F);
+  dp.cap_b = round4(cap_build(nb, F) + 32 + pad_allow(nb / tile_b + 1, pad_b));
+  dp.cap_p = round8(cap_probe(np, F) + pad_allow(np / tile_p + 1, pad_p));
+  if (dp.cap_b > 0xfffffff0ull || dp.cap_p > 0xfffffff0ull) return dp;
+  dp.ok = true;
+  return dp;
+}
+
+fj_status Engine::attempt_dense(unsigned flags, const DensePlan& dp, const unsigned long long* bk,
+                                const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                                fj_stats* s) {
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
+  const uint32_t F = djoin_fan();
+  FJ_TRY(part_a_b.ensure((size_t)F * dp.cap_b * 8));
+  FJ_TRY(part_a_p.ensure((size_t)F * dp.cap_p * 4));
+  // cursor layout: [build F][probe F][k_djoin sync words]
+  const size_t ncur = 2 * (size_t)F + djoin_sync_words();
+  FJ_TRY(cursors.ensure(ncur * 4));
+  uint32_t* cur_b = cursors.as<uint32_t>();
+  uint32_t* cur_p = cur_b + F;
+  Ctl* d_ctl = ctl.as<Ctl>();
+  int launches = 0;
+  FJ_CUDA(cudaEventRecord(ev[0], st));
+  launch_prepare(d_ctl, nullptr, 0, cursors.p, ncur * 4, di, st);
+  ++launches;
+  FJ_CUDA(cudaEventRecord(ev[1], st));
+  ScatterArgs a;
+  a.ctl = d_ctl; a.shift = 0; a.fan = F;
+  a.dom.klimit = dp.klimit; a.dom.vlimit = 0xFFFFFFFEull; a.dom.badflag = CTL_NOT_DENSE; a.dom.ident = 1;
+  a.in_keys = bk; a.in_vals = bv; a.n = nb; a.out = part_a_b.p; a.out_cursor = cur_b; a.out_cap = dp.cap_b;
+  launch_scatter(true, true, 1, a, di, st, &launches);
+  a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.out = part_a_p.p; a.out_cursor = cur_p; a.out_cap = dp.cap_p;
+  launch_scatter(false, true, 1, a, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[2], st));
+  DjoinArgs j;
+  j.build = part_a_b.p; j.bcnt = cur_b; j.cap_b = dp.cap_b;
+  j.probe = part_a_p.p; j.pcnt = cur_p; j.cap_p = dp.cap_p;
+  j.direct = direct.as<uint32_t>(); j.rstride = dp.rstride;
+  j.group_bytes = (uint64_t)std::max<int64_t>(1, cfg["dense_group_mb"]) << 20;
+  j.ctl = d_ctl; j.sync = cur_p + F;
+  j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
+  j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
+  const bool launched = launch_djoin(mat, j, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  FJ_CUDA(cudaGetLastError());
+  if (!launched) h_ctl->flags |= CTL_NOT_DENSE;  // the host falls back to the general radix path
+  // fewer non-empty slots than rows stored: some key was stored twice (duplicate build keys)
+  if (mat && !(h_ctl->flags & (CTL_NOT_DENSE | CTL_OVERFLOW)) && h_ctl->dense_slots != h_ctl->dense_rows) h_ctl->flags |= CTL_DUP;
+  s->clear_s += ms(0, 1) * 1e-3;
+  s->partition_s += ms(1, 2) * 1e-3;
+  s->probe_s += ms(2, 3) * 1e-3;
+  s->device_s += ms(0, 3) * 1e-3;
+  s->kernel_launches += launches;
+  s->table_bytes = (uint64_t)F * (dp.cap_b * 8 + dp.cap_p * 4 + dp.rstride * 4);
+  s->path = FJ_ALGO_RADIX;
+  s->narrow = 1;
+  s->bloom_kind = 0;
+  s->dedup_exact = 0;
+  s->radix_bits1 = 8;
+  s->radix_bits2 = 0;
+  s->dense = 1;
+  return FJ_OK;
+}
+
 fj_status Engine::finish_attempt(unsigned flags, fj_stats* s) {
   s->matches = h_ctl->match_count;
   if (flags & FJ_FLAG_MATERIALIZE) {
@@ -497,26 +635,41 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
     return FJ_OK;
   }
   FJ_TRY(ensure_out(flags, np));
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
   bool narrow = !(flags & FJ_FLAG_FORCE_WIDE) && cfg["narrow"] != 0;
   bool exact = false;
   RadixPlan plan = plan_radix(nb, np, narrow);
   int path = choose_path(algo, flags, nb, narrow, plan);
-  if ((flags & FJ_FLAG_PROBE_IDX) && (flags & FJ_FLAG_MATERIALIZE)) path = FJ_ALGO_SCALAR;  // radix drops row ids (:254-292)
-  for (int attempt = 1; attempt <= 5; ++attempt) {
+  if ((flags & FJ_FLAG_PROBE_IDX) && mat) path = FJ_ALGO_SCALAR;  // radix drops row ids (:254-292)
+  // optimistic dense-key-domain fast paths (both leave through CTL_NOT_DENSE when the data says otherwise)
+  uint64_t dense_bits = (narrow && !mat && path == FJ_ALGO_SCALAR) ? dense_bitmap_bits(nb) : 0;
+  DensePlan dplan;
+  if (narrow && path == FJ_ALGO_RADIX) {
+    dplan = plan_dense(flags, nb, np);
+    if (dplan.ok && direct.ensure((size_t)djoin_fan() * dplan.rstride * 4) != FJ_OK) dplan.ok = false;  // no room: general path
+  }
+  for (int attempt = 1; attempt <= 6; ++attempt) {
     s->attempts = attempt;
+    s->dense = 0;
     if (path == FJ_ALGO_RADIX) {
       if (plan.narrow != narrow) plan = plan_radix(nb, np, narrow);
       if (!plan.ok) { path = FJ_ALGO_SCALAR; }
     }
-    if (path == FJ_ALGO_RADIX) FJ_TRY(attempt_radix(flags, plan, bk, bv, nb, pk, np, s));
+    const bool dense_radix = path == FJ_ALGO_RADIX && narrow && dplan.ok;
+    const bool dense_scalar = path == FJ_ALGO_SCALAR && narrow && !exact && !mat && dense_bits != 0;
+    if (dense_radix) FJ_TRY(attempt_dense(flags, dplan, bk, bv, nb, pk, np, s));
+    else if (dense_scalar) FJ_TRY(attempt_scalar_dense(dense_bits, bk, nb, pk, np, s));
+    else if (path == FJ_ALGO_RADIX) FJ_TRY(attempt_radix(flags, plan, bk, bv, nb, pk, np, s));
     else FJ_TRY(attempt_scalar(flags, narrow, exact, bk, bv, nb, pk, np, idx_base, s));
     const unsigned f = h_ctl->flags;
+    if (f & CTL_NOT_DENSE) { dplan.ok = false; dense_bits = 0; continue; }
+    if ((f & CTL_OVERFLOW) && dense_radix) { dplan.ok = false; continue; }  // skewed low key bits: hash partitioning instead
     if ((f & CTL_NEED_WIDE) && narrow) { narrow = false; continue; }
     if ((f & CTL_OVERFLOW) && path == FJ_ALGO_RADIX) { path = FJ_ALGO_SCALAR; continue; }
     if ((f & CTL_DUP) && !exact) { exact = true; narrow = false; path = FJ_ALGO_SCALAR; continue; }
     return finish_attempt(flags, s);
   }
-  return set_err(FJ_ERR_STATE, "internal: join did not converge after 5 attempts (flags %u)", h_ctl->flags);
+  return set_err(FJ_ERR_STATE, "internal: join did not converge after 6 attempts (flags %u)", h_ctl->flags);
 }
 
 fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb, const uint64_t* pk,

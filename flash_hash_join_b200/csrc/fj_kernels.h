@@ -47,8 +47,25 @@ void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np,
                   const ProbeOut* out, bool bloom_in_smem, int ctas_per_sm, Ctl* ctl, const DeviceInfo& di,
                   cudaStream_t st, int* launches);
 size_t probe_smem_bloom_limit_words(const DeviceInfo& di);
+// dense key domain (count only): exact membership bitmap of `dbits` bits (multiple of 128) instead of table + filter;
+// a build key >= dbits raises CTL_NOT_DENSE
+size_t probe_smem_bitmap_limit_bytes(const DeviceInfo& di);
+void launch_build_bitmap(uint32_t* bitmap, uint64_t dbits, const unsigned long long* bk, uint64_t nb, Ctl* ctl,
+                         const DeviceInfo& di, cudaStream_t st, int* launches);
+void launch_probe_count_dense(const unsigned long long* pk, uint64_t np, const uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
+                              const DeviceInfo& di, cudaStream_t st, int* launches);
 
 // ---------------------------------------------------------------- radix-partitioned path
+// key / value domain of the packed (narrow) stage-1 scatter.  General packed rows: keys < 2^32 - 1, values < 2^32,
+// digit from hash32, a row outside raises CTL_NEED_WIDE.  Dense key domain: keys < the optimistic bound `klimit`,
+// values < 2^32 - 1 (the direct-address slot stores value + 1), digit = the low key bits themselves (`ident`), a row
+// outside raises CTL_NOT_DENSE and the largest staged key is recorded in Ctl::max_key.
+struct DomainArgs {
+  unsigned long long klimit = 0xFFFFFFFFull;  // packed rows need key < klimit ...
+  unsigned long long vlimit = 0xFFFFFFFFull;  // ... and value <= vlimit
+  unsigned badflag = CTL_NEED_WIDE;
+  int ident = 0;
+};
 struct ScatterArgs {
   // stage 1 input: raw 64-bit columns
   const unsigned long long* in_keys = nullptr;
@@ -70,6 +87,7 @@ struct ScatterArgs {
                       // < 0 : shuffle destination = ((hash32(key) & 0xffff) * fan) >> 16, any fan
   uint32_t fan = 1;   // <= 256
   Ctl* ctl = nullptr;
+  DomainArgs dom;
 };
 struct JoinArgs {
   const void* build = nullptr;
@@ -101,6 +119,27 @@ size_t join3_smem_bytes(uint32_t smax, int rbits);
 uint32_t join3_probe_chunk();
 uint32_t join3_max_build_rows();
 int join3_min_rbits();
+// dense key domain: direct-address join of the 256 stage-1 partitions made with DomainArgs::ident (k_djoin).
+// `direct` holds 256 regions of `rstride` 4-byte slots; `sync` = djoin_sync_words() zeroed words; returns false
+// when the kernel cannot be made fully co-resident (nothing is launched then).  cap_p must be a multiple of 8.
+struct DjoinArgs {
+  const void* build = nullptr;
+  const uint32_t* bcnt = nullptr;
+  uint64_t cap_b = 0;
+  const void* probe = nullptr;
+  const uint32_t* pcnt = nullptr;
+  uint64_t cap_p = 0;
+  uint32_t* direct = nullptr;
+  uint64_t rstride = 0;
+  uint64_t group_bytes = 0;  // bytes of regions per pipeline stage (three stages are live at once)
+  Ctl* ctl = nullptr;
+  uint32_t* sync = nullptr;
+  unsigned long long* out_keys = nullptr;
+  unsigned long long* out_vals = nullptr;
+};
+size_t djoin_sync_words();
+uint32_t djoin_fan();
+bool launch_djoin(bool mat, const DjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
                           unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
 

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
               const typename Elem<BUILD, NARROW>::T* __restrict__ in_part,  // stage 2
               const uint32_t* __restrict__ in_counts, uint32_t in_nparts, uint64_t in_cap,
               typename Elem<BUILD, NARROW>::T* __restrict__ out, uint32_t* __restrict__ out_cursor, uint64_t out_cap,
-              int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base) {
+              int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base, DomainArgs dom) {
   using E = Elem<BUILD, NARROW>;
   using T = typename E::T;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
   }
 
   unsigned long long sentinel_local = 0;
+  uint32_t kmax = 0;
 
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---- locate the tile
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
             const unsigned long long v = ld_stream1(in_vals + in_base + e);
             if constexpr (NARROW) {
               const unsigned long long packed = (k << 32) | (v & 0xffffffffull);
-              if (!narrow_ok(k, v)) { atomicOr(&ctl->flags, CTL_NEED_WIDE); ok = false; }
+              if (!((k < dom.klimit) & (v <= dom.vlimit))) { atomicOr(&ctl->flags, dom.badflag); ok = false; }
+              else kmax = max(kmax, (uint32_t)k);
               elem[i] = packed;
             } else {
               if (k == EMPTY64) { atomicMin(&ctl->sentinel_row, (unsigned long long)(row_base + in_base + e)); ok = false; }
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
             }
           } else {
             if constexpr (NARROW) {
-              if ((k >> 32) != 0 || (uint32_t)k == 0xFFFFFFFFu) ok = false;  // cannot match a packed build side
+              if (k >= dom.klimit) ok = false;  // cannot match a packed build side
               elem[i] = (uint32_t)k;
             } else {
               if (k == EMPTY64) { ++sentinel_local; ok = false; }
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
           k = E::key(elem[i]);
         }
         if (ok) {
-          const uint32_t d = scatter_digit(hash32(k), shift, fan);
+          const uint32_t d = scatter_digit(dom.ident ? (uint32_t)k : hash32(k), shift, fan);
           const uint32_t r = atomicAdd(&s_hist[d], 1u);
           dr[i] = (d << 16) | r;
         }
@@ -231,6 +233,10 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
     // next iteration's first __syncthreads (after zeroing s_hist) orders these reads before reuse
   }
 
+  if (BUILD && NARROW && STAGE == 1 && dom.ident) {
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if ((tid & 31) == 0 && kmax) atomicMax(&ctl->max_key, (unsigned long long)kmax);
+  }
   if (!BUILD && !NARROW && STAGE == 1) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sentinel_local += __shfl_xor_sync(0xffffffffu, sentinel_local, d);
@@ -252,7 +258,7 @@ static void launch_scatter_inst(const ScatterArgs& a, const DeviceInfo& di, cuda
   if (grid == 0) return;
   kern<<<(unsigned)grid, SC_THREADS, smem, st>>>(a.in_keys, a.in_vals, a.n, reinterpret_cast<const T*>(a.in_part),
                                                  a.in_counts, a.in_nparts, a.in_cap, reinterpret_cast<T*>(a.out),
-                                                 a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl, a.row_base);
+                                                 a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl, a.row_base, a.dom);
 }
 
 size_t radix_elem_bytes(bool build, bool narrow) {
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
                const typename Elem<BUILD, NARROW>::T* __restrict__ in_part,  // stage 2
                const uint32_t* __restrict__ in_counts, uint32_t in_nparts, uint64_t in_cap, int merge,
                typename Elem<BUILD, NARROW>::T* __restrict__ out, uint32_t* __restrict__ out_cursor, uint64_t out_cap,
-               int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base) {
+               int shift, uint32_t fan, Ctl* __restrict__ ctl, uint64_t row_base, DomainArgs dom) {
   using E = Elem<BUILD, NARROW>;
   using T = typename E::T;
   using H = Hole<BUILD, NARROW>;
@@ -411,6 +417,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
 
   const uint32_t dpl = (fan + 31u) >> 5;  // digits per lane in the single-warp scan
   unsigned long long sentinel_local = 0;
+  uint32_t kmax = 0;  // packed stage-1 build: largest staged key (the dense-domain join sizes its regions by it)
   // digit threads (tid < fan): the run reserved for this thread's digit in the tile staged last
   uint32_t my_g = 0, my_pc = 0, my_off = 0, my_outp = 0;
   uint32_t it = 0;
@@ -443,9 +450,10 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         k = reinterpret_cast<const unsigned long long*>(src)[e];
         if constexpr (BUILD) {
           if constexpr (NARROW) {
-            const bool fits = ((k >> 32) == 0) & ((uint32_t)k != 0xFFFFFFFFu);
+            const bool fits = k < dom.klimit;  // general: < 2^32 - 1; dense domain: < the optimistic key bound
             bad |= ok & !fits;
             ok &= fits;
+            kmax = max(kmax, ok ? (uint32_t)k : 0u);
             elem[i] = k << 32;
           } else {
             const bool oob = k == EMPTY64;
@@ -455,7 +463,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
           }
         } else {
           if constexpr (NARROW) {
-            ok &= ((k >> 32) == 0) & ((uint32_t)k != 0xFFFFFFFFu);  // else: cannot match a packed build side
+            ok &= k < dom.klimit;  // else: cannot match a packed build side
             elem[i] = (uint32_t)k;
           } else {
             const bool oob = k == EMPTY64;
@@ -469,13 +477,13 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
         ok &= !H::is(elem[i]);
         k = E::key(elem[i]);
       }
-      const uint32_t h = hash32(k);
+      const uint32_t h = (STAGE == 1 && NARROW && !DEST && dom.ident) ? (uint32_t)k : hash32(k);
       const uint32_t d = ok ? (DEST ? ((h & 0xffffu) * fan) >> 16 : (h >> shift) & (fan - 1)) : fan;
       const uint32_t r = atomicAdd(&s_hist[d], 1u);
       dr[i] = ok ? ((d << 16) | r) : (fan << 16);  // dropped rows are staged into one spare slot
     }
     if constexpr (STAGE == 1 && BUILD && NARROW) {
-      if (bad) atomicOr(&ctl->flags, CTL_NEED_WIDE);  // the attempt is abandoned by the host
+      if (bad) atomicOr(&ctl->flags, dom.badflag);  // the attempt is abandoned by the host
     }
     if constexpr (STAGE == 1 && BUILD && !NARROW) {
       if (sent_row != EMPTY64) atomicMin(&ctl->sentinel_row, sent_row);
@@ -536,7 +544,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
     for (int i = 0; i < IPT; ++i) {
       if constexpr (STAGE == 1 && BUILD) {
         if constexpr (NARROW) {
-          bad3 |= ((bval[i] >> 32) != 0) & ((dr[i] >> 16) != fan);
+          bad3 |= (bval[i] > dom.vlimit) & ((dr[i] >> 16) != fan);
           elem[i] |= bval[i] & 0xffffffffull;
         } else {
           elem[i].y = bval[i];
@@ -548,7 +556,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
                                                      // byte; a dropped row writes past the staged chunks)
     }
     if constexpr (STAGE == 1 && BUILD && NARROW) {
-      if (bad3) atomicOr(&ctl->flags, CTL_NEED_WIDE);
+      if (bad3) atomicOr(&ctl->flags, dom.badflag);
     }
     if (tid < (int)fan) {
       const uint32_t my_c = s_cnt[tid];
@@ -575,6 +583,10 @@ __global__ void __launch_bounds__(S2_THREADS, 2)
     copy_out(s_nchunk[(it - 1) & 1], true);
   }
 
+  if (BUILD && NARROW && STAGE == 1 && dom.ident) {
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0 && kmax) atomicMax(&ctl->max_key, (unsigned long long)kmax);
+  }
   if (!BUILD && !NARROW && STAGE == 1) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sentinel_local += __shfl_xor_sync(0xffffffffu, sentinel_local, d);
@@ -601,7 +613,7 @@ static void launch_scatter2_inst(const ScatterArgs& a, const DeviceInfo& di, cud
   kern<<<(unsigned)grid, S2_THREADS, smem, st>>>(a.in_keys, a.in_vals, n_tiles1, reinterpret_cast<const T*>(a.in_part),
                                                  a.in_counts, a.in_nparts, a.in_cap, a.merge ? 1 : 0,
                                                  reinterpret_cast<T*>(a.out), a.out_cursor, a.out_cap, a.shift, a.fan, a.ctl,
-                                                 a.row_base);
+                                                 a.row_base, a.dom);
 }
 
 // rows per tile of the pipelined scatter for one element format
@@ -1131,6 +1143,303 @@ void launch_join3(bool mat, const JoinArgs& a, int rbits, const DeviceInfo& di, 
   if (mat) FJ_J3(true); else FJ_J3(false);
 #undef FJ_J3
   ++*launches;
+}
+
+// ================================================================================= dense key domain: direct-address join
+// k_djoin (packed rows whose keys lie in a dense domain [0, klimit)): ONE scatter pass
+// by the low 8 key bits, then no hashing at all — partition p owns a direct-address region
+// region_p[key >> 8] = value + 1 (0 = absent) of 4-byte slots in HBM that is zeroed, filled and probed while
+// it is L2 RESIDENT: the kernel walks the 256 partitions in groups sized so that three groups of regions
+// (one being zeroed, one being filled, one being probed) fit the L2 budget.  This replaces the second
+// scatter pass of both sides and the shared-memory partition join (k_scatter2 x2 + k_join3) by one
+// random 4-byte L2 store per build row and one random 4-byte L2 load per probe row.
+//
+// Persistent CTAs (all co-resident) pull work items in a fixed global order from an atomic ticket:
+//   step s:  Z(group s) zero regions | B(group s-1) store build rows | P(group s-2) probe | C(group s-2) count
+// B(p, .) waits until all Z(p, .) are done, P/C(p, .) until all B(p, .) are done (per-partition completion
+// counters; a waiter only ever waits for items with smaller tickets, which are running or finished, so the
+// spin cannot deadlock).  Duplicate build keys are found without atomics: C counts the non-empty slots and
+// the host compares with the number of rows stored (fewer slots than rows <=> some key was stored twice ->
+// CTL_DUP, the exact keep-first path runs instead).  The count-only variant skips C (a duplicate does not
+// change the key set).
+constexpr int DJ_THREADS = 512;
+constexpr int DJ_WARPS = DJ_THREADS / 32;
+constexpr int DJ_F = 256;                 // partitions = low 8 key bits
+constexpr int DJ_IPT = 8;
+constexpr int DJ_ROWS = DJ_THREADS * DJ_IPT;  // rows per build / probe item
+constexpr int DJ_ZSLOTS = 16384;          // direct-address slots per zero / count item (64 KB)
+constexpr int DJ_MAXSEG = 4 * (DJ_F + 2);
+enum { DJ_Z = 0, DJ_B = 1, DJ_P = 2, DJ_C = 3, DJ_DONE = 4 };
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_cg_u128(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// one 32-byte sector of a read-once stream: no L1 allocation, first in line for L2 eviction (LDG.E.NA.EFL2.256) so
+// that the stream does not push the direct-address regions out of L2
+__device__ __forceinline__ void ld_stream256(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+
+template <bool MAT>
+__global__ void __launch_bounds__(DJ_THREADS, 2)
+    k_djoin(const unsigned long long* __restrict__ build, const uint32_t* __restrict__ bcnt, uint64_t cap_b,
+            const uint32_t* __restrict__ probe, const uint32_t* __restrict__ pcnt, uint64_t cap_p,
+            uint32_t* __restrict__ direct, uint64_t rstride /*slots per region, multiple of 4*/, uint64_t group_bytes,
+            Ctl* __restrict__ ctl, uint32_t* __restrict__ sync /*[0] ticket, [4..] zdone[256], bdone[256]*/,
+            unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_vals) {
+  __shared__ uint32_t s_seg[DJ_MAXSEG + 1];
+  __shared__ uint32_t s_preb[DJ_F + 1], s_prep[DJ_F + 1];
+  __shared__ uint32_t s_warp[DJ_WARPS];
+  __shared__ uint32_t s_item[3];
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t* ticket = sync;
+  uint32_t* zdone = sync + 4;
+  uint32_t* bdone = sync + 4 + DJ_F;
+
+  // an earlier kernel of this attempt gave up (key outside the dense domain, partition overflow): nothing to do
+  if (*reinterpret_cast<volatile unsigned int*>(&ctl->flags) & (CTL_NOT_DENSE | CTL_OVERFLOW)) return;
+  uint64_t reff64 = ((*reinterpret_cast<volatile unsigned long long*>(&ctl->max_key) >> 8) + 4) & ~3ull;  // slots in use per region
+  if (reff64 > rstride) reff64 = rstride;
+  const uint32_t reff = (uint32_t)reff64;
+  const uint32_t nz = (reff + DJ_ZSLOTS - 1) / DJ_ZSLOTS;
+  uint32_t gp = (uint32_t)(group_bytes / ((uint64_t)reff * 4));
+  gp = gp < 1 ? 1 : (gp > DJ_F ? DJ_F : gp);
+  const uint32_t ng = (DJ_F + gp - 1) / gp;
+
+  // ---- chunks per partition and their prefix sums
+  {
+    uint32_t cb = 0, cp = 0;
+    if (tid < DJ_F) {
+      uint64_t nb = bcnt[tid], np = pcnt[tid];
+      if (nb > cap_b) nb = cap_b;
+      if (np > cap_p) np = cap_p;
+      cb = (uint32_t)((nb + DJ_ROWS - 1) / DJ_ROWS);
+      cp = nb ? (uint32_t)((np + DJ_ROWS - 1) / DJ_ROWS) : 0u;  // no build rows: nothing can match
+    }
+    uint32_t total;
+    uint32_t pre = block_excl_scan_512(cb, s_warp, total);
+    if (tid < DJ_F) s_preb[tid] = pre;
+    if (tid == 0) s_preb[DJ_F] = total;
+    pre = block_excl_scan_512(cp, s_warp, total);
+    if (tid < DJ_F) s_prep[tid] = pre;
+    if (tid == 0) s_prep[DJ_F] = total;
+  }
+  __syncthreads();
+  // ---- the item order: 4 segments per step (Z, B, P, C); thread t sizes segments 3t .. 3t+2
+  const uint32_t nseg = 4 * (ng + 2);
+  auto seg_count = [&](uint32_t seg) -> uint32_t {
+    if (seg >= nseg) return 0u;
+    const uint32_t kind = seg & 3u, step = seg >> 2;
+    const uint32_t delay = kind == DJ_Z ? 0u : (kind == DJ_B ? 1u : 2u);
+    if (step < delay || step - delay >= ng) return 0u;
+    const uint32_t lo = (step - delay) * gp, hi = lo + gp < DJ_F ? lo + gp : DJ_F;
+    if (kind == DJ_Z) return (hi - lo) * nz;
+    if (kind == DJ_C) return MAT ? (hi - lo) * nz : 0u;
+    if (kind == DJ_B) return s_preb[hi] - s_preb[lo];
+    return s_prep[hi] - s_prep[lo];
+  };
+  uint32_t total_items;
+  {
+    const uint32_t c0 = seg_count(3 * tid), c1 = seg_count(3 * tid + 1), c2 = seg_count(3 * tid + 2);
+    const uint32_t pre = block_excl_scan_512(c0 + c1 + c2, s_warp, total_items);
+    if (3u * tid < nseg + 1) s_seg[3 * tid] = pre;
+    if (3u * tid + 1 < nseg + 1) s_seg[3 * tid + 1] = pre + c0;
+    if (3u * tid + 2 < nseg + 1) s_seg[3 * tid + 2] = pre + c0 + c1;
+  }
+  __syncthreads();
+
+  unsigned long long local_count = 0;
+  uint32_t rows_stored = 0, slots_set = 0;
+  uint32_t cur = 0;
+  if (tid == 0) cur = atomicAdd(ticket, 1u);
+  for (;;) {
+    uint32_t nxt = 0;
+    if (tid == 0) {
+      if (cur < total_items) {
+        nxt = atomicAdd(ticket, 1u);  // consumed after this item: its latency hides behind the work
+        uint32_t lo = 0, hi = nseg;   // largest seg with s_seg[seg] <= cur
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s_seg[mid] <= cur) lo = mid; else hi = mid;
+        }
+        const uint32_t kind = lo & 3u, step = lo >> 2;
+        const uint32_t g = step - (kind == DJ_Z ? 0u : (kind == DJ_B ? 1u : 2u));
+        const uint32_t p0 = g * gp, p1 = p0 + gp < DJ_F ? p0 + gp : DJ_F;
+        const uint32_t j = cur - s_seg[lo];
+        uint32_t p, c;
+        if (kind == DJ_Z || kind == DJ_C) {
+          p = p0 + j / nz;
+          c = j - (p - p0) * nz;
+        } else {
+          const uint32_t* pre = kind == DJ_B ? s_preb : s_prep;
+          const uint32_t want = pre[p0] + j;
+          uint32_t a = p0, b = p1;  // largest p with pre[p] <= want
+          while (b - a > 1) {
+            const uint32_t mid = (a + b) >> 1;
+            if (pre[mid] <= want) a = mid; else b = mid;
+          }
+          p = a;
+          c = want - pre[p];
+        }
+        if (kind != DJ_Z) {
+          while (ld_acquire_u32(zdone + p) < nz) __nanosleep(64);
+          if (kind != DJ_B) {
+            const uint32_t need = s_preb[p + 1] - s_preb[p];
+            while (ld_acquire_u32(bdone + p) < need) __nanosleep(64);
+          }
+        }
+        s_item[0] = kind; s_item[1] = p; s_item[2] = c;
+      } else {
+        s_item[0] = DJ_DONE;
+      }
+    }
+    __syncthreads();
+    const uint32_t kind = s_item[0], p = s_item[1], c = s_item[2];
+    if (kind == DJ_DONE) break;
+    uint32_t* region = direct + (uint64_t)p * rstride;
+
+    if (kind == DJ_Z) {
+      uint4* dst = reinterpret_cast<uint4*>(region + (uint64_t)c * DJ_ZSLOTS);
+      const uint32_t n4 = ((reff - c * DJ_ZSLOTS) < (uint32_t)DJ_ZSLOTS ? (reff - c * DJ_ZSLOTS) : (uint32_t)DJ_ZSLOTS) / 4;
+      for (uint32_t i = tid; i < n4; i += DJ_THREADS) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (kind == DJ_C) {
+      const uint4* src = reinterpret_cast<const uint4*>(region + (uint64_t)c * DJ_ZSLOTS);
+      const uint32_t n4 = ((reff - c * DJ_ZSLOTS) < (uint32_t)DJ_ZSLOTS ? (reff - c * DJ_ZSLOTS) : (uint32_t)DJ_ZSLOTS) / 4;
+      for (uint32_t i = tid; i < n4; i += DJ_THREADS) {
+        const uint4 v = ld_cg_u128(src + i);
+        slots_set += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+      }
+    } else if (kind == DJ_B) {
+      uint64_t nbp = bcnt[p];
+      if (nbp > cap_b) nbp = cap_b;
+      const uint32_t cnt = (uint32_t)((nbp - (uint64_t)c * DJ_ROWS) < (uint64_t)DJ_ROWS ? (nbp - (uint64_t)c * DJ_ROWS) : DJ_ROWS);
+      const unsigned long long* rows = build + (uint64_t)p * cap_b + (uint64_t)c * DJ_ROWS;
+      uint32_t w[2][8];  // two 32-byte units per thread: rows 4u .. 4u + 3 as {value, key} word pairs
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t u = i * DJ_THREADS + tid;
+        if (4u * u < cnt) {
+          ld_stream256(rows + 4u * u, w[i]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) w[i][r] = 0xFFFFFFFFu;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t u = i * DJ_THREADS + tid;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t k = w[i][2 * r + 1];  // packed row = key32 << 32 | value32 (little endian)
+          const bool ok = (4u * u + r < cnt) & (k != 0xFFFFFFFFu);  // 0xFFFFFFFF: padding written by k_scatter2
+          if (ok) region[k >> 8] = w[i][2 * r] + 1u;
+          rows_stored += ok ? 1u : 0u;
+        }
+      }
+    } else {  // DJ_P
+      uint64_t npp = pcnt[p];
+      if (npp > cap_p) npp = cap_p;
+      const uint32_t cnt = (uint32_t)((npp - (uint64_t)c * DJ_ROWS) < (uint64_t)DJ_ROWS ? (npp - (uint64_t)c * DJ_ROWS) : DJ_ROWS);
+      const uint32_t* rows = probe + (uint64_t)p * cap_p + (uint64_t)c * DJ_ROWS;
+      uint32_t key[DJ_IPT], val[DJ_IPT];
+      if (8u * tid < cnt) {  // one 32-byte unit per thread: rows 8 tid .. 8 tid + 7
+        ld_stream256(rows + 8u * tid, key);
+      } else {
+#pragma unroll
+        for (int i = 0; i < DJ_IPT; ++i) key[i] = 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int i = 0; i < DJ_IPT; ++i) key[i] = 8u * tid + i < cnt ? key[i] : 0xFFFFFFFFu;
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int i = 0; i < DJ_IPT; ++i) {  // all 8 L2 gathers in flight
+        const uint32_t idx = key[i] >> 8;
+        const bool ok = (key[i] != 0xFFFFFFFFu) & (idx < reff);  // hole / past the end / beyond every build key
+        val[i] = ok ? ld_cg_u32(region + idx) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < DJ_IPT; ++i) hitmask |= val[i] ? (1u << i) : 0u;
+      if (!MAT) {
+        local_count += __popc(hitmask);
+      } else {
+        uint32_t off[DJ_IPT];
+        uint32_t wtot = 0;
+#pragma unroll
+        for (int i = 0; i < DJ_IPT; ++i) {
+          const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> i) & 1u);
+          off[i] = wtot + __popc(bal & lanemask_lt());
+          wtot += __popc(bal);
+        }
+        unsigned long long base = 0;
+        if (lane == 0 && wtot) {
+          base = atomicAdd(&ctl->out_cursor, (unsigned long long)wtot);
+          local_count += wtot;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int i = 0; i < DJ_IPT; ++i) {
+          if ((hitmask >> i) & 1u) {
+            st_stream(out_keys + base + off[i], (unsigned long long)key[i]);
+            st_stream(out_vals + base + off[i], (unsigned long long)(val[i] - 1u));
+          }
+        }
+      }
+    }
+    __syncthreads();  // the item is complete (its stores are ordered before thread 0's fence); s_item is free
+    if (tid == 0) {
+      if (kind == DJ_Z || kind == DJ_B) {
+        __threadfence();
+        atomicAdd((kind == DJ_Z ? zdone : bdone) + p, 1u);
+      }
+      cur = nxt;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
+    rows_stored += __shfl_xor_sync(0xffffffffu, rows_stored, d);
+    slots_set += __shfl_xor_sync(0xffffffffu, slots_set, d);
+  }
+  if (lane == 0) {
+    if (local_count) atomicAdd(&ctl->match_count, local_count);
+    if (rows_stored) atomicAdd(&ctl->dense_rows, (unsigned long long)rows_stored);
+    if (slots_set) atomicAdd(&ctl->dense_slots, (unsigned long long)slots_set);
+  }
+}
+
+size_t djoin_sync_words() { return 4 + 2 * DJ_F; }
+uint32_t djoin_fan() { return DJ_F; }
+
+bool launch_djoin(bool mat, const DjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  int occ = 0;
+  cudaError_t e = mat ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_djoin<true>, DJ_THREADS, 0)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_djoin<false>, DJ_THREADS, 0);
+  if (e != cudaSuccess || occ < 1) return false;  // cannot guarantee co-residency: the caller takes the general path
+  const unsigned grid = (unsigned)(di.sms * occ);  // every CTA must be resident: the items synchronise by spinning
+  if (mat)
+    k_djoin<true><<<grid, DJ_THREADS, 0, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
+                                               reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride,
+                                               a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals);
+  else
+    k_djoin<false><<<grid, DJ_THREADS, 0, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
+                                                reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride,
+                                                a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals);
+  ++*launches;
+  return true;
 }
 
 // probe rows whose key is the out-of-band sentinel (wide path only)

@@ -29,6 +29,9 @@ __global__ void k_init_ctl(Ctl* ctl) {
   ctl->sentinel_probes = 0;
   ctl->flags = 0;
   ctl->pad = 0;
+  ctl->max_key = 0;
+  ctl->dense_rows = 0;
+  ctl->dense_slots = 0;
 }
 void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ctl); }
 
@@ -46,6 +49,9 @@ __global__ void __launch_bounds__(512) k_prepare(Ctl* __restrict__ ctl, uint4* _
     ctl->sentinel_probes = 0;
     ctl->flags = 0;
     ctl->pad = 0;
+    ctl->max_key = 0;
+    ctl->dense_rows = 0;
+    ctl->dense_slots = 0;
   }
   const uint4 f = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0u, 0u, 0u, 0u);
   for (uint64_t i = t; i < n_ones; i += stride) ones[i] = f;
@@ -580,6 +586,113 @@ static uint64_t persistent_grid(K kern, int threads, size_t smem, uint64_t ntile
   }
   uint64_t grid = (uint64_t)di.sms * ctas_per_sm;
   return grid > ntiles ? ntiles : grid;
+}
+
+// ------------------------------------------------------------------------------------ dense key domain
+// Data-dependent fast path of the count entry points: when every build key is
+// smaller than `dbits` (optimistic; a key outside raises CTL_NOT_DENSE and the host re-runs the attempt on
+// the general path) the build side is an exact membership bitmap of dbits bits — a Bloom filter without
+// false positives, so the count needs no table at all: num_matches = |{j : bit[pk[j]]}|
+// (hash_join.cpp:536-567 counts exactly the probe rows whose key is in the build set; duplicates in the
+// build side do not change that set).  The bitmap is staged in shared memory by TMA like the Bloom filter.
+__global__ void __launch_bounds__(256) k_build_bitmap(uint32_t* __restrict__ bitmap, unsigned long long dbits,
+                                                      const unsigned long long* __restrict__ bk, uint64_t nb,
+                                                      Ctl* __restrict__ ctl) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nb; i += stride) {
+    const unsigned long long k = bk[i];
+    if (k >= dbits) {
+      atomicOr(&ctl->flags, CTL_NOT_DENSE);  // attempt is abandoned by the host
+      return;
+    }
+    atomicOr(bitmap + (uint32_t)(k >> 5), 1u << ((uint32_t)k & 31u));
+  }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    k_probe_count_dense(const unsigned long long* __restrict__ pk, uint64_t np, const uint32_t* __restrict__ bitmap,
+                        uint32_t dwords /*multiple of 4*/, Ctl* __restrict__ ctl, int vec_ok) {
+  constexpr uint32_t TILE = THREADS * PROBE_KPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const uint32_t* sbm = reinterpret_cast<const uint32_t*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  if (*reinterpret_cast<volatile unsigned int*>(&ctl->flags) & CTL_NOT_DENSE) return;  // block-uniform, before any TMA
+  stage_bloom(smem_raw, bitmap, dwords, &s_bar);
+  const unsigned long long dbits = (unsigned long long)dwords * 32ull;
+
+  uint32_t cnt = 0;
+  const uint64_t ntiles = (np + TILE - 1) / TILE;
+  auto do_tile = [&](const unsigned long long (&key)[PROBE_KPT], const uint32_t valid) {
+    uint32_t w[PROBE_KPT];
+#pragma unroll
+    for (int q = 0; q < PROBE_KPT; ++q) {
+      const bool in = key[q] < dbits;
+      w[q] = sbm[in ? (uint32_t)(key[q] >> 5) : 0u];
+      w[q] = in ? w[q] : 0u;
+    }
+    uint32_t hits = 0;
+#pragma unroll
+    for (int q = 0; q < PROBE_KPT; ++q) hits |= ((w[q] >> ((uint32_t)key[q] & 31u)) & 1u) << q;
+    cnt += __popc(hits & valid);
+  };
+  unsigned long long ka[PROBE_KPT], kb[PROBE_KPT];
+  uint32_t va = 0, vb = 0;
+  auto fetch = [&](uint64_t tile, unsigned long long (&k)[PROBE_KPT]) -> uint32_t {
+    const uint64_t tb = tile * TILE;
+    return load_tile<THREADS>(pk, np, tb, vec_ok && tb + TILE <= np, k);
+  };
+  uint64_t tile = blockIdx.x;
+  if (tile < ntiles) va = fetch(tile, ka);
+  mbar_wait(&s_bar, 0);
+  while (tile < ntiles) {
+    const uint64_t t1 = tile + gridDim.x;
+    if (t1 < ntiles) vb = fetch(t1, kb);
+    do_tile(ka, va);
+    if (t1 >= ntiles) break;
+    const uint64_t t2 = t1 + gridDim.x;
+    if (t2 < ntiles) va = fetch(t2, ka);
+    do_tile(kb, vb);
+    tile = t2;
+  }
+  unsigned long long total = cnt;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+  if (lane == 0 && total) atomicAdd(&ctl->match_count, total);
+}
+
+size_t probe_smem_bitmap_limit_bytes(const DeviceInfo& di) {
+  return di.smem_optin > 8192 ? ((di.smem_optin - 8192) / 16) * 16 : 0;
+}
+
+void launch_build_bitmap(uint32_t* bitmap, uint64_t dbits, const unsigned long long* bk, uint64_t nb, Ctl* ctl,
+                         const DeviceInfo& di, cudaStream_t st, int* launches) {
+  if (nb == 0) return;
+  const int threads = 256;
+  const uint64_t want = (nb + threads - 1) / threads, cap = (uint64_t)di.sms * 16;
+  k_build_bitmap<<<(int)(want < cap ? want : cap), threads, 0, st>>>(bitmap, dbits, bk, nb, ctl);
+  ++*launches;
+}
+
+template <int THREADS>
+static void launch_count_dense_inst(const unsigned long long* pk, uint64_t np, const uint32_t* bitmap, uint32_t dwords,
+                                    Ctl* ctl, const DeviceInfo& di, cudaStream_t st) {
+  auto kern = k_probe_count_dense<THREADS>;
+  const size_t smem = (size_t)dwords * 4;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
+  const uint64_t grid = persistent_grid(kern, THREADS, smem, (np + tile - 1) / tile, 0, di);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(pk, np, bitmap, dwords, ctl, vec_ok);
+}
+void launch_probe_count_dense(const unsigned long long* pk, uint64_t np, const uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
+                              const DeviceInfo& di, cudaStream_t st, int* launches) {
+  if (np == 0) return;
+  // two 512-thread CTAs per SM while two bitmaps fit next to each other, one 1024-thread CTA otherwise
+  if ((size_t)dwords * 4 * 2 + 4096 <= di.smem_optin) launch_count_dense_inst<512>(pk, np, bitmap, dwords, ctl, di, st);
+  else launch_count_dense_inst<1024>(pk, np, bitmap, dwords, ctl, di, st);
+  ++*launches;
 }
 
 template <bool NARROW, int BLOOM, int THREADS>

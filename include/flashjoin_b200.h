@@ -79,13 +79,16 @@ typedef struct fj_stats {
   uint64_t h2d_bytes;
   int32_t path;        /* FJ_ALGO_SCALAR or FJ_ALGO_RADIX actually taken                           */
   int32_t narrow;      /* 1 = packed 32-bit key|value slots were used, 0 = 16-byte slots           */
-  int32_t bloom_kind;  /* 0 none, 1 shared-memory resident, 2 global (L2) resident                 */
+  int32_t bloom_kind;  /* 0 none, 1 shared-memory resident, 2 global (L2) resident,                */
+                       /* 3 exact membership bitmap (dense key domain, count only; no table)       */
   int32_t attempts;    /* 1 normally; >1 when an optimistic attempt was abandoned and re-run       */
   int32_t dedup_exact; /* 1 = duplicate build keys were seen and the keep-first slow path ran      */
   int32_t kernel_launches; /* number of this library's kernels launched by the call               */
   int32_t radix_bits1, radix_bits2; /* fan-out of the radix passes (0 = pass not run)              */
   int32_t n_gpus;
-  int32_t reserved[7];
+  int32_t dense;       /* 1 = a dense-key-domain fast path produced the result (bitmap count or     */
+                       /* direct-address radix join); 0 = the general hash path                    */
+  int32_t reserved[6];
 } fj_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------
@@ -124,7 +127,9 @@ FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values,
  * hash_join.cpp:38, :79, :99, :302, :393, :576) ------------------------------------------------
  * keys: "load_pct" (table load factor, %), "load_pct_auto" (1: small tables drop to 25 %), "bloom_bits_per_key", "adaptive_table_l2_pct",
  *       "radix_sub_rows" (target build rows per shared-memory partition), "radix_optimistic",
- *       "smem_bloom" (0/1), "join3" (0/1: collision-free pipelined partition join for packed rows), "probe_ctas_per_sm", "chunk_rows" (host-input pipelining chunk). */
+ *       "smem_bloom" (0/1), "join3" (0/1: collision-free pipelined partition join for packed rows), "probe_ctas_per_sm", "chunk_rows" (host-input pipelining chunk),
+ *       "dense" (0/1: optimistic dense-key-domain fast paths), "dense_min_rows" (smallest build side that takes the
+ *       direct-address radix join), "dense_group_mb" (MB of direct-address regions per L2 pipeline stage). */
 FJ_API fj_status fj_config_set(const char* key, int64_t value);
 FJ_API fj_status fj_config_get(const char* key, int64_t* value);
 

@@ -185,7 +185,9 @@ def test_duplicate_build_keys_keep_first(fj):
     for algo, bloom, mat in ALL:
         n, pairs = run_entry(fj, algo, bloom, mat, bk, bv, pk)
         assert n == n0
-        assert fj.last_stats()["dedup_exact"] is True
+        st = fj.last_stats()
+        # the exact bitmap count (dense key domain) is a set: duplicates need no keep-first pass there
+        assert st["dedup_exact"] is True or (not mat and st["dense"] == 1), st
         if mat:
             assert np.array_equal(O.sorted_pairs(*pairs), O.sorted_pairs(k0, v0))
 
@@ -201,22 +203,26 @@ def test_probe_skew(fj):
 
 def test_bloom_invariance_and_kinds(fj):
     bk, bv, pk = g1(500_000, 50_000, 10)
+    n_dense, _ = fj.hash_join_count_bloom(bk, bv, pk)
+    assert fj.last_stats()["bloom_kind"] == "bitmap" and fj.last_stats()["dense"] == 1
+    fj.configure(dense=0)  # the general hash path: table + register-blocked Bloom filter
     n_plain, _ = fj.hash_join_count(bk, bv, pk)
     n_bloom, _ = fj.hash_join_count_bloom(bk, bv, pk)
-    assert fj.last_stats()["bloom_kind"] == "smem"
-    assert n_plain == n_bloom == O.np_join(bk, bv, pk)[0]
+    assert fj.last_stats()["bloom_kind"] == "smem" and fj.last_stats()["dense"] == 0
+    assert n_dense == n_plain == n_bloom == O.np_join(bk, bv, pk)[0]
     fj.configure(smem_bloom=0)
     try:
         n_g, _ = fj.hash_join_count_bloom(bk, bv, pk)
         assert fj.last_stats()["bloom_kind"] == "global" and n_g == n_plain
         n_g, _ = fj.hash_join_bloom(bk, bv, pk)
         assert n_g == n_plain
-    finally:
+        # a build side too large for the shared-memory filter takes the global (L2) filter
         fj.configure(smem_bloom=1)
-    # a build side too large for the shared-memory filter takes the global (L2) filter
-    bk, bv, pk = g1(600_000, 400_000, 10)
-    n_b, _ = fj.hash_join_count_bloom(bk, bv, pk)
-    assert fj.last_stats()["bloom_kind"] == "global" and n_b == O.np_join(bk, bv, pk)[0]
+        bk, bv, pk = g1(600_000, 400_000, 10)
+        n_b, _ = fj.hash_join_count_bloom(bk, bv, pk)
+        assert fj.last_stats()["bloom_kind"] == "global" and n_b == O.np_join(bk, bv, pk)[0]
+    finally:
+        fj.configure(smem_bloom=1, dense=1)
 
 
 def test_radix_two_pass_small_partitions(fj):
@@ -328,6 +334,106 @@ def test_idempotence_and_arena_reuse(fj):
     assert len(set(r)) == 1
     small = np.arange(10, dtype=np.uint64)
     assert fj.hash_join_count(small, small, small)[0] == 10  # a smaller join after a larger one
+
+
+# ------------------------------------------------------------------------------------------------ dense key domain
+def test_dense_bitmap_count(fj):
+    """Count entry points on a dense key domain: exact membership bitmap, no table."""
+    for N, ny, pct in ((500_000, 50_000, 10), (300_000, 1_000, 90), (2_000_000, 700_000, 90)):
+        bk, bv, pk = g1(N, ny, pct)
+        n0 = O.np_join(bk, bv, pk)[0]
+        for name in ("hash_join_count", "hash_join_count_bloom", "adaptive_join_count", "adaptive_join_count_bloom"):
+            n, _ = getattr(fj, name)(bk, bv, pk)
+            st = fj.last_stats()
+            assert n == n0 and st["dense"] == 1 and st["bloom_kind"] == "bitmap" and st["attempts"] == 1, (name, st)
+    # key 0, duplicates in the build side (a set: no keep-first pass needed), probe keys far outside the domain
+    bk = np.array([0, 3, 3, 7, 200, 0], dtype=np.uint64)
+    pk = np.array([0, 0, 3, 4, 7, 200, 2**40, 2**64 - 1, 255, 256], dtype=np.uint64)
+    n, _ = fj.hash_join_count(bk, bk, pk)
+    assert n == 6 and fj.last_stats()["dense"] == 1
+    # one build key outside the optimistic domain: the attempt is abandoned and the hash path answers
+    bk, bv, pk = g1(500_000, 50_000, 10)
+    bk = bk.copy(); bk[777] = 10**9
+    n, _ = fj.hash_join_count_bloom(bk, bv, pk)
+    st = fj.last_stats()
+    assert n == O.np_join(bk, bv, pk)[0] and st["dense"] == 0 and st["attempts"] == 2 and st["bloom_kind"] == "smem", st
+    # values play no role in a count: 64-bit values do not disturb the bitmap path
+    bk, bv, pk = g1(200_000, 20_000, 90)
+    bv = bv.copy(); bv[5] = 2**50
+    n, _ = fj.hash_join_count(bk, bv, pk)
+    assert n == O.np_join(bk, bv, pk)[0] and fj.last_stats()["dense"] == 1
+
+
+@pytest.fixture()
+def dense_small(fj):
+    fj.configure(dense_min_rows=1024)
+    yield fj
+    fj.configure(dense_min_rows=1 << 20, dense_group_mb=16, dense=1)
+
+
+@pytest.mark.parametrize("group_mb", [16, 1])
+def test_dense_radix_direct_join(dense_small, group_mb):
+    """Radix entry points on a dense key domain: one scatter pass by the low key bits + direct-address join
+    (k_djoin); group_mb = 1 forces many L2 groups (the whole Z/B/P/C item pipeline with its waits)."""
+    fj = dense_small
+    fj.configure(dense_group_mb=group_mb)
+    for N, ny, pct in ((400_000, 300_000, 90), (3_000_000, 2_000_000, 90), (1_000_000, 70_000, 10)):
+        bk, bv, pk = g1(N, ny, pct)
+        expect = O.np_join(bk, bv, pk)
+        check_all_entry_points(fj, bk, bv, pk, expect=expect, algos=("radix",))
+        st = fj.last_stats()
+        assert st["dense"] == 1 and st["path"] == "radix" and st["radix_bits"] == (8, 0) and st["attempts"] == 1, st
+    fj.configure(dense=0)
+    n, _ = fj.hash_join_radix(bk, bv, pk)
+    assert n == expect[0] and fj.last_stats()["dense"] == 0
+    fj.configure(dense=1)
+
+
+def test_dense_radix_edges(dense_small):
+    fj = dense_small
+    rng = np.random.default_rng(11)
+    # key 0, sparse low bits (only even keys: half of the partitions stay empty), probe keys beyond the domain
+    bk = (rng.permutation(60_000) * 2).astype(np.uint64)  # 60 000 rows -> optimistic key bound 2^17
+    bv = rng.integers(0, 2**32 - 1, bk.size).astype(np.uint64)
+    pk = np.concatenate([rng.integers(0, 140_000, 500_000).astype(np.uint64),
+                         np.array([2**17 - 1, 2**17, 2**31, 2**32 - 1, 2**32, 2**63, 2**64 - 1], dtype=np.uint64)])
+    check_all_entry_points(fj, bk, bv, pk, algos=("radix",))
+    assert fj.last_stats()["dense"] == 1
+    # the largest value a packed row can hold does not fit value + 1: general packed path
+    bv2 = bv.copy(); bv2[100] = 2**32 - 1
+    check_all_entry_points(fj, bk, bv2, pk, algos=("radix",))
+    st = fj.last_stats()
+    assert st["dense"] == 0 and st["narrow"] is True and st["attempts"] == 2, st
+    # a build key outside the optimistic bound 2^(ceil(log2 nb) + 1)
+    bk3 = bk.copy(); bk3[5] = 3_000_000
+    check_all_entry_points(fj, bk3, bv, pk, algos=("radix",))
+    assert fj.last_stats()["dense"] == 0
+    # 64-bit key: dense attempt, packed attempt, wide rows
+    bk4 = bk.copy(); bk4[5] = 2**40
+    n, _ = fj.hash_join_radix(bk4, bv, pk)
+    st = fj.last_stats()
+    assert n == O.np_join(bk4, bv, pk)[0] and st["narrow"] is False and st["attempts"] == 3, st
+    # duplicate build keys: fewer direct-address slots than rows -> exact keep-first path
+    bk5 = rng.integers(0, 50_000, 120_000).astype(np.uint64)
+    bv5 = np.arange(bk5.size, dtype=np.uint64)
+    pk5 = rng.integers(0, 60_000, 300_000).astype(np.uint64)
+    n0, k0, v0 = O.join("radix", False, True, bk5, bv5, pk5)
+    n, _ = fj.hash_join_radix(bk5, bv5, pk5)
+    assert n == n0 and fj.last_stats()["dedup_exact"] is True
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(k0, v0))
+    n, _ = fj.hash_join_count_radix(bk5, bv5, pk5)  # a count is a set operation: the dense path answers directly
+    assert n == n0 and fj.last_stats()["dense"] == 1
+    # skewed low key bits (only 100 of the 256 residues occur, inside the optimistic bound 2^18): the partitions of
+    # those residues overflow their fixed-capacity regions -> hash partitioning instead
+    allk = np.arange(262_144, dtype=np.uint64)
+    bk6 = rng.permutation(allk[(allk & np.uint64(255)) < 100])[:100_000]
+    pk6 = rng.choice(allk, 400_000)
+    check_all_entry_points(fj, bk6, bk6 + np.uint64(1), pk6, algos=("radix",))
+    st = fj.last_stats()
+    assert st["dense"] == 0 and st["path"] == "radix" and st["attempts"] == 2, st
+    # all probe rows carry one key
+    bk7 = np.arange(1, 50_001, dtype=np.uint64)
+    check_all_entry_points(fj, bk7, bk7 * np.uint64(7), np.full(600_000, 4242, dtype=np.uint64), algos=("radix",))
 
 
 # ------------------------------------------------------------------------------------------------ full sizes
