@@ -184,7 +184,8 @@ def main() -> None:
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-other", action="store_true", help="skip the additional C3 measurement of a default N=1 run")
+    ap.add_argument("--no-other", action="store_true", help="skip the additional C3 / general-path measurements of a default N=1 run")
+    ap.add_argument("--no-dense", action="store_true", help="switch the dense-key-domain fast paths off (general hash path only)")
     ap.add_argument("--_cpu_worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3 and not args._cpu_worker and args.impl == "ours":
@@ -253,8 +254,17 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def measure(cfg_name: str, steps: int, warmup: int, want_e2e: bool) -> dict:
+    def dominant_kernel(last: dict) -> str:
+        if last["path"] == "radix":
+            if last["dense"]:
+                return "k_djoin (L2-resident direct-address join)"
+            return "k_join3 (shared-memory partition join)" if last["radix_bits2"] else "k_join (shared-memory partition join)"
+        return "k_probe_count_dense (exact bitmap)" if last["dense"] else "k_probe_count"
+
+    def measure(cfg_name: str, steps: int, warmup: int, want_e2e: bool, dense: bool = True) -> dict:
         from flash_hash_join_b200.dist import row_slice
+
+        capi.config_set(dense=1 if dense else 0)
 
         w = WORKLOADS[cfg_name]
         ny, pct = w["ny"], w["pct"]
@@ -320,11 +330,11 @@ def main() -> None:
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get(cfg_name, {}).get("dram_bytes_per_launch")
+                traffic = json.loads(tp.read_text()).get(cfg_name + ("" if last["dense"] else "_general"), {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         alg_step = (16.0 * ny + 8.0 * n_total + 16.0 * matches) if w["mat"] else 8.0 * (ny + n_total)
-        roofline = {"bound": "hbm", "kernel": "k_join3 (shared-memory partition join)" if last["path"] == "radix" else "k_probe_count",
+        roofline = {"bound": "hbm", "kernel": dominant_kernel(last),
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes_kernel, "kernel_ms": kern_s * 1e3,
                     "whole_step_frac": (alg_step / (elapsed / steps) * 1e-9) / (peak * world),
@@ -364,6 +374,7 @@ def main() -> None:
             del h_bk, h_bv, h_pk
         for x in (d_bk, d_bv, d_pk):
             x.free()
+        capi.config_set(dense=1)
         if shuffle:
             par = f"both sides split over {world} GPUs, rows hash-partitioned by destination, NCCL all-to-all-v, local radix join, count ncclAllReduce"
         elif world > 1:
@@ -374,16 +385,36 @@ def main() -> None:
                 "launches": launches, "roofline": roofline, "e2e": e2e, "scaling": "strong" if shuffle else "weak", "parallelism": par,
                 "phases": {k: v / steps * 1e3 for k, v in phases.items()}}
 
-    m = measure(args.config, args.steps, args.warmup, not args.no_e2e)
+    def summary(o: dict) -> dict:
+        return {"workload": o["w"]["desc"], "value": o["value"], "unit": "rows/s", "ms_per_step": o["elapsed"] / o["steps"] * 1e3,
+                "matches": o["matches"], "path": o["last"]["path"], "dense_key_domain": bool(o["last"]["dense"]),
+                "filter": o["last"]["bloom_kind"], "radix_bits": [o["last"]["radix_bits1"], o["last"]["radix_bits2"]],
+                "narrow_rows": bool(o["last"]["narrow"]), "phases_ms_per_step": o["phases"], "roofline": o["roofline"],
+                "gpu_launches": o["launches"]}
+
+    m = measure(args.config, args.steps, args.warmup, not args.no_e2e, dense=not args.no_dense)
     w, matches = m["w"], m["matches"]
+    # the same workload with the data-dependent dense-key-domain fast paths switched off: the general hash path
+    # (table + register-blocked Bloom filter / two radix passes + shared-memory join)
+    general = None
+    if world == 1 and m["last"]["dense"] and not args.no_other:
+        try:
+            g = measure(args.config, max(5, args.steps // 2), 3, False, dense=False)
+            general = summary(g)
+            if g["matches"] != matches:
+                general["MISMATCH"] = f"general path counted {g['matches']}, dense path {matches}"
+        except Exception as e:
+            general = {"error": str(e)[:300]}
     other = None
     if world == 1 and args.config == "C2" and not args.no_other:
         try:
-            o = measure("C3", 5, 3, False)
-            other = {"C3": {"workload": o["w"]["desc"], "value": o["value"], "unit": "rows/s", "ms_per_step": o["elapsed"] / o["steps"] * 1e3,
-                            "matches": o["matches"], "path": o["last"]["path"], "radix_bits": [o["last"]["radix_bits1"], o["last"]["radix_bits2"]],
-                            "narrow_rows": bool(o["last"]["narrow"]), "phases_ms_per_step": o["phases"], "roofline": o["roofline"],
-                            "gpu_launches": o["launches"]}}
+            o = measure("C3", 5, 3, False, dense=not args.no_dense)
+            other = {"C3": summary(o)}
+            if o["last"]["dense"]:
+                og = measure("C3", 5, 3, False, dense=False)
+                other["C3"]["general_path"] = summary(og)
+                if og["matches"] != o["matches"]:
+                    other["C3"]["MISMATCH"] = f"general path counted {og['matches']}, dense path {o['matches']}"
         except Exception as e:  # never lose the headline line
             other = {"C3": {"error": str(e)[:300]}}
     clocks = sampler.stop()
@@ -408,10 +439,13 @@ def main() -> None:
             "config": {"workload": w["desc"], "entry_point": w["entry"], "rows_probe_per_gpu": m["N"], "rows_probe_total": m["n_total"],
                        "rows_build": w["ny"], "match_pct": w["pct"],
                        "l2": f"inputs {8 * m['N'] / 1e6:.0f} MB per step > 126 MB L2 (no flush needed); table / partitions are rebuilt every step",
-                       "parallelism": m["parallelism"], "path": last["path"], "narrow_slots": bool(last["narrow"]), "bloom": last["bloom_kind"]},
+                       "parallelism": m["parallelism"], "path": last["path"], "narrow_slots": bool(last["narrow"]), "bloom": last["bloom_kind"],
+                       "dense_key_domain": bool(last["dense"]),
+                       "note": ("dense-key-domain fast path (keys < 2*rows: exact membership bitmap, no false positives, no table); "
+                                "the general hash path on the same inputs is under general_path") if last["dense"] else "general hash path"},
             "clocks": dict(clocks, window="sampled every 100 ms from before warm-up to the end of the e2e loop"),
             "e2e": m["e2e"], "gpu_launches": m["launches"], "roofline": m["roofline"], "cpu_baseline": cpu,
-            "matches": matches, "phases_ms_per_step": m["phases"], "other_configs": other,
+            "matches": matches, "phases_ms_per_step": m["phases"], "general_path": general, "other_configs": other,
         }
         print(json.dumps(line))
     if dist is not None:

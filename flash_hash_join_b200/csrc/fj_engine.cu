@@ -9,6 +9,7 @@
 // The reference allocates every table/partition/result buffer inside each call (std::vector,
 // make_unique through mimalloc); here buffers live in a grow-only device arena reused across calls.
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -125,6 +126,12 @@ struct Engine {
     cfg["dense"] = 1;               // optimistic dense-key-domain fast paths (exact bitmap count, direct-address radix join)
     cfg["dense_min_rows"] = 1 << 20;  // radix: smallest build side that takes the direct-address join
     cfg["dense_group_mb"] = 16;     // radix: direct-address regions kept L2 resident per pipeline stage (3 stages)
+    // FJ_CFG_<KEY>=<integer> in the environment overrides a default (e.g. FJ_CFG_DENSE=0)
+    for (auto& kv : cfg) {
+      std::string name = "FJ_CFG_";
+      for (char ch : kv.first) name += (char)std::toupper((unsigned char)ch);
+      if (const char* v = getenv(name.c_str())) kv.second = atoll(v);
+    }
     cfg["shuffle_virtual_ranks"] = 1;  // > 1: every rank owns that many shuffle destinations (exercises the
                                        // multi-destination scatter / exchange layout on few GPUs)
   }

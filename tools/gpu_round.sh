@@ -1,10 +1,10 @@
 #!/usr/bin/env bash
 # tools/gpu_round.sh <tag> [steps...] — one gpurun call's worth of work; everything lands in gpurun_out/<tag>/.
-# steps: tests quick bench ref launches ncu_c2 ncu_c3 sanitize   (default: all but sanitize)
+# steps: sanity tests quick bench ref launches ncu_c2 ncu_c3 ncu_general sanitize   (default: all but ncu_general, sanitize)
 set -u
 TAG=${1:-r1}
 shift || true
-STEPS=${*:-tests quick bench ref launches ncu_c2 ncu_c3}
+STEPS=${*:-sanity tests quick bench ref launches ncu_c2 ncu_c3}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 export FJ_OUT=$OUT
@@ -12,8 +12,18 @@ has() { [[ " $STEPS " == *" $1 "* ]]; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,memory.total,power.limit --format=csv > "$OUT/gpu.txt" 2>&1
 nproc > "$OUT/host_cores.txt"; free -g >> "$OUT/host_cores.txt"
 
+if has sanity; then
+  # the direct-address join synchronises CTAs by spinning: make sure it terminates and is right on a small case
+  # before anything larger depends on it; if not, the rest of the round runs with that path switched off
+  timeout 180 python tools/prof_case.py S radix mat --check --reps 2 --set dense_min_rows=1024 > "$OUT/sanity.log" 2>&1
+  rc=$?
+  echo "sanity exit $rc" >> "$OUT/sanity.log"
+  if [ $rc -ne 0 ]; then export FJ_CFG_DENSE_MIN_ROWS=4000000000; echo "dense radix path DISABLED for this round" >> "$OUT/sanity.log"; fi
+  timeout 180 compute-sanitizer --tool memcheck python tools/prof_case.py S radix mat --reps 1 --set dense_min_rows=1024 > "$OUT/memcheck_dense.log" 2>&1
+  tail -3 "$OUT/sanity.log" "$OUT/memcheck_dense.log"
+fi
 if has tests; then
-  timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > "$OUT/pytest_gpu.log" 2>&1
   echo "pytest exit $?" >> "$OUT/pytest_gpu.log"
   tail -5 "$OUT/pytest_gpu.log"
 fi
@@ -41,8 +51,14 @@ if has ncu_c2; then
     python tools/prof_case.py C2 scalar count bloom --reps 4 > "$OUT/ncu_c2.log" 2>&1
 fi
 if has ncu_c3; then
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_scatter2|k_join" -s 5 -c 5 -f -o "$OUT/c3_radix" \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_scatter2|k_djoin|k_join" -s 3 -c 3 -f -o "$OUT/c3_radix" \
     python tools/prof_case.py C3 radix mat --reps 3 > "$OUT/ncu_c3.log" 2>&1
+fi
+if has ncu_general; then  # the general hash path of the same two workloads (dense key domain switched off)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_probe -s 2 -c 1 -f -o "$OUT/c2_probe_general" \
+    python tools/prof_case.py C2 scalar count bloom --reps 4 --set dense=0 > "$OUT/ncu_c2_general.log" 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_scatter2|k_join" -s 5 -c 5 -f -o "$OUT/c3_radix_general" \
+    python tools/prof_case.py C3 radix mat --reps 3 --set dense=0 > "$OUT/ncu_c3_general.log" 2>&1
 fi
 if has sanitize; then
   timeout 900 compute-sanitizer --tool memcheck python tools/prof_case.py S scalar mat bloom --reps 1 > "$OUT/memcheck.log" 2>&1

@@ -25,7 +25,7 @@ def run(name, algo, flags, d, reps, N, cfg=None):
     n, sec, st = best
     out = {"case": name, "matches": n, "ms": round(sec * 1e3, 4), "rows_per_s": round(N / sec, 1),
            "alg_GBps": round(st["algorithmic_bytes"] / sec * 1e-9, 1), "frac": round(st["algorithmic_bytes"] / sec * 1e-9 / PEAK, 4),
-           "path": st["path"], "narrow": st["narrow"], "bloom": st["bloom_kind"], "attempts": st["attempts"],
+           "path": st["path"], "narrow": st["narrow"], "bloom": st["bloom_kind"], "dense": st["dense"], "attempts": st["attempts"],
            "clear_ms": round(st["clear_s"] * 1e3, 4), "build_ms": round(st["build_s"] * 1e3, 4),
            "part_ms": round(st["partition_s"] * 1e3, 4), "probe_ms": round(st["probe_s"] * 1e3, 4),
            "launches": st["kernel_launches"], "bits": [st["radix_bits1"], st["radix_bits2"]], "cfg": cfg or {}}
@@ -46,6 +46,9 @@ def main():
         pk = capi.generate_g2("probe", N, ny, pct, 108, 0, N)
         d = (bk, bv, pk)
         if ny <= 10**7:
+            run(f"{c} scalar count bloom (dense bitmap)", S, B, d, a.reps, N)
+            run(f"{c} adaptive count (dense bitmap)", A, 0, d, a.reps, N)
+            capi.config_set(dense=0)
             run(f"{c} scalar count bloom", S, B, d, a.reps, N)
             run(f"{c} scalar count", S, 0, d, a.reps, N)
             run(f"{c} scalar count bloom(global)", S, B, d, a.reps, N, {"smem_bloom": 0})
@@ -56,7 +59,14 @@ def main():
             run(f"{c} radix count", R, 0, d, a.reps, N)
             run(f"{c} radix mat", R, M, d, a.reps, N)
             run(f"{c} adaptive count", A, 0, d, a.reps, N)
+            capi.config_set(dense=1)
         else:
+            for mb in (16, 8, 32, 4, 24):
+                run(f"{c} radix mat (dense, direct-address)", R, M, d, a.reps, N, {"dense_group_mb": mb})
+            capi.config_set(dense_group_mb=16)
+            run(f"{c} radix count (dense, direct-address)", R, 0, d, a.reps, N)
+            run(f"{c} adaptive mat (dense)", A, M, d, a.reps, N)
+            capi.config_set(dense=0)
             run(f"{c} radix mat", R, M, d, a.reps, N)
             run(f"{c} radix count", R, 0, d, a.reps, N)
             run(f"{c} radix mat 2^16 parts", R, M, d, a.reps, N, {"radix_sub_rows": 2400})
@@ -65,6 +75,7 @@ def main():
             run(f"{c} scalar count", S, 0, d, max(1, a.reps // 2), N)
             run(f"{c} scalar mat", S, M, d, max(1, a.reps // 2), N)
             run(f"{c} adaptive mat", A, M, d, a.reps, N)
+            capi.config_set(dense=1)
         for x in d:
             x.free()
 
