@@ -125,7 +125,12 @@ struct Engine {
     cfg["chunk_rows"] = 1 << 24;
     cfg["dense"] = 1;               // optimistic dense-key-domain fast paths (exact bitmap count, direct-address radix join)
     cfg["dense_min_rows"] = 1 << 20;  // radix: smallest build side that takes the direct-address join
-    cfg["dense_group_mb"] = 16;     // radix: direct-address regions kept L2 resident per pipeline stage (3 stages)
+    cfg["dense_group_mb"] = 8;      // radix: direct-address regions kept L2 resident per pipeline stage (delay_b + delay_p + 1 stages live)
+    cfg["dense_ring"] = 4;          // k_djoin: items a CTA's dispatcher may publish ahead of its slowest worker warp
+    cfg["dense_batch"] = 2;         // k_djoin: tickets per dispatcher round trip
+    cfg["dense_delay_b"] = 1;       // k_djoin: steps between zeroing a group of regions and filling it
+    cfg["dense_delay_p"] = 3;       // k_djoin: steps between filling a group and probing it (sweep: profiles/r01f_sweep_djoin.jsonl)
+    cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
     // FJ_CFG_<KEY>=<integer> in the environment overrides a default (e.g. FJ_CFG_DENSE=0)
     for (auto& kv : cfg) {
       std::string name = "FJ_CFG_";
@@ -213,7 +218,8 @@ fj_status Engine::init(int device) {
   FJ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto& x : ev) FJ_CUDA(cudaEventCreate(&x));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl)));
-  FJ_TRY(ctl.ensure(sizeof(Ctl)));
+  FJ_TRY(ctl.ensure(4096));  // [0, 256): Ctl; [256, 272): grid-barrier words of the fused kernels (zero between launches)
+  FJ_CUDA(cudaMemset(ctl.p, 0, 4096));
   inited = true;
   return FJ_OK;
 }
@@ -411,19 +417,29 @@ fj_status Engine::attempt_scalar_dense(uint64_t dbits, const unsigned long long*
   Ctl* d_ctl = ctl.as<Ctl>();
   int launches = 0;
   FJ_CUDA(cudaEventRecord(ev[0], st));
-  launch_prepare(d_ctl, nullptr, 0, bloom.p, bytes, di, st);
-  ++launches;
-  FJ_CUDA(cudaEventRecord(ev[1], st));
-  launch_build_bitmap(bloom.as<uint32_t>(), dbits, bk, nb, d_ctl, di, st, &launches);
-  FJ_CUDA(cudaEventRecord(ev[2], st));
-  launch_probe_count_dense(pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, di, st, &launches);
+  // one persistent launch (prepare | build | probe separated by grid barriers), else the three-kernel sequence
+  uint32_t* gsync = reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 256);  // zeroed at init, kept zero by the kernel
+  const bool fused = cfg["dense_fused"] != 0 &&
+                     launch_count_dense_fused(bk, nb, pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, gsync, di, st, &launches);
+  if (!fused) {
+    launch_prepare(d_ctl, nullptr, 0, bloom.p, bytes, di, st);
+    ++launches;
+    FJ_CUDA(cudaEventRecord(ev[1], st));
+    launch_build_bitmap(bloom.as<uint32_t>(), dbits, bk, nb, d_ctl, di, st, &launches);
+    FJ_CUDA(cudaEventRecord(ev[2], st));
+    launch_probe_count_dense(pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, di, st, &launches);
+  }
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
-  s->clear_s += ms(0, 1) * 1e-3;
-  s->build_s += ms(1, 2) * 1e-3;
-  s->probe_s += ms(2, 3) * 1e-3;
+  if (fused) {
+    s->probe_s += ms(0, 3) * 1e-3;  // one kernel: clear, build and probe are phases of it
+  } else {
+    s->clear_s += ms(0, 1) * 1e-3;
+    s->build_s += ms(1, 2) * 1e-3;
+    s->probe_s += ms(2, 3) * 1e-3;
+  }
   s->device_s += ms(0, 3) * 1e-3;
   s->kernel_launches += launches;
   s->table_bytes = bytes;
@@ -590,6 +606,10 @@ fj_status Engine::attempt_dense(unsigned flags, const DensePlan& dp, const unsig
   j.probe = part_a_p.p; j.pcnt = cur_p; j.cap_p = dp.cap_p;
   j.direct = direct.as<uint32_t>(); j.rstride = dp.rstride;
   j.group_bytes = (uint64_t)std::max<int64_t>(1, cfg["dense_group_mb"]) << 20;
+  j.ring = (uint32_t)std::max<int64_t>(1, cfg["dense_ring"]);
+  j.batch = (uint32_t)std::max<int64_t>(1, cfg["dense_batch"]);
+  j.delay_b = (uint32_t)std::max<int64_t>(1, cfg["dense_delay_b"]);
+  j.delay_p = (uint32_t)std::max<int64_t>(1, cfg["dense_delay_p"]);
   j.ctl = d_ctl; j.sync = cur_p + F;
   j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
   j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;

@@ -54,6 +54,12 @@ void launch_build_bitmap(uint32_t* bitmap, uint64_t dbits, const unsigned long l
                          const DeviceInfo& di, cudaStream_t st, int* launches);
 void launch_probe_count_dense(const unsigned long long* pk, uint64_t np, const uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
                               const DeviceInfo& di, cudaStream_t st, int* launches);
+// the three steps above (control block + empty bitmap, build, probe) as ONE persistent launch with two grid
+// barriers; gsync = 3 words that are zero between launches (the kernel leaves them zero).  Initialises *ctl
+// itself.  false: the launch configuration cannot guarantee co-residency -> use the three-kernel sequence
+bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                              uint32_t* bitmap, uint32_t dwords, Ctl* ctl, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st,
+                              int* launches);
 
 // ---------------------------------------------------------------- radix-partitioned path
 // key / value domain of the packed (narrow) stage-1 scatter.  General packed rows: keys < 2^32 - 1, values < 2^32,
@@ -131,7 +137,9 @@ struct DjoinArgs {
   uint64_t cap_p = 0;
   uint32_t* direct = nullptr;
   uint64_t rstride = 0;
-  uint64_t group_bytes = 0;  // bytes of regions per pipeline stage (three stages are live at once)
+  uint64_t group_bytes = 0;  // bytes of regions per pipeline stage (delay_b + delay_p + 1 stages are live at once)
+  uint32_t ring = 4, batch = 2;        // per-CTA item look-ahead: published-item ring slots, tickets per dispatcher round trip
+  uint32_t delay_b = 1, delay_p = 1;   // pipeline distance in steps: zero -> fill, fill -> probe
   Ctl* ctl = nullptr;
   uint32_t* sync = nullptr;
   unsigned long long* out_keys = nullptr;

@@ -1154,7 +1154,9 @@ void launch_join3(bool mat, const JoinArgs& a, int rbits, const DeviceInfo& di, 
 // scatter pass of both sides and the shared-memory partition join (k_scatter2 x2 + k_join3) by one
 // random 4-byte L2 store per build row and one random 4-byte L2 load per probe row.
 //
-// Persistent CTAs (all co-resident) pull work items in a fixed global order from an atomic ticket:
+// Persistent CTAs (all co-resident) pull work items in a fixed global order from an atomic ticket (one
+// dispatcher warp per CTA resolves tickets and publishes items to a ring; 15 worker warps consume them
+// independently, without block barriers):
 //   step s:  Z(group s) zero regions | B(group s-1) store build rows | P(group s-2) probe | C(group s-2) count
 // B(p, .) waits until all Z(p, .) are done, P/C(p, .) until all B(p, .) are done (per-partition completion
 // counters; a waiter only ever waits for items with smaller tickets, which are running or finished, so the
@@ -1166,9 +1168,13 @@ constexpr int DJ_THREADS = 512;
 constexpr int DJ_WARPS = DJ_THREADS / 32;
 constexpr int DJ_F = 256;                 // partitions = low 8 key bits
 constexpr int DJ_IPT = 8;
-constexpr int DJ_ROWS = DJ_THREADS * DJ_IPT;  // rows per build / probe item
+constexpr int DJ_WT = DJ_THREADS - 32;    // worker threads (warp 0 dispatches)
+constexpr int DJ_ROWS = DJ_WT * DJ_IPT;   // rows per build / probe item
+constexpr int DJ_RING_MAX = 16;           // published-item ring: `ring` slots in use (power of two, runtime knob)
+constexpr int DJ_BATCH_MAX = 8;           // tickets per dispatcher round trip (runtime knob)
+constexpr int DJ_DELAY_MAX = 6;           // largest Z->B plus B->P distance in steps
 constexpr int DJ_ZSLOTS = 16384;          // direct-address slots per zero / count item (64 KB)
-constexpr int DJ_MAXSEG = 4 * (DJ_F + 2);
+constexpr int DJ_MAXSEG = 4 * (DJ_F + DJ_DELAY_MAX);
 enum { DJ_Z = 0, DJ_B = 1, DJ_P = 2, DJ_C = 3, DJ_DONE = 4 };
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -1200,12 +1206,20 @@ __global__ void __launch_bounds__(DJ_THREADS, 2)
             const uint32_t* __restrict__ probe, const uint32_t* __restrict__ pcnt, uint64_t cap_p,
             uint32_t* __restrict__ direct, uint64_t rstride /*slots per region, multiple of 4*/, uint64_t group_bytes,
             Ctl* __restrict__ ctl, uint32_t* __restrict__ sync /*[0] ticket, [4..] zdone[256], bdone[256]*/,
-            unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_vals) {
+            unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_vals,
+            uint32_t tune /*ring | batch << 8 | Z->B steps << 16 | B->P steps << 24*/) {
   __shared__ uint32_t s_seg[DJ_MAXSEG + 1];
   __shared__ uint32_t s_preb[DJ_F + 1], s_prep[DJ_F + 1];
   __shared__ uint32_t s_warp[DJ_WARPS];
-  __shared__ uint32_t s_item[3];
+  __shared__ volatile uint32_t s_kind[DJ_RING_MAX], s_part[DJ_RING_MAX], s_chunk[DJ_RING_MAX];
+  __shared__ volatile uint32_t s_seq[DJ_RING_MAX];  // n + 1 once the CTA's n-th item is published in slot n % ring
+  __shared__ uint32_t s_done[DJ_RING_MAX];          // worker-warp completions per slot (monotonic)
   const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t ring = tune & 0xffu, batch = (tune >> 8) & 0xffu, dly_b = (tune >> 16) & 0xffu, dly_p = dly_b + (tune >> 24);
+  if (tid < DJ_RING_MAX) {
+    s_seq[tid] = 0;
+    s_done[tid] = 0;
+  }
   uint32_t* ticket = sync;
   uint32_t* zdone = sync + 4;
   uint32_t* bdone = sync + 4 + DJ_F;
@@ -1240,11 +1254,11 @@ __global__ void __launch_bounds__(DJ_THREADS, 2)
   }
   __syncthreads();
   // ---- the item order: 4 segments per step (Z, B, P, C); thread t sizes segments 3t .. 3t+2
-  const uint32_t nseg = 4 * (ng + 2);
+  const uint32_t nseg = 4 * (ng + dly_p);
   auto seg_count = [&](uint32_t seg) -> uint32_t {
     if (seg >= nseg) return 0u;
     const uint32_t kind = seg & 3u, step = seg >> 2;
-    const uint32_t delay = kind == DJ_Z ? 0u : (kind == DJ_B ? 1u : 2u);
+    const uint32_t delay = kind == DJ_Z ? 0u : (kind == DJ_B ? dly_b : dly_p);
     if (step < delay || step - delay >= ng) return 0u;
     const uint32_t lo = (step - delay) * gp, hi = lo + gp < DJ_F ? lo + gp : DJ_F;
     if (kind == DJ_Z) return (hi - lo) * nz;
@@ -1262,25 +1276,35 @@ __global__ void __launch_bounds__(DJ_THREADS, 2)
   }
   __syncthreads();
 
+  // ---- warp roles.  Warp 0 is the DISPATCHER: it pulls tickets in batches, resolves each ticket to an item
+  // (kind, partition, chunk), waits for the item's dependencies and publishes it into a ring of `ring` slots.
+  // Warps 1..15 are WORKERS: every warp walks the ring on its own (no block barrier per item — in the first
+  // version 48 % of all warp stall samples sat in the two __syncthreads around thread 0's serial section,
+  // profiles/r01c_c3_radix_ncu_summary.txt); the last warp to finish a Z / B item sends the completion signal.
+  const uint32_t warp = tid >> 5;
   unsigned long long local_count = 0;
   uint32_t rows_stored = 0, slots_set = 0;
-  uint32_t cur = 0;
-  if (tid == 0) cur = atomicAdd(ticket, 1u);
-  for (;;) {
-    uint32_t nxt = 0;
-    if (tid == 0) {
-      if (cur < total_items) {
-        nxt = atomicAdd(ticket, 1u);  // consumed after this item: its latency hides behind the work
-        uint32_t lo = 0, hi = nseg;   // largest seg with s_seg[seg] <= cur
+  if (warp == 0) {
+    uint32_t n = 0;  // items published by this CTA so far
+    bool finished = false;
+    while (!finished) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(ticket, batch);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      // lanes 0 .. batch-1 resolve one ticket each
+      uint32_t kind = DJ_DONE, p = 0, c = 0;
+      const uint32_t t = base + lane;
+      if ((uint32_t)lane < batch && t < total_items) {
+        uint32_t lo = 0, hi = nseg;  // largest seg with s_seg[seg] <= t
         while (hi - lo > 1) {
           const uint32_t mid = (lo + hi) >> 1;
-          if (s_seg[mid] <= cur) lo = mid; else hi = mid;
+          if (s_seg[mid] <= t) lo = mid; else hi = mid;
         }
-        const uint32_t kind = lo & 3u, step = lo >> 2;
-        const uint32_t g = step - (kind == DJ_Z ? 0u : (kind == DJ_B ? 1u : 2u));
+        kind = lo & 3u;
+        const uint32_t step = lo >> 2;
+        const uint32_t g = step - (kind == DJ_Z ? 0u : (kind == DJ_B ? dly_b : dly_p));
         const uint32_t p0 = g * gp, p1 = p0 + gp < DJ_F ? p0 + gp : DJ_F;
-        const uint32_t j = cur - s_seg[lo];
-        uint32_t p, c;
+        const uint32_t j = t - s_seg[lo];
         if (kind == DJ_Z || kind == DJ_C) {
           p = p0 + j / nz;
           c = j - (p - p0) * nz;
@@ -1295,117 +1319,153 @@ __global__ void __launch_bounds__(DJ_THREADS, 2)
           p = a;
           c = want - pre[p];
         }
-        if (kind != DJ_Z) {
-          while (ld_acquire_u32(zdone + p) < nz) __nanosleep(64);
-          if (kind != DJ_B) {
-            const uint32_t need = s_preb[p + 1] - s_preb[p];
-            while (ld_acquire_u32(bdone + p) < need) __nanosleep(64);
+      }
+      auto deps_ok = [&]() -> bool {  // every dependency has a smaller ticket: it is running or finished
+        if (kind == DJ_DONE || kind == DJ_Z) return true;
+        if (ld_acquire_u32(zdone + p) < nz) return false;
+        if (kind == DJ_B) return true;
+        return ld_acquire_u32(bdone + p) >= s_preb[p + 1] - s_preb[p];
+      };
+      bool ok = deps_ok();  // first poll of the whole batch in parallel
+#pragma unroll 1
+      for (int j = 0; j < (int)batch; ++j) {
+        while (!__shfl_sync(0xffffffffu, ok, j)) {  // warp-uniform loop: no lane waits at a reconvergence point
+          if (lane == j) {
+            __nanosleep(64);
+            ok = deps_ok();
           }
         }
-        s_item[0] = kind; s_item[1] = p; s_item[2] = c;
-      } else {
-        s_item[0] = DJ_DONE;
+        const uint32_t slot = n & (ring - 1);
+        // the slot is free once every worker warp has finished the item published `ring` items ago
+        const uint32_t freed = (uint32_t)(DJ_WARPS - 1) * (n / ring);
+        while (*reinterpret_cast<volatile uint32_t*>(&s_done[slot]) < freed) __nanosleep(32);
+        if (lane == j) {
+          s_kind[slot] = kind;
+          s_part[slot] = p;
+          s_chunk[slot] = c;
+          __threadfence_block();
+          s_seq[slot] = n + 1;
+        }
+        __syncwarp();
+        ++n;
+        if (__shfl_sync(0xffffffffu, kind, j) == DJ_DONE) {
+          finished = true;
+          break;
+        }
       }
     }
-    __syncthreads();
-    const uint32_t kind = s_item[0], p = s_item[1], c = s_item[2];
-    if (kind == DJ_DONE) break;
-    uint32_t* region = direct + (uint64_t)p * rstride;
-
-    if (kind == DJ_Z) {
-      uint4* dst = reinterpret_cast<uint4*>(region + (uint64_t)c * DJ_ZSLOTS);
-      const uint32_t n4 = ((reff - c * DJ_ZSLOTS) < (uint32_t)DJ_ZSLOTS ? (reff - c * DJ_ZSLOTS) : (uint32_t)DJ_ZSLOTS) / 4;
-      for (uint32_t i = tid; i < n4; i += DJ_THREADS) dst[i] = make_uint4(0u, 0u, 0u, 0u);
-    } else if (kind == DJ_C) {
-      const uint4* src = reinterpret_cast<const uint4*>(region + (uint64_t)c * DJ_ZSLOTS);
-      const uint32_t n4 = ((reff - c * DJ_ZSLOTS) < (uint32_t)DJ_ZSLOTS ? (reff - c * DJ_ZSLOTS) : (uint32_t)DJ_ZSLOTS) / 4;
-      for (uint32_t i = tid; i < n4; i += DJ_THREADS) {
-        const uint4 v = ld_cg_u128(src + i);
-        slots_set += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+  } else {
+    const uint32_t wt = tid - 32;  // worker thread 0 .. DJ_WT-1
+    for (uint32_t n = 0;; ++n) {
+      const uint32_t slot = n & (ring - 1);
+      while (s_seq[slot] != n + 1) {
       }
-    } else if (kind == DJ_B) {
-      uint64_t nbp = bcnt[p];
-      if (nbp > cap_b) nbp = cap_b;
-      const uint32_t cnt = (uint32_t)((nbp - (uint64_t)c * DJ_ROWS) < (uint64_t)DJ_ROWS ? (nbp - (uint64_t)c * DJ_ROWS) : DJ_ROWS);
-      const unsigned long long* rows = build + (uint64_t)p * cap_b + (uint64_t)c * DJ_ROWS;
-      uint32_t w[2][8];  // two 32-byte units per thread: rows 4u .. 4u + 3 as {value, key} word pairs
+      __syncwarp();
+      const uint32_t kind = s_kind[slot], p = s_part[slot], c = s_chunk[slot];
+      if (kind == DJ_DONE) break;
+      uint32_t* region = direct + (uint64_t)p * rstride;
+
+      if (kind == DJ_Z) {
+        uint4* dst = reinterpret_cast<uint4*>(region + (uint64_t)c * DJ_ZSLOTS);
+        const uint32_t n4 = ((reff - c * DJ_ZSLOTS) < (uint32_t)DJ_ZSLOTS ? (reff - c * DJ_ZSLOTS) : (uint32_t)DJ_ZSLOTS) / 4;
+        for (uint32_t i = wt; i < n4; i += DJ_WT) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      } else if (kind == DJ_C) {
+        const uint4* src = reinterpret_cast<const uint4*>(region + (uint64_t)c * DJ_ZSLOTS);
+        const uint32_t n4 = ((reff - c * DJ_ZSLOTS) < (uint32_t)DJ_ZSLOTS ? (reff - c * DJ_ZSLOTS) : (uint32_t)DJ_ZSLOTS) / 4;
+        for (uint32_t i = wt; i < n4; i += DJ_WT) {
+          const uint4 v = ld_cg_u128(src + i);
+          slots_set += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+        }
+      } else if (kind == DJ_B) {
+        uint64_t nbp = bcnt[p];
+        if (nbp > cap_b) nbp = cap_b;
+        const uint32_t cnt = (uint32_t)((nbp - (uint64_t)c * DJ_ROWS) < (uint64_t)DJ_ROWS ? (nbp - (uint64_t)c * DJ_ROWS) : DJ_ROWS);
+        const unsigned long long* rows = build + (uint64_t)p * cap_b + (uint64_t)c * DJ_ROWS;
+        uint32_t w[2][8];  // two 32-byte units per thread: rows 4u .. 4u + 3 as {value, key} word pairs
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t u = i * DJ_THREADS + tid;
-        if (4u * u < cnt) {
-          ld_stream256(rows + 4u * u, w[i]);
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t u = i * DJ_WT + wt;
+          if (4u * u < cnt) {
+            ld_stream256(rows + 4u * u, w[i]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) w[i][r] = 0xFFFFFFFFu;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t u = i * DJ_WT + wt;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const uint32_t k = w[i][2 * r + 1];  // packed row = key32 << 32 | value32 (little endian)
+            const bool ok = (4u * u + r < cnt) & (k != 0xFFFFFFFFu);  // 0xFFFFFFFF: padding written by k_scatter2
+            if (ok) region[k >> 8] = w[i][2 * r] + 1u;
+            rows_stored += ok ? 1u : 0u;
+          }
+        }
+      } else {  // DJ_P
+        uint64_t npp = pcnt[p];
+        if (npp > cap_p) npp = cap_p;
+        const uint32_t cnt = (uint32_t)((npp - (uint64_t)c * DJ_ROWS) < (uint64_t)DJ_ROWS ? (npp - (uint64_t)c * DJ_ROWS) : DJ_ROWS);
+        const uint32_t* rows = probe + (uint64_t)p * cap_p + (uint64_t)c * DJ_ROWS;
+        uint32_t key[DJ_IPT], val[DJ_IPT];
+        if (8u * wt < cnt) {  // one 32-byte unit per thread: rows 8 wt .. 8 wt + 7
+          ld_stream256(rows + 8u * wt, key);
         } else {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) w[i][r] = 0xFFFFFFFFu;
+          for (int i = 0; i < DJ_IPT; ++i) key[i] = 0xFFFFFFFFu;
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t u = i * DJ_THREADS + tid;
+        for (int i = 0; i < DJ_IPT; ++i) key[i] = 8u * wt + i < cnt ? key[i] : 0xFFFFFFFFu;
+        uint32_t hitmask = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const uint32_t k = w[i][2 * r + 1];  // packed row = key32 << 32 | value32 (little endian)
-          const bool ok = (4u * u + r < cnt) & (k != 0xFFFFFFFFu);  // 0xFFFFFFFF: padding written by k_scatter2
-          if (ok) region[k >> 8] = w[i][2 * r] + 1u;
-          rows_stored += ok ? 1u : 0u;
+        for (int i = 0; i < DJ_IPT; ++i) {  // all 8 L2 gathers in flight
+          const uint32_t idx = key[i] >> 8;
+          const bool ok = (key[i] != 0xFFFFFFFFu) & (idx < reff);  // hole / past the end / beyond every build key
+          val[i] = ok ? ld_cg_u32(region + idx) : 0u;
         }
-      }
-    } else {  // DJ_P
-      uint64_t npp = pcnt[p];
-      if (npp > cap_p) npp = cap_p;
-      const uint32_t cnt = (uint32_t)((npp - (uint64_t)c * DJ_ROWS) < (uint64_t)DJ_ROWS ? (npp - (uint64_t)c * DJ_ROWS) : DJ_ROWS);
-      const uint32_t* rows = probe + (uint64_t)p * cap_p + (uint64_t)c * DJ_ROWS;
-      uint32_t key[DJ_IPT], val[DJ_IPT];
-      if (8u * tid < cnt) {  // one 32-byte unit per thread: rows 8 tid .. 8 tid + 7
-        ld_stream256(rows + 8u * tid, key);
-      } else {
 #pragma unroll
-        for (int i = 0; i < DJ_IPT; ++i) key[i] = 0xFFFFFFFFu;
-      }
+        for (int i = 0; i < DJ_IPT; ++i) hitmask |= val[i] ? (1u << i) : 0u;
+        if (!MAT) {
+          local_count += __popc(hitmask);
+        } else {
+          uint32_t off[DJ_IPT];
+          uint32_t wtot = 0;
 #pragma unroll
-      for (int i = 0; i < DJ_IPT; ++i) key[i] = 8u * tid + i < cnt ? key[i] : 0xFFFFFFFFu;
-      uint32_t hitmask = 0;
+          for (int i = 0; i < DJ_IPT; ++i) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> i) & 1u);
+            off[i] = wtot + __popc(bal & lanemask_lt());
+            wtot += __popc(bal);
+          }
+          unsigned long long base = 0;
+          if (lane == 0 && wtot) {
+            base = atomicAdd(&ctl->out_cursor, (unsigned long long)wtot);
+            local_count += wtot;
+          }
+          base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-      for (int i = 0; i < DJ_IPT; ++i) {  // all 8 L2 gathers in flight
-        const uint32_t idx = key[i] >> 8;
-        const bool ok = (key[i] != 0xFFFFFFFFu) & (idx < reff);  // hole / past the end / beyond every build key
-        val[i] = ok ? ld_cg_u32(region + idx) : 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < DJ_IPT; ++i) hitmask |= val[i] ? (1u << i) : 0u;
-      if (!MAT) {
-        local_count += __popc(hitmask);
-      } else {
-        uint32_t off[DJ_IPT];
-        uint32_t wtot = 0;
-#pragma unroll
-        for (int i = 0; i < DJ_IPT; ++i) {
-          const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> i) & 1u);
-          off[i] = wtot + __popc(bal & lanemask_lt());
-          wtot += __popc(bal);
-        }
-        unsigned long long base = 0;
-        if (lane == 0 && wtot) {
-          base = atomicAdd(&ctl->out_cursor, (unsigned long long)wtot);
-          local_count += wtot;
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-        for (int i = 0; i < DJ_IPT; ++i) {
-          if ((hitmask >> i) & 1u) {
-            st_stream(out_keys + base + off[i], (unsigned long long)key[i]);
-            st_stream(out_vals + base + off[i], (unsigned long long)(val[i] - 1u));
+          for (int i = 0; i < DJ_IPT; ++i) {
+            if ((hitmask >> i) & 1u) {
+              st_stream(out_keys + base + off[i], (unsigned long long)key[i]);
+              st_stream(out_vals + base + off[i], (unsigned long long)(val[i] - 1u));
+            }
           }
         }
       }
-    }
-    __syncthreads();  // the item is complete (its stores are ordered before thread 0's fence); s_item is free
-    if (tid == 0) {
-      if (kind == DJ_Z || kind == DJ_B) {
-        __threadfence();
-        atomicAdd((kind == DJ_Z ? zdone : bdone) + p, 1u);
+      __syncwarp();  // the warp's share of the item is complete
+      if (lane == 0) {
+        // release chain: this warp's stores -> (cta-scope fence + shared-memory atomic) -> the last warp of the item
+        // -> (gpu-scope fence + global atomic) -> the waiting dispatcher's ld.acquire.  Fences are cumulative, so
+        // only the last warp pays for a gpu-scope fence (one per item instead of one per warp: 18 % of the stall
+        // samples of the first dispatcher version were MEMBAR.GPU, profiles/r01d_c3_radix_ncu_summary.txt)
+        const bool signals = kind == DJ_Z || kind == DJ_B;
+        if (signals) __threadfence_block();
+        const uint32_t old = atomicAdd(&s_done[slot], 1u);
+        if (signals && old + 1 == (uint32_t)(DJ_WARPS - 1) * (n / ring + 1)) {  // last warp of the item
+          __threadfence();
+          atomicAdd((kind == DJ_Z ? zdone : bdone) + p, 1u);
+        }
       }
-      cur = nxt;
     }
   }
 #pragma unroll
@@ -1430,14 +1490,21 @@ bool launch_djoin(bool mat, const DjoinArgs& a, const DeviceInfo& di, cudaStream
                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_djoin<false>, DJ_THREADS, 0);
   if (e != cudaSuccess || occ < 1) return false;  // cannot guarantee co-residency: the caller takes the general path
   const unsigned grid = (unsigned)(di.sms * occ);  // every CTA must be resident: the items synchronise by spinning
+  uint32_t ring = 1;
+  while (ring * 2 <= (uint32_t)DJ_RING_MAX && ring * 2 <= a.ring) ring *= 2;
+  const uint32_t batch = a.batch < 1 ? 1u : (a.batch > (uint32_t)DJ_BATCH_MAX ? (uint32_t)DJ_BATCH_MAX : a.batch);
+  uint32_t db = a.delay_b < 1 ? 1u : a.delay_b, dp = a.delay_p < 1 ? 1u : a.delay_p;
+  if (db > (uint32_t)DJ_DELAY_MAX - 1) db = DJ_DELAY_MAX - 1;
+  if (db + dp > (uint32_t)DJ_DELAY_MAX) dp = DJ_DELAY_MAX - db;
+  const uint32_t tune = ring | (batch << 8) | (db << 16) | (dp << 24);
   if (mat)
     k_djoin<true><<<grid, DJ_THREADS, 0, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
                                                reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride,
-                                               a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals);
+                                               a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals, tune);
   else
     k_djoin<false><<<grid, DJ_THREADS, 0, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
                                                 reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride,
-                                                a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals);
+                                                a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals, tune);
   ++*launches;
   return true;
 }

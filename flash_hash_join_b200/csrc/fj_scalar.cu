@@ -662,6 +662,166 @@ __global__ void __launch_bounds__(THREADS)
   if (lane == 0 && total) atomicAdd(&ctl->match_count, total);
 }
 
+// The same count as ONE launch: {k_prepare, k_build_bitmap, k_probe_count_dense} cost ~7 us each for the two
+// small kernels (launch + drain), 10 % of the whole C2 step.  Here the persistent grid (all CTAs co-resident)
+// zeroes the bitmap and the control block, meets at a grid barrier, inserts the build keys, meets again, and
+// then every CTA copies the finished bitmap into its shared memory and streams its probe tiles; the first
+// probe tile is already in flight across both barriers.  The three barrier words are self-cleaning: the last
+// CTA to leave resets them, so no host-side state or memset is needed between calls.
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(uint32_t* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_gpu_u32(counter) < gridDim.x) {
+    }
+  }
+  __syncthreads();
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    k_count_dense_fused(const unsigned long long* __restrict__ bk, uint64_t nb, const unsigned long long* __restrict__ pk,
+                        uint64_t np, uint32_t* __restrict__ bitmap, uint32_t dwords /*multiple of 4*/, Ctl* __restrict__ ctl,
+                        uint32_t* __restrict__ gsync /*[0], [1] barriers, [2] exit count; all zero between launches*/,
+                        int vec_ok) {
+  constexpr uint32_t TILE = THREADS * PROBE_KPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* sbm = reinterpret_cast<uint32_t*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t gtid = blockIdx.x * (uint64_t)THREADS + tid, gthreads = (uint64_t)gridDim.x * THREADS;
+  const unsigned long long dbits = (unsigned long long)dwords * 32ull;
+
+  // ---- phase 0: control block + empty bitmap; first probe tile in flight
+  if (gtid == 0) {
+    ctl->match_count = 0;
+    ctl->out_cursor = 0;
+    ctl->sentinel_row = EMPTY64;
+    ctl->sentinel_probes = 0;
+    ctl->flags = 0;
+    ctl->pad = 0;
+    ctl->max_key = 0;
+    ctl->dense_rows = 0;
+    ctl->dense_slots = 0;
+  }
+  for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const uint64_t ntiles = (np + TILE - 1) / TILE;
+  unsigned long long ka[PROBE_KPT], kb[PROBE_KPT];
+  uint32_t va = 0, vb = 0;
+  auto fetch = [&](uint64_t tile, unsigned long long (&k)[PROBE_KPT]) -> uint32_t {
+    const uint64_t tb = tile * TILE;
+    return load_tile<THREADS>(pk, np, tb, vec_ok && tb + TILE <= np, k);
+  };
+  uint64_t tile = blockIdx.x;
+  if (tile < ntiles) va = fetch(tile, ka);
+  grid_barrier(gsync + 0);
+
+  // ---- phase 1: build side -> bitmap bits (a key outside the optimistic domain abandons the attempt)
+  {
+    bool bad = false;
+    for (uint64_t i = gtid; i < nb; i += gthreads) {
+      const unsigned long long k = bk[i];
+      if (k >= dbits) bad = true;
+      else atomicOr(bitmap + (uint32_t)(k >> 5), 1u << ((uint32_t)k & 31u));
+    }
+    if (bad) atomicOr(&ctl->flags, CTL_NOT_DENSE);
+  }
+  grid_barrier(gsync + 1);
+
+  // ---- phase 2: every CTA takes a private copy of the bitmap and streams its probe tiles
+  uint32_t cnt = 0;
+  const bool dense = !(*reinterpret_cast<volatile unsigned int*>(&ctl->flags) & CTL_NOT_DENSE);  // same answer in every CTA
+  if (dense) {
+    for (uint32_t i = tid; i < dwords / 4; i += THREADS) {
+      uint4 v;
+      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(reinterpret_cast<const uint4*>(bitmap) + i));
+      reinterpret_cast<uint4*>(sbm)[i] = v;
+    }
+    __syncthreads();
+    auto do_tile = [&](const unsigned long long (&key)[PROBE_KPT], const uint32_t valid) {
+      uint32_t w[PROBE_KPT];
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const bool in = key[q] < dbits;
+        w[q] = sbm[in ? (uint32_t)(key[q] >> 5) : 0u];
+        w[q] = in ? w[q] : 0u;
+      }
+      uint32_t hits = 0;
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) hits |= ((w[q] >> ((uint32_t)key[q] & 31u)) & 1u) << q;
+      cnt += __popc(hits & valid);
+    };
+    while (tile < ntiles) {
+      const uint64_t t1 = tile + gridDim.x;
+      if (t1 < ntiles) vb = fetch(t1, kb);
+      do_tile(ka, va);
+      if (t1 >= ntiles) break;
+      const uint64_t t2 = t1 + gridDim.x;
+      if (t2 < ntiles) va = fetch(t2, ka);
+      do_tile(kb, vb);
+      tile = t2;
+    }
+  }
+  unsigned long long total = cnt;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+  if (lane == 0 && total) atomicAdd(&ctl->match_count, total);
+
+  // ---- leave the barrier words clean for the next launch
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(gsync + 2, 1u) == gridDim.x - 1) {
+      gsync[0] = 0;
+      gsync[1] = 0;
+      gsync[2] = 0;
+    }
+  }
+}
+
+template <int THREADS>
+static bool launch_count_dense_fused_inst(const unsigned long long* bk, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                                          uint32_t* bitmap, uint32_t dwords, Ctl* ctl, uint32_t* gsync, const DeviceInfo& di,
+                                          cudaStream_t st) {
+  auto kern = k_count_dense_fused<THREADS>;
+  const size_t smem = (size_t)dwords * 4;
+  static size_t smem_set = 0;   // per instantiation: attribute and occupancy are looked up once per size
+  static int occ_cached = 0;
+  if (smem != smem_set || occ_cached == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) return false;
+    smem_set = smem;
+    occ_cached = occ;
+  }
+  // every CTA must be resident (the phases meet at spinning grid barriers): never more than sms * occupancy
+  const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
+  uint64_t grid = (uint64_t)di.sms * occ_cached;
+  const uint64_t ntiles = (np + tile - 1) / tile;
+  if (grid > ntiles) grid = ntiles ? ntiles : 1;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(bk, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok);
+  return true;
+}
+bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                              uint32_t* bitmap, uint32_t dwords, Ctl* ctl, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st,
+                              int* launches) {
+  bool ok;
+  if ((size_t)dwords * 4 * 2 + 4096 <= di.smem_optin)
+    ok = launch_count_dense_fused_inst<512>(bk, nb, pk, np, bitmap, dwords, ctl, gsync, di, st);
+  else
+    ok = launch_count_dense_fused_inst<1024>(bk, nb, pk, np, bitmap, dwords, ctl, gsync, di, st);
+  if (ok) ++*launches;
+  return ok;
+}
+
 size_t probe_smem_bitmap_limit_bytes(const DeviceInfo& di) {
   return di.smem_optin > 8192 ? ((di.smem_optin - 8192) / 16) * 16 : 0;
 }

@@ -65,7 +65,7 @@ def test_smoke_first_kernel(fj):
     n, sec = fj.hash_join_count(bk, bv, pk)
     assert n == 4
     st = fj.last_stats()
-    assert st["kernel_launches"] >= 3 and st["path"] == "scalar"
+    assert st["kernel_launches"] >= 1 and st["path"] == "scalar"
     n, sec = fj.hash_join(build_keys=bk, build_values=bv, probe_keys=pk)
     k, v = fj.last_pairs()
     assert n == 4 and np.array_equal(O.sorted_pairs(k, v), O.sorted_pairs([5, 7, 7, 11], [50, 70, 70, 110]))
@@ -339,13 +339,17 @@ def test_idempotence_and_arena_reuse(fj):
 # ------------------------------------------------------------------------------------------------ dense key domain
 def test_dense_bitmap_count(fj):
     """Count entry points on a dense key domain: exact membership bitmap, no table."""
-    for N, ny, pct in ((500_000, 50_000, 10), (300_000, 1_000, 90), (2_000_000, 700_000, 90)):
-        bk, bv, pk = g1(N, ny, pct)
-        n0 = O.np_join(bk, bv, pk)[0]
-        for name in ("hash_join_count", "hash_join_count_bloom", "adaptive_join_count", "adaptive_join_count_bloom"):
-            n, _ = getattr(fj, name)(bk, bv, pk)
-            st = fj.last_stats()
-            assert n == n0 and st["dense"] == 1 and st["bloom_kind"] == "bitmap" and st["attempts"] == 1, (name, st)
+    # fused = 1: one persistent launch (zero | grid barrier | build | grid barrier | probe); 0: three kernels
+    for fused in (1, 0, 1):
+        fj.configure(dense_fused=fused)
+        for N, ny, pct in ((500_000, 50_000, 10), (300_000, 1_000, 90), (2_000_000, 700_000, 90), (3_000, 40, 90)):
+            bk, bv, pk = g1(N, ny, pct)
+            n0 = O.np_join(bk, bv, pk)[0]
+            for name in ("hash_join_count", "hash_join_count_bloom", "adaptive_join_count", "adaptive_join_count_bloom"):
+                n, _ = getattr(fj, name)(bk, bv, pk)
+                st = fj.last_stats()
+                assert n == n0 and st["dense"] == 1 and st["bloom_kind"] == "bitmap" and st["attempts"] == 1, (name, st)
+                assert st["kernel_launches"] == (1 if fused else 3), st
     # key 0, duplicates in the build side (a set: no keep-first pass needed), probe keys far outside the domain
     bk = np.array([0, 3, 3, 7, 200, 0], dtype=np.uint64)
     pk = np.array([0, 0, 3, 4, 7, 200, 2**40, 2**64 - 1, 255, 256], dtype=np.uint64)
@@ -368,15 +372,17 @@ def test_dense_bitmap_count(fj):
 def dense_small(fj):
     fj.configure(dense_min_rows=1024)
     yield fj
-    fj.configure(dense_min_rows=1 << 20, dense_group_mb=16, dense=1)
+    fj.configure(dense_min_rows=1 << 20, dense_group_mb=8, dense_ring=4, dense_batch=2, dense_delay_b=1, dense_delay_p=3, dense=1)
 
 
-@pytest.mark.parametrize("group_mb", [16, 1])
-def test_dense_radix_direct_join(dense_small, group_mb):
+@pytest.mark.parametrize("group_mb,ring,batch,delay_b,delay_p", [(8, 4, 2, 1, 3), (1, 4, 2, 1, 3), (1, 1, 1, 1, 1), (1, 16, 8, 2, 4),
+                                                                (16, 8, 4, 1, 1)])
+def test_dense_radix_direct_join(dense_small, group_mb, ring, batch, delay_b, delay_p):
     """Radix entry points on a dense key domain: one scatter pass by the low key bits + direct-address join
-    (k_djoin); group_mb = 1 forces many L2 groups (the whole Z/B/P/C item pipeline with its waits)."""
+    (k_djoin); group_mb = 1 forces many L2 groups (the whole Z/B/P/C item pipeline with its waits); the other
+    knobs are the dispatcher look-ahead and the pipeline distances (results must not depend on any of them)."""
     fj = dense_small
-    fj.configure(dense_group_mb=group_mb)
+    fj.configure(dense_group_mb=group_mb, dense_ring=ring, dense_batch=batch, dense_delay_b=delay_b, dense_delay_p=delay_p)
     for N, ny, pct in ((400_000, 300_000, 90), (3_000_000, 2_000_000, 90), (1_000_000, 70_000, 10)):
         bk, bv, pk = g1(N, ny, pct)
         expect = O.np_join(bk, bv, pk)

@@ -20,7 +20,14 @@ if has sanity; then
   echo "sanity exit $rc" >> "$OUT/sanity.log"
   if [ $rc -ne 0 ]; then export FJ_CFG_DENSE_MIN_ROWS=4000000000; echo "dense radix path DISABLED for this round" >> "$OUT/sanity.log"; fi
   timeout 180 compute-sanitizer --tool memcheck python tools/prof_case.py S radix mat --reps 1 --set dense_min_rows=1024 > "$OUT/memcheck_dense.log" 2>&1
-  tail -3 "$OUT/sanity.log" "$OUT/memcheck_dense.log"
+  # the fused bitmap count meets at spinning grid barriers: same precaution (small and large bitmap variant)
+  { timeout 120 python tools/prof_case.py C1 scalar count --check --reps 3 && timeout 120 python tools/prof_case.py S scalar count bloom --check --reps 3; } > "$OUT/sanity_fused.log" 2>&1
+  rc=$?
+  echo "sanity_fused exit $rc" >> "$OUT/sanity_fused.log"
+  if [ $rc -ne 0 ]; then export FJ_CFG_DENSE_FUSED=0; echo "fused bitmap count DISABLED for this round" >> "$OUT/sanity_fused.log"; fi
+  timeout 180 compute-sanitizer --tool memcheck python tools/prof_case.py S scalar count --reps 1 > "$OUT/memcheck_fused.log" 2>&1
+  tail -n 4 "$OUT/sanity_fused.log" "$OUT/memcheck_fused.log"
+  tail -n 3 "$OUT/sanity.log" "$OUT/memcheck_dense.log"
 fi
 if has tests; then
   timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > "$OUT/pytest_gpu.log" 2>&1

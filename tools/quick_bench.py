@@ -61,9 +61,7 @@ def main():
             run(f"{c} adaptive count", A, 0, d, a.reps, N)
             capi.config_set(dense=1)
         else:
-            for mb in (16, 8, 32, 4, 24):
-                run(f"{c} radix mat (dense, direct-address)", R, M, d, a.reps, N, {"dense_group_mb": mb})
-            capi.config_set(dense_group_mb=16)
+            run(f"{c} radix mat (dense, direct-address)", R, M, d, a.reps, N)
             run(f"{c} radix count (dense, direct-address)", R, 0, d, a.reps, N)
             run(f"{c} adaptive mat (dense)", A, M, d, a.reps, N)
             capi.config_set(dense=0)
