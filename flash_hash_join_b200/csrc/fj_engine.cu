@@ -156,8 +156,8 @@ struct Engine {
   DevBuf direct;
   // dense key domain, count only: exact membership bitmap in shared memory instead of table + filter
   uint64_t dense_bitmap_bits(uint64_t nb) const;
-  fj_status attempt_scalar_dense(uint64_t dbits, const unsigned long long* bk, uint64_t nb, const unsigned long long* pk,
-                                 uint64_t np, fj_stats* s);
+  fj_status attempt_scalar_dense(unsigned flags, uint64_t dbits, const unsigned long long* bk, const unsigned long long* bv,
+                                 uint64_t nb, const unsigned long long* pk, uint64_t np, uint64_t idx_base, fj_stats* s);
   // flat != nullptr: both sides are already in partition-element format (rows received from the multi-GPU
   // shuffle, holes included): flat->b / flat->p replace bk,bv / pk and every pass is a stage-2 pass
   struct FlatInput { const void* b; uint64_t nb; const void* p; uint64_t np; };
@@ -410,24 +410,42 @@ uint64_t Engine::dense_bitmap_bits(uint64_t nb) const {
   return d >= nb + 1 ? d : 0;
 }
 
-fj_status Engine::attempt_scalar_dense(uint64_t dbits, const unsigned long long* bk, uint64_t nb,
-                                       const unsigned long long* pk, uint64_t np, fj_stats* s) {
+fj_status Engine::attempt_scalar_dense(unsigned flags, uint64_t dbits, const unsigned long long* bk,
+                                       const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                                       uint64_t idx_base, fj_stats* s) {
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
   const size_t bytes = dbits / 8;
   FJ_TRY(bloom.ensure(bytes));
+  if (mat) FJ_TRY(table.ensure((size_t)dbits * 8));  // direct-address values: 8 bytes per key of the domain
   Ctl* d_ctl = ctl.as<Ctl>();
   int launches = 0;
   FJ_CUDA(cudaEventRecord(ev[0], st));
   // one persistent launch (prepare | build | probe separated by grid barriers), else the three-kernel sequence
   uint32_t* gsync = reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 256);  // zeroed at init, kept zero by the kernel
-  const bool fused = cfg["dense_fused"] != 0 &&
-                     launch_count_dense_fused(bk, nb, pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, gsync, di, st, &launches);
-  if (!fused) {
-    launch_prepare(d_ctl, nullptr, 0, bloom.p, bytes, di, st);
-    ++launches;
-    FJ_CUDA(cudaEventRecord(ev[1], st));
-    launch_build_bitmap(bloom.as<uint32_t>(), dbits, bk, nb, d_ctl, di, st, &launches);
-    FJ_CUDA(cudaEventRecord(ev[2], st));
-    launch_probe_count_dense(pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, di, st, &launches);
+  bool fused = false;
+  if (mat) {
+    ProbeOut po;
+    po.keys = out_keys.as<unsigned long long>();
+    po.vals = out_vals.as<unsigned long long>();
+    po.idx = (flags & FJ_FLAG_PROBE_IDX) ? out_idx.as<unsigned long long>() : nullptr;
+    po.idx_base = idx_base;
+    fused = launch_mat_dense_fused(bk, bv, nb, pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), table.as<unsigned long long>(),
+                                   d_ctl, gsync, po, di, st, &launches);
+    if (!fused) {  // no co-resident launch configuration: this attempt did not run, the hash path answers
+      h_ctl->flags = CTL_NOT_DENSE;
+      return FJ_OK;
+    }
+  } else {
+    fused = cfg["dense_fused"] != 0 &&
+            launch_count_dense_fused(bk, nb, pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, gsync, di, st, &launches);
+    if (!fused) {
+      launch_prepare(d_ctl, nullptr, 0, bloom.p, bytes, di, st);
+      ++launches;
+      FJ_CUDA(cudaEventRecord(ev[1], st));
+      launch_build_bitmap(bloom.as<uint32_t>(), dbits, bk, nb, d_ctl, di, st, &launches);
+      FJ_CUDA(cudaEventRecord(ev[2], st));
+      launch_probe_count_dense(pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, di, st, &launches);
+    }
   }
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
@@ -442,7 +460,7 @@ fj_status Engine::attempt_scalar_dense(uint64_t dbits, const unsigned long long*
   }
   s->device_s += ms(0, 3) * 1e-3;
   s->kernel_launches += launches;
-  s->table_bytes = bytes;
+  s->table_bytes = bytes + (mat ? (uint64_t)dbits * 8 : 0);
   s->path = FJ_ALGO_SCALAR;
   s->narrow = 1;
   s->bloom_kind = 3;
@@ -669,7 +687,14 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
   int path = choose_path(algo, flags, nb, narrow, plan);
   if ((flags & FJ_FLAG_PROBE_IDX) && mat) path = FJ_ALGO_SCALAR;  // radix drops row ids (:254-292)
   // optimistic dense-key-domain fast paths (both leave through CTL_NOT_DENSE when the data says otherwise)
-  uint64_t dense_bits = (narrow && !mat && path == FJ_ALGO_SCALAR) ? dense_bitmap_bits(nb) : 0;
+  uint64_t dense_bits = (narrow && path == FJ_ALGO_SCALAR && (!mat || cfg["dense_fused"] != 0)) ? dense_bitmap_bits(nb) : 0;
+  // materialize: only while two CTAs (two bitmaps) fit one SM — with a single 1024-thread CTA per SM the
+  // direct-address kernel was slower than the hash-table kernel at 90 % match rate (1.30 vs 1.03 ms at 1.25e8 x 1e6,
+  // profiles/r01h_quick_bench.jsonl), so larger domains keep the general path
+  if (mat && dense_bits / 8 * 2 + 8192 > (uint64_t)di.smem_optin) {
+    const uint64_t lim2 = (((uint64_t)di.smem_optin - 8192) / 2 * 8) & ~uint64_t(127);
+    dense_bits = lim2 >= nb + 1 ? lim2 : 0;
+  }
   DensePlan dplan;
   if (narrow && path == FJ_ALGO_RADIX) {
     dplan = plan_dense(flags, nb, np);
@@ -683,9 +708,9 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
       if (!plan.ok) { path = FJ_ALGO_SCALAR; }
     }
     const bool dense_radix = path == FJ_ALGO_RADIX && narrow && dplan.ok;
-    const bool dense_scalar = path == FJ_ALGO_SCALAR && narrow && !exact && !mat && dense_bits != 0;
+    const bool dense_scalar = path == FJ_ALGO_SCALAR && narrow && !exact && dense_bits != 0;
     if (dense_radix) FJ_TRY(attempt_dense(flags, dplan, bk, bv, nb, pk, np, s));
-    else if (dense_scalar) FJ_TRY(attempt_scalar_dense(dense_bits, bk, nb, pk, np, s));
+    else if (dense_scalar) FJ_TRY(attempt_scalar_dense(flags, dense_bits, bk, bv, nb, pk, np, idx_base, s));
     else if (path == FJ_ALGO_RADIX) FJ_TRY(attempt_radix(flags, plan, bk, bv, nb, pk, np, s));
     else FJ_TRY(attempt_scalar(flags, narrow, exact, bk, bv, nb, pk, np, idx_base, s));
     const unsigned f = h_ctl->flags;

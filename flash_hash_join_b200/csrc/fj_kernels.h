@@ -61,6 +61,12 @@ bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const u
                               uint32_t* bitmap, uint32_t dwords, Ctl* ctl, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st,
                               int* launches);
 
+// dense key domain, materialize: bitmap + direct-address value table direct[key] (8 bytes per key of the domain,
+// L2 resident), one persistent launch; a duplicate build key raises CTL_DUP, a key >= dbits CTL_NOT_DENSE
+bool launch_mat_dense_fused(const unsigned long long* bk, const unsigned long long* bv, uint64_t nb, const unsigned long long* pk,
+                            uint64_t np, uint32_t* bitmap, uint32_t dwords, unsigned long long* direct, Ctl* ctl, uint32_t* gsync,
+                            const ProbeOut& po, const DeviceInfo& di, cudaStream_t st, int* launches);
+
 // ---------------------------------------------------------------- radix-partitioned path
 // key / value domain of the packed (narrow) stage-1 scatter.  General packed rows: keys < 2^32 - 1, values < 2^32,
 // digit from hash32, a row outside raises CTL_NEED_WIDE.  Dense key domain: keys < the optimistic bound `klimit`,

@@ -822,6 +822,224 @@ bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const u
   return ok;
 }
 
+// Materialize on a dense key domain (global-table path, hash_join.cpp:383-496): the same persistent launch,
+// with a direct-address value table next to the bitmap: direct[key] = build value (8 bytes, L2 resident:
+// 2 MB at C2, 14 MB at 1e6 build rows).  The exact bitmap in shared memory answers "does this probe row
+// match" without touching memory; only matching rows gather their value from L2, and pairs are compacted per
+// tile like k_probe_mat (one cursor bump per tile).  A duplicate build key shows up as an already-set bit
+// (atomicOr returns it) -> CTL_DUP: keep-first needs row order, the host re-runs on the exact path.
+template <bool IDX, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
+    k_mat_dense_fused(const unsigned long long* __restrict__ bk, const unsigned long long* __restrict__ bv, uint64_t nb,
+                      const unsigned long long* __restrict__ pk, uint64_t np, uint32_t* __restrict__ bitmap,
+                      uint32_t dwords /*multiple of 4*/, unsigned long long* __restrict__ direct, Ctl* __restrict__ ctl,
+                      uint32_t* __restrict__ gsync, unsigned long long* __restrict__ out_keys,
+                      unsigned long long* __restrict__ out_vals, unsigned long long* __restrict__ out_idx,
+                      unsigned long long idx_base, int vec_ok) {
+  // the CTA shares one bitmap but probes as NG independent groups of 256 threads (own tiles, own compaction scratch,
+  // own named barrier): a 1024-thread CTA whose 32 warps met at three block barriers per tile ran 30 % slower
+  // than the hash-table kernel at 90 % match rate (C4 shape, profiles/r01g_quick_bench.jsonl)
+  constexpr int GT = 256, NG = THREADS / GT, WARPS = GT / 32;
+  constexpr uint32_t TILE = GT * PROBE_KPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t s_wcnt_all[NG][WARPS * PROBE_KPT];
+  __shared__ unsigned long long s_base_all[NG];
+  uint32_t* sbm = reinterpret_cast<uint32_t*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, grp = tid / GT, gtid_l = tid % GT, warp = gtid_l >> 5;
+  uint32_t* s_wcnt = s_wcnt_all[grp];
+  unsigned long long& s_base = s_base_all[grp];
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(GT) : "memory"); };
+  const uint64_t gtid = blockIdx.x * (uint64_t)THREADS + tid, gthreads = (uint64_t)gridDim.x * THREADS;
+  const unsigned long long dbits = (unsigned long long)dwords * 32ull;
+
+  // ---- phase 0
+  if (gtid == 0) {
+    ctl->match_count = 0;
+    ctl->out_cursor = 0;
+    ctl->sentinel_row = EMPTY64;
+    ctl->sentinel_probes = 0;
+    ctl->flags = 0;
+    ctl->pad = 0;
+    ctl->max_key = 0;
+    ctl->dense_rows = 0;
+    ctl->dense_slots = 0;
+  }
+  for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0u, 0u, 0u, 0u);
+  grid_barrier(gsync + 0);
+
+  // ---- phase 1: bitmap bits + direct-address values
+  {
+    unsigned bad = 0;
+    for (uint64_t i = gtid; i < nb; i += gthreads) {
+      const unsigned long long k = bk[i];
+      if (k >= dbits) {
+        bad |= CTL_NOT_DENSE;
+      } else {
+        const uint32_t bit = 1u << ((uint32_t)k & 31u);
+        const uint32_t old = atomicOr(bitmap + (uint32_t)(k >> 5), bit);
+        if (old & bit) bad |= CTL_DUP;
+        else direct[k] = bv[i];
+      }
+    }
+    if (bad) atomicOr(&ctl->flags, bad);
+  }
+  grid_barrier(gsync + 1);
+
+  // ---- phase 2
+  unsigned long long local_count = 0;
+  const bool go = !(*reinterpret_cast<volatile unsigned int*>(&ctl->flags) & (CTL_NOT_DENSE | CTL_DUP));  // grid-uniform
+  if (go) {
+    for (uint32_t i = tid; i < dwords / 4; i += THREADS) {
+      uint4 v;
+      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(reinterpret_cast<const uint4*>(bitmap) + i));
+      reinterpret_cast<uint4*>(sbm)[i] = v;
+    }
+    __syncthreads();
+    const uint64_t ntiles = (np + TILE - 1) / TILE;
+    for (uint64_t tile = (uint64_t)blockIdx.x * NG + grp; tile < ntiles; tile += (uint64_t)gridDim.x * NG) {
+      const uint64_t tbase = tile * TILE;
+      unsigned long long key[PROBE_KPT], val[PROBE_KPT];
+      const bool vec = vec_ok && tbase + TILE <= np;
+      uint32_t vmask = 0;
+      if (vec) {
+#pragma unroll
+        for (int r = 0; r < PROBE_KPT / 2; ++r) ld_stream2(pk + tbase + 2ull * ((uint64_t)r * GT + gtid_l), key[2 * r], key[2 * r + 1]);
+        vmask = 0xffu;
+      } else {
+#pragma unroll
+        for (int q = 0; q < PROBE_KPT; ++q) {
+          const uint64_t e = tbase + (uint64_t)q * GT + gtid_l;
+          const bool ok = e < np;
+          key[q] = ok ? ld_stream1(pk + e) : 0ull;
+          vmask |= ok ? (1u << q) : 0u;
+        }
+      }
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const bool in = key[q] < dbits;
+        const uint32_t w = sbm[in ? (uint32_t)(key[q] >> 5) : 0u];
+        const bool hit = in & ((vmask >> q) & 1u) & ((w >> ((uint32_t)key[q] & 31u)) & 1u);
+        hitmask |= hit ? (1u << q) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {  // all gathers of the thread in flight (L2-resident table)
+        val[q] = 0ull;
+        if ((hitmask >> q) & 1u)
+          asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(val[q]) : "l"(direct + key[q]));
+      }
+      uint32_t rank[PROBE_KPT];
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> q) & 1u);
+        rank[q] = __popc(bal & lanemask_lt());
+        if (lane == 0) s_wcnt[warp * PROBE_KPT + q] = __popc(bal);
+      }
+      group_sync();
+      if (warp == 0) {
+        constexpr int PER = (WARPS * PROBE_KPT + 31) / 32;
+        uint32_t c[PER];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int e = lane * PER + u;
+          c[u] = e < WARPS * PROBE_KPT ? s_wcnt[e] : 0u;
+          sum += c[u];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int e = lane * PER + u;
+          if (e < WARPS * PROBE_KPT) s_wcnt[e] = run;
+          run += c[u];
+        }
+        if (lane == 31) {
+          s_base = incl ? atomicAdd(&ctl->out_cursor, (unsigned long long)incl) : 0ull;
+          local_count += incl;  // counted once per tile by this lane
+        }
+      }
+      group_sync();
+      const unsigned long long base = s_base;
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        if ((hitmask >> q) & 1u) {
+          const unsigned long long pos = base + s_wcnt[warp * PROBE_KPT + q] + rank[q];
+          st_stream(out_keys + pos, key[q]);
+          st_stream(out_vals + pos, val[q]);
+          if (IDX) {
+            const uint64_t row = vec ? tbase + 2ull * ((uint64_t)(q >> 1) * GT + gtid_l) + (q & 1)
+                                     : tbase + (uint64_t)q * GT + gtid_l;
+            st_stream(out_idx + pos, idx_base + row);
+          }
+        }
+      }
+      group_sync();  // s_wcnt / s_base are reused by the group's next tile
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
+  if (lane == 0 && local_count) atomicAdd(&ctl->match_count, local_count);
+
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(gsync + 2, 1u) == gridDim.x - 1) {
+      gsync[0] = 0;
+      gsync[1] = 0;
+      gsync[2] = 0;
+    }
+  }
+}
+
+template <bool IDX, int THREADS>
+static bool launch_mat_dense_fused_inst(const unsigned long long* bk, const unsigned long long* bv, uint64_t nb,
+                                        const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords,
+                                        unsigned long long* direct, Ctl* ctl, uint32_t* gsync, const ProbeOut& po,
+                                        const DeviceInfo& di, cudaStream_t st) {
+  auto kern = k_mat_dense_fused<IDX, THREADS>;
+  const size_t smem = (size_t)dwords * 4;
+  static size_t smem_set = 0;
+  static int occ_cached = 0;
+  if (smem != smem_set || occ_cached == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) return false;
+    smem_set = smem;
+    occ_cached = occ;
+  }
+  const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;  // rows per CTA and round (NG group tiles of 256 * PROBE_KPT rows)
+  uint64_t grid = (uint64_t)di.sms * occ_cached;  // all CTAs resident: the phases meet at spinning grid barriers
+  const uint64_t ntiles = (np + tile - 1) / tile;
+  if (grid > ntiles) grid = ntiles ? ntiles : 1;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po.keys, po.vals, po.idx,
+                                              po.idx_base, vec_ok);
+  return true;
+}
+bool launch_mat_dense_fused(const unsigned long long* bk, const unsigned long long* bv, uint64_t nb, const unsigned long long* pk,
+                            uint64_t np, uint32_t* bitmap, uint32_t dwords, unsigned long long* direct, Ctl* ctl, uint32_t* gsync,
+                            const ProbeOut& po, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  const bool two = (size_t)dwords * 4 * 2 + 8192 <= di.smem_optin;
+  bool ok;
+  if (po.idx) {
+    ok = two ? launch_mat_dense_fused_inst<true, 512>(bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po, di, st)
+             : launch_mat_dense_fused_inst<true, 1024>(bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po, di, st);
+  } else {
+    ok = two ? launch_mat_dense_fused_inst<false, 512>(bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po, di, st)
+             : launch_mat_dense_fused_inst<false, 1024>(bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po, di, st);
+  }
+  if (ok) ++*launches;
+  return ok;
+}
+
 size_t probe_smem_bitmap_limit_bytes(const DeviceInfo& di) {
   return di.smem_optin > 8192 ? ((di.smem_optin - 8192) / 16) * 16 : 0;
 }

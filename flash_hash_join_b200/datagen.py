@@ -24,6 +24,7 @@ CONFIGS = {
     "C3": (100_000_000, 100_000_000, 90),
     "C4": (1_000_000_000, 1_000_000, 90),
     "C5": (1_000_000_000, 1_000_000_000, 90),
+    "C4s": (125_000_000, 1_000_000, 90),  # shape of one GPU's share of C4 on 8 GPUs (probe split, build replicated)
     "S": (2_000_000, 1_500_000, 90),  # small radix-shaped case for sanitizer / sanity runs (not a BASELINE config)
 }
 

@@ -156,8 +156,19 @@ def test_wide_keys_and_values(fj):
     for algo in ("scalar", "radix"):
         n, _ = run_entry(fj, algo, False, True, bk, bv, pk)
         st = fj.last_stats()
+        if st["dense"]:  # global-table path on a dense key domain: the direct-address table holds 64-bit values
+            assert algo == "scalar" and n == n0[0] and st["attempts"] == 1
+        else:
+            assert n == n0[0] and st["attempts"] == 2 and st["narrow"] is False
+        assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(n0[1], n0[2]))
+    fj.configure(dense=0)
+    try:
+        n, _ = run_entry(fj, "scalar", False, True, bk, bv, pk)
+        st = fj.last_stats()
         assert n == n0[0] and st["attempts"] == 2 and st["narrow"] is False
         assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(n0[1], n0[2]))
+    finally:
+        fj.configure(dense=1)
 
 
 def test_force_wide_flag(fj):
@@ -366,6 +377,60 @@ def test_dense_bitmap_count(fj):
     bv = bv.copy(); bv[5] = 2**50
     n, _ = fj.hash_join_count(bk, bv, pk)
     assert n == O.np_join(bk, bv, pk)[0] and fj.last_stats()["dense"] == 1
+
+
+def test_dense_direct_materialize(fj):
+    """Materialize entry points of the global-table path on a dense key domain: exact bitmap in shared memory +
+    L2-resident direct-address value table, one persistent launch (k_mat_dense_fused)."""
+    for N, ny, pct in ((500_000, 50_000, 10), (300_000, 1_000, 90), (2_000_000, 700_000, 90), (3_000, 40, 90), (5, 3, 100)):
+        # 700 000 build rows: the bitmap is clipped to what two CTAs per SM can hold (896 k keys >= 1.1 * 700 000)
+        bk, bv, pk = g1(N, ny, pct)
+        bv = bv.copy(); bv[ny // 2] = 2**63 + 12345  # 64-bit values are fine: the table holds 8-byte values
+        n0, k0, v0 = O.np_join(bk, bv, pk)
+        sp0 = O.sorted_pairs(k0, v0)
+        for name in ("hash_join", "hash_join_bloom", "adaptive_join", "adaptive_join_bloom"):
+            n, _ = getattr(fj, name)(bk, bv, pk)
+            st = fj.last_stats()
+            assert n == n0 and st["dense"] == 1 and st["bloom_kind"] == "bitmap" and st["attempts"] == 1 and st["kernel_launches"] == 1, (name, st)
+            assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), sp0), name
+    # probe row indices ride along
+    bk, bv, pk = g1(400_000, 30_000, 50)
+    n0, k0, v0 = O.np_join(bk, bv, pk)
+    n, _ = fj.join_flags("scalar", False, True, bk, bv, pk, probe_idx=True)
+    k, v, idx = fj.last_pairs(with_probe_idx=True)
+    assert n == n0 and fj.last_stats()["dense"] == 1 and np.array_equal(pk[idx.astype(np.int64)], k)
+    assert np.array_equal(O.sorted_pairs(k, v), O.sorted_pairs(k0, v0)) and np.unique(idx).size == n0
+    # key 0 and probe keys far outside the domain
+    bk = np.array([0, 3, 7, 200], dtype=np.uint64)
+    pk = np.array([0, 0, 3, 4, 7, 200, 2**40, 2**64 - 1, 255, 256], dtype=np.uint64)
+    n, _ = fj.hash_join(bk, bk + np.uint64(10), pk)
+    assert n == 5 and fj.last_stats()["dense"] == 1
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(*O.np_join(bk, bk + np.uint64(10), pk)[1:]))
+    # one build key outside the optimistic domain: the hash path answers
+    bk, bv, pk = g1(500_000, 50_000, 10)
+    bk = bk.copy(); bk[777] = 10**9
+    n0, k0, v0 = O.np_join(bk, bv, pk)
+    n, _ = fj.hash_join(bk, bv, pk)
+    st = fj.last_stats()
+    assert n == n0 and st["dense"] == 0 and st["attempts"] == 2, st
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(k0, v0))
+    # a domain too large for two bitmaps per SM keeps the hash-table kernel (faster at high match rates there)
+    bk, bv, pk = g1(2_000_000, 1_000_000, 90)
+    n0, k0, v0 = O.np_join(bk, bv, pk)
+    n, _ = fj.hash_join(bk, bv, pk)
+    st = fj.last_stats()
+    assert n == n0 and st["dense"] == 0 and st["attempts"] == 1, st
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(k0, v0))
+    # duplicate build keys: an already-set bit -> exact keep-first path
+    rng = np.random.default_rng(3)
+    bk = rng.integers(0, 5000, 60_000).astype(np.uint64)
+    bv = np.arange(60_000, dtype=np.uint64)
+    pk = rng.integers(0, 6000, 200_000).astype(np.uint64)
+    n0, k0, v0 = O.join("scalar", False, True, bk, bv, pk)
+    n, _ = fj.hash_join(bk, bv, pk)
+    st = fj.last_stats()
+    assert n == n0 and st["dedup_exact"] is True and st["dense"] == 0, st
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(k0, v0))
 
 
 @pytest.fixture()

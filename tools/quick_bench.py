@@ -48,6 +48,8 @@ def main():
         if ny <= 10**7:
             run(f"{c} scalar count bloom (dense bitmap)", S, B, d, a.reps, N)
             run(f"{c} adaptive count (dense bitmap)", A, 0, d, a.reps, N)
+            run(f"{c} scalar mat (dense bitmap + direct table)", S, M, d, a.reps, N)
+            run(f"{c} adaptive mat (dense)", A, M, d, a.reps, N)
             capi.config_set(dense=0)
             run(f"{c} scalar count bloom", S, B, d, a.reps, N)
             run(f"{c} scalar count", S, 0, d, a.reps, N)
