@@ -102,6 +102,10 @@ fj_status_t dist_broadcast_u64(DistState& d, void* buf, size_t count, int root, 
   FJ_NCCL(g_api.Broadcast(buf, buf, count, ncclUint64, root, reinterpret_cast<ncclComm_t>(d.comm), st));
   return 0;
 }
+fj_status_t dist_broadcast_oop_u64(DistState& d, const void* send, void* recv, size_t count, int root, cudaStream_t st) {
+  FJ_NCCL(g_api.Broadcast(send, recv, count, ncclUint64, root, reinterpret_cast<ncclComm_t>(d.comm), st));
+  return 0;
+}
 fj_status_t dist_broadcast2_u64(DistState& d, const void* send_a, void* recv_a, const void* send_b, void* recv_b, size_t count,
                                 int root, cudaStream_t st) {
   ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);

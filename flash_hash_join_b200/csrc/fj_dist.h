@@ -25,6 +25,8 @@ fj_status_t dist_init(DistState& d, int rank, int world, const void* id128);
 void dist_destroy(DistState& d);
 // collectives on 64-bit words
 fj_status_t dist_broadcast_u64(DistState& d, void* buf, size_t count, int root, cudaStream_t st);
+// out of place: root sends from `send`, everybody (root included) receives in `recv`
+fj_status_t dist_broadcast_oop_u64(DistState& d, const void* send, void* recv, size_t count, int root, cudaStream_t st);
 // two broadcasts in one NCCL group (one launch): root sends from send_a / send_b, everybody receives in recv_a / recv_b
 fj_status_t dist_broadcast2_u64(DistState& d, const void* send_a, void* recv_a, const void* send_b, void* recv_b, size_t count,
                                 int root, cudaStream_t st);

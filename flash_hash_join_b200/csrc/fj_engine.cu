@@ -104,6 +104,12 @@ struct Engine {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[12] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases
   Ctl* h_ctl = nullptr;  // pinned
+  // multi-GPU count: the ncclAllReduce of the control block is enqueued right behind the first attempt's kernels
+  // (before the host has seen the flags), so a step has ONE host synchronisation instead of two.  The summed
+  // flags word tells every rank whether any rank has to retry; only then a second all-reduce follows.
+  bool spec_ar = false, spec_done = false;
+  unsigned long long* h_spec = nullptr;  // pinned, sizeof(Ctl): element-wise sum of all ranks' control blocks
+  fj_status spec_allreduce();
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
   DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush;
   uint64_t pairs_n = 0;
@@ -130,6 +136,7 @@ struct Engine {
     cfg["dense_batch"] = 2;         // k_djoin: tickets per dispatcher round trip
     cfg["dense_delay_b"] = 1;       // k_djoin: steps between zeroing a group of regions and filling it
     cfg["dense_delay_p"] = 3;       // k_djoin: steps between filling a group and probing it (sweep: profiles/r01f_sweep_djoin.jsonl)
+    cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
     cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
     // FJ_CFG_<KEY>=<integer> in the environment overrides a default (e.g. FJ_CFG_DENSE=0)
     for (auto& kv : cfg) {
@@ -218,6 +225,7 @@ fj_status Engine::init(int device) {
   FJ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto& x : ev) FJ_CUDA(cudaEventCreate(&x));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl)));
+  FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_spec), sizeof(Ctl)));
   FJ_TRY(ctl.ensure(4096));  // [0, 256): Ctl; [256, 272): grid-barrier words of the fused kernels (zero between launches)
   FJ_CUDA(cudaMemset(ctl.p, 0, 4096));
   inited = true;
@@ -234,6 +242,8 @@ void Engine::shutdown() {
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
+  if (h_spec) cudaFreeHost(h_spec);
+  h_spec = nullptr;
   for (auto& x : ev) { if (x) cudaEventDestroy(x); x = nullptr; }
   if (st) cudaStreamDestroy(st);
   st = nullptr;
@@ -320,6 +330,16 @@ int Engine::choose_path(int algo, unsigned flags, uint64_t nb, bool narrow_guess
   return FJ_ALGO_RADIX;
 }
 
+fj_status Engine::spec_allreduce() {
+  if (!spec_ar || spec_done) return FJ_OK;
+  spec_done = true;
+  static_assert(sizeof(Ctl) % 8 == 0, "Ctl is summed as 64-bit words");
+  unsigned long long* d_sum = reinterpret_cast<unsigned long long*>(static_cast<char*>(ctl.p) + 512);
+  FJ_TRY(dist_allreduce_sum_u64(dist, ctl.p, d_sum, sizeof(Ctl) / 8, st));
+  FJ_CUDA(cudaMemcpyAsync(h_spec, d_sum, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  return FJ_OK;
+}
+
 fj_status Engine::ensure_out(unsigned flags, uint64_t np) {
   if (!(flags & FJ_FLAG_MATERIALIZE)) return FJ_OK;
   const size_t bytes = std::max<uint64_t>(np, 1) * 8;
@@ -381,6 +401,7 @@ fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const 
   }
   launch_probe(t, pk, np, bv, mat ? &po : nullptr, bloom_smem, (int)cfg["probe_ctas_per_sm"], d_ctl, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
@@ -448,6 +469,7 @@ fj_status Engine::attempt_scalar_dense(unsigned flags, uint64_t dbits, const uns
     }
   }
   FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
@@ -552,6 +574,7 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   else launch_join(pl.narrow, mat, j, st, &launches);
   if (!pl.narrow && !flat) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
@@ -633,6 +656,7 @@ fj_status Engine::attempt_dense(unsigned flags, const DensePlan& dp, const unsig
   j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
   const bool launched = launch_djoin(mat, j, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
+  if (launched) FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
@@ -1068,21 +1092,51 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
       s.h2d_bytes = (uint64_t)((is_root ? 2 * nb : 0) + np) * 8;
       d_pk = in_pk.as<unsigned long long>();
     }
-    // broadcast the raw build rows (keys and values in one NCCL group)
+    // broadcast the raw build rows (keys and values in one NCCL group; a count never reads the values, so only
+    // the keys travel then)
+    const bool mat = jflags & FJ_FLAG_MATERIALIZE;
     FJ_CUDA(cudaEventRecord(ev[4], st));
-    if (nb) FJ_TRY(dist_broadcast2_u64(dist, src_bk, in_bk.p, src_bv, in_bv.p, nb, root, st));
-    FJ_CUDA(cudaEventRecord(ev[5], st));
-    FJ_TRY(join_device(algo, jflags, in_bk.as<unsigned long long>(), in_bv.as<unsigned long long>(), nb, d_pk, np, 0, &s));
-    // global count: all-reduce straight from the control block the probe kernel wrote
-    FJ_CUDA(cudaEventRecord(ev[0], st));
-    const void* cnt_src = &ctl.as<Ctl>()->match_count;
-    if (nb == 0 || np == 0) {  // no kernel ran on this rank
-      FJ_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
-      cnt_src = d_cnt;
+    if (nb) {
+      if (mat) FJ_TRY(dist_broadcast2_u64(dist, src_bk, in_bk.p, src_bv, in_bv.p, nb, root, st));
+      else FJ_TRY(dist_broadcast_oop_u64(dist, src_bk, in_bk.p, nb, root, st));
     }
-    FJ_TRY(dist_allreduce_sum_u64(dist, cnt_src, d_cnt + 1, 1, st));
+    FJ_CUDA(cudaEventRecord(ev[5], st));
+    const unsigned long long* d_bvals = mat ? in_bv.as<unsigned long long>() : in_bk.as<unsigned long long>();
+    // count: the all-reduce of the control block rides behind the first attempt's kernels (one host sync per step)
+    spec_ar = !mat && cfg["dist_spec_allreduce"] != 0;
+    spec_done = false;
+    fj_status js = join_device(algo, jflags, in_bk.as<unsigned long long>(), d_bvals, nb, d_pk, np, 0, &s);
+    const bool spec = spec_ar;
+    spec_ar = false;
+    if (js != FJ_OK) return js;
     unsigned long long total = 0;
-    FJ_CUDA(cudaMemcpyAsync(&total, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
+    bool need_plain = true;
+    if (spec) {
+      if (!spec_done) {  // no kernel ran on this rank (empty side): contribute an all-zero control block
+        spec_ar = true;
+        launch_init_ctl(ctl.as<Ctl>(), st);
+        fj_status hs = spec_allreduce();
+        spec_ar = false;
+        if (hs != FJ_OK) return hs;
+        FJ_CUDA(cudaStreamSynchronize(st));
+      }
+      // word 4 = flags | pad << 32 summed over the ranks: zero <=> nobody had to retry, word 0 is the global count
+      if (h_spec[4] == 0) {
+        total = h_spec[0];
+        need_plain = false;
+      }
+    }
+    FJ_CUDA(cudaEventRecord(ev[0], st));
+    if (need_plain) {
+      // global count: all-reduce straight from the control block the probe kernel wrote
+      const void* cnt_src = &ctl.as<Ctl>()->match_count;
+      if (nb == 0 || np == 0) {  // no kernel ran on this rank
+        FJ_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+        cnt_src = d_cnt;
+      }
+      FJ_TRY(dist_allreduce_sum_u64(dist, cnt_src, d_cnt + 1, 1, st));
+      FJ_CUDA(cudaMemcpyAsync(&total, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
+    }
     FJ_CUDA(cudaEventRecord(ev[1], st));
     FJ_CUDA(cudaStreamSynchronize(st));
     s.comm_s = (ms(4, 5) + ms(0, 1)) * 1e-3;

@@ -73,6 +73,43 @@ def main():
                 report["cases"].append({"mode": name, "materialize": bool(flags), "rows": N, "build_rows": ny, "matches": g, "expected": n0,
                                         "ok": bool(case_ok), "device_ms_max": max(x[3] for x in gathered) * 1e3,
                                         "comm_ms_max": max(x[4] for x in gathered) * 1e3, "paths": [x[5] for x in gathered]})
+    # ---- broadcast-mode COUNT with retries.  The all-reduce of the control block is enqueued behind the first
+    # attempt (one host sync per step); when any rank has to retry, every rank must notice and take the second
+    # all-reduce.  (a) symmetric: one build key far outside every optimistic domain -> all ranks re-run;
+    # (b) asymmetric: radix count where only the LAST rank's probe slice is skewed onto one key -> only that rank's
+    # partitions overflow and only it re-runs on the global table.
+    import ctypes as C
+
+    def bcast_count(algo, bk, bv, nb, pk):
+        g, l, sec, st = C.c_uint64(0), C.c_uint64(0), C.c_double(0), capi.Stats()
+        pkc = np.ascontiguousarray(pk)
+        if rank == 0:
+            bkc, bvc = np.ascontiguousarray(bk), np.ascontiguousarray(bv)
+            capi.check(capi.lib().fj_join_dist_u64(capi.DIST_BROADCAST, algo, 0, 0, bkc.ctypes.data, bvc.ctypes.data, nb, pkc.ctypes.data,
+                                                   pkc.size, C.byref(g), C.byref(l), C.byref(sec), C.byref(st)))
+        else:
+            capi.check(capi.lib().fj_join_dist_u64(capi.DIST_BROADCAST, algo, 0, 0, None, None, nb, pkc.ctypes.data, pkc.size,
+                                                   C.byref(g), C.byref(l), C.byref(sec), C.byref(st)))
+        return g.value, l.value, st.as_dict()
+
+    N, ny = 2_000_000, 1_200_000
+    fbk, fbv = g2_slice(N, ny, 90, 108, "build", 0, ny)
+    fpk = g2_slice(N, ny, 90, 108, "probe", 0, N)
+    p0, p1 = row_slice(N, world, rank)
+    for label, algo, bk, pk_local in (
+            ("symmetric retry (key outside the domain)", capi.ALGO_SCALAR, np.concatenate([fbk[:-1], np.array([10**12], np.uint64)]), fpk[p0:p1]),
+            ("asymmetric retry (one rank's probe slice skewed)", capi.ALGO_RADIX, fbk,
+             np.full(p1 - p0, fbk[5], np.uint64) if rank == world - 1 else fpk[p0:p1]),
+            ("no retry", capi.ALGO_ADAPTIVE, fbk, fpk[p0:p1])):
+        g, l, st = bcast_count(algo, bk, fbv, ny, pk_local)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (g, l, st["attempts"], pk_local))
+        if rank == 0:
+            n0 = O.np_join(bk, fbv, np.concatenate([x[3] for x in gathered]))[0]
+            case_ok = all(x[0] == n0 for x in gathered) and sum(x[1] for x in gathered) == n0
+            ok = ok and case_ok
+            report["cases"].append({"mode": "broadcast count, " + label, "matches": g, "expected": n0, "ok": bool(case_ok),
+                                    "attempts": [x[2] for x in gathered]})
     if rank == 0:
         report["ok"] = bool(ok)
         print(json.dumps(report))
