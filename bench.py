@@ -260,8 +260,10 @@ def main() -> None:
                 return "k_djoin (L2-resident direct-address join)"
             return "k_join3 (shared-memory partition join)" if last["radix_bits2"] else "k_join (shared-memory partition join)"
         if last["dense"]:
-            return ("k_count_dense_fused (bitmap build + probe, one persistent launch)" if last["kernel_launches"] == 1
-                    else "k_probe_count_dense (exact bitmap)")
+            if last["kernel_launches"] == 1:
+                return ("k_count_dense_peer (bitmap build + probe + count exchange over NVLink peer memory, one launch per GPU)" if world > 1
+                        else "k_count_dense_fused (bitmap build + probe, one persistent launch)")
+            return "k_probe_count_dense (exact bitmap)"
         return "k_probe_count"
 
     def measure(cfg_name: str, steps: int, warmup: int, want_e2e: bool, dense: bool = True) -> dict:
@@ -385,6 +387,9 @@ def main() -> None:
         capi.config_set(dense=1)
         if shuffle:
             par = f"both sides split over {world} GPUs, rows hash-partitioned by destination, NCCL all-to-all-v, local radix join, count ncclAllReduce"
+        elif world > 1 and last["dense"] and last["kernel_launches"] == 1 and not w["mat"]:
+            par = (f"probe side split over {world} GPUs; every GPU reads the build keys from rank 0 and exchanges its count through "
+                   "IPC-mapped peer memory inside the one count kernel (no NCCL call in the step)")
         elif world > 1:
             par = f"build side ncclBroadcast from rank 0, probe side split over {world} GPUs, count ncclAllReduce"
         else:

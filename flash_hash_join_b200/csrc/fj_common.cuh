@@ -24,12 +24,15 @@ struct Ctl {
   unsigned long long max_key;       // largest build key the stage-1 scatter staged
   unsigned long long dense_rows;    // build rows stored into the direct-address regions
   unsigned long long dense_slots;   // non-empty direct-address slots afterwards (< dense_rows <=> duplicate build keys)
+  // multi-GPU count over peer memory (k_count_dense_peer): sum of every rank's match_count
+  unsigned long long global_count;
 };
 enum : unsigned {
   CTL_NEED_WIDE = 1u,  // a build key or value does not fit the packed 32|32 slot
   CTL_DUP = 2u,        // duplicate build keys seen: keep-first needs the exact path
   CTL_OVERFLOW = 4u,   // an optimistic fixed-capacity partition buffer overflowed
   CTL_NOT_DENSE = 8u,  // a build key (or value) lies outside the optimistic dense key domain
+  CTL_PEER_TIMEOUT = 16u,  // a peer GPU did not show up in the peer-memory exchange (k_count_dense_peer)
 };
 
 // ---- hashing -----------------------------------------------------------------------------------

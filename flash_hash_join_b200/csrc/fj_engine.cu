@@ -116,6 +116,19 @@ struct Engine {
   bool pairs_valid = false, pairs_idx = false;
   std::map<std::string, int64_t> cfg;
   DistState dist;
+  // peer-memory exchange buffers (CUDA IPC over NVLink), set up at fj_comm_init; see k_count_dense_peer
+  struct PeerState {
+    bool ready = false;
+    void* local = nullptr;
+    size_t bytes = 0;
+    std::vector<void*> mapped;            // [world], mapped[rank] == local
+    unsigned long long** d_ptrs = nullptr;  // the same table in device memory
+    unsigned long long step = 0;          // advances in lockstep on every rank (one per peer-path call)
+  } peer;
+  fj_status peer_setup();
+  void peer_teardown();
+  fj_status attempt_count_peer(uint64_t dbits, int root, const unsigned long long* bk_root, bool bk_on_device, uint64_t nb,
+                               const unsigned long long* pk, uint64_t np, fj_stats* s);
 
   Engine() {
     cfg["load_pct"] = 50;
@@ -136,6 +149,7 @@ struct Engine {
     cfg["dense_batch"] = 2;         // k_djoin: tickets per dispatcher round trip
     cfg["dense_delay_b"] = 1;       // k_djoin: steps between zeroing a group of regions and filling it
     cfg["dense_delay_p"] = 3;       // k_djoin: steps between filling a group and probing it (sweep: profiles/r01f_sweep_djoin.jsonl)
+    cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
     cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
     cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
     // FJ_CFG_<KEY>=<integer> in the environment overrides a default (e.g. FJ_CFG_DENSE=0)
@@ -234,6 +248,7 @@ fj_status Engine::init(int device) {
 
 void Engine::shutdown() {
   if (!inited) return;
+  peer_teardown();
   dist_destroy(dist);
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
@@ -1044,6 +1059,104 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
   return set_err(FJ_ERR_STATE, "internal: shuffle join did not converge");
 }
 
+// ---- peer-memory exchange (CUDA IPC) ------------------------------------------------------------
+// Every rank allocates one exchange buffer, publishes its IPC handle with an ncclAllGather and maps everybody
+// else's buffer.  All ranks must agree on whether the peer path exists, so the per-rank outcome is summed.
+fj_status Engine::peer_setup() {
+  peer_teardown();
+  const int W = dist.world, R = dist.rank;
+  if (!dist.ready || W < 2 || W > 32 || !cfg["dist_peer"]) return FJ_OK;
+  const size_t bytes = peer_staging_offset_bytes() + (size_t(16) << 20);  // staging area: 2 Mi build keys
+  bool ok = cudaMalloc(&peer.local, bytes) == cudaSuccess;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) ok = cudaMemset(peer.local, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine, peer.local) == cudaSuccess;
+  cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle travels as 8 64-bit words");
+  FJ_TRY(dist_scratch.ensure((size_t)(W + 1) * 64 + 64));
+  unsigned long long* d_h = dist_scratch.as<unsigned long long>();
+  std::vector<cudaIpcMemHandle_t> all((size_t)W);
+  FJ_CUDA(cudaMemcpyAsync(d_h, &mine, 64, cudaMemcpyHostToDevice, st));
+  FJ_TRY(dist_allgather_u64(dist, d_h, d_h + 8, 8, st));
+  FJ_CUDA(cudaMemcpyAsync(all.data(), d_h + 8, (size_t)W * 64, cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  peer.mapped.assign((size_t)W, nullptr);
+  peer.mapped[(size_t)R] = peer.local;
+  for (int r = 0; r < W && ok; ++r) {
+    if (r == R) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+    peer.mapped[(size_t)r] = p;
+  }
+  if (ok) ok = cudaMalloc(reinterpret_cast<void**>(&peer.d_ptrs), (size_t)W * 8) == cudaSuccess &&
+               cudaMemcpy(peer.d_ptrs, peer.mapped.data(), (size_t)W * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+  cudaGetLastError();
+  // everybody or nobody
+  unsigned long long flag = ok ? 1ull : 0ull, sum = 0;
+  FJ_CUDA(cudaMemcpyAsync(d_h, &flag, 8, cudaMemcpyHostToDevice, st));
+  FJ_TRY(dist_allreduce_sum_u64(dist, d_h, d_h + 1, 1, st));
+  FJ_CUDA(cudaMemcpyAsync(&sum, d_h + 1, 8, cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  if (sum != (unsigned long long)W) {
+    peer_teardown();
+    return FJ_OK;  // the NCCL path stays
+  }
+  peer.bytes = bytes;
+  peer.step = 0;
+  peer.ready = true;
+  return FJ_OK;
+}
+
+void Engine::peer_teardown() {
+  if (st) cudaStreamSynchronize(st);
+  for (size_t r = 0; r < peer.mapped.size(); ++r)
+    if (peer.mapped[r] && peer.mapped[r] != peer.local) cudaIpcCloseMemHandle(peer.mapped[r]);
+  peer.mapped.clear();
+  if (peer.d_ptrs) cudaFree(peer.d_ptrs);
+  if (peer.local) cudaFree(peer.local);
+  peer.d_ptrs = nullptr;
+  peer.local = nullptr;
+  peer.bytes = 0;
+  peer.ready = false;
+  cudaGetLastError();
+}
+
+// One step of the multi-GPU count over peer memory: (root) copy the build keys into the staging area, then one
+// launch of k_count_dense_peer on every rank.  h_ctl->global_count is the answer unless h_ctl->flags says otherwise.
+fj_status Engine::attempt_count_peer(uint64_t dbits, int root, const unsigned long long* bk_root, bool bk_on_device, uint64_t nb,
+                                     const unsigned long long* pk, uint64_t np, fj_stats* s) {
+  const size_t bytes = dbits / 8;
+  FJ_TRY(bloom.ensure(bytes));
+  Ctl* d_ctl = ctl.as<Ctl>();
+  uint32_t* gsync = reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 256);
+  int launches = 0;
+  const unsigned long long step = ++peer.step;
+  FJ_CUDA(cudaEventRecord(ev[0], st));
+  if (dist.rank == root)
+    FJ_CUDA(cudaMemcpyAsync(static_cast<char*>(peer.local) + peer_staging_offset_bytes(), bk_root, nb * 8,
+                            bk_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  if (!launch_count_dense_peer(nb, pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, gsync, peer.d_ptrs, dist.rank,
+                               dist.world, root, step, di, st, &launches))
+    return set_err(FJ_ERR_CUDA, "k_count_dense_peer: no co-resident launch configuration");
+  FJ_CUDA(cudaEventRecord(ev[3], st));
+  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  FJ_CUDA(cudaGetLastError());
+  if (h_ctl->flags & CTL_PEER_TIMEOUT) return set_err(FJ_ERR_NCCL, "peer-memory exchange timed out (a rank did not join the step)");
+  s->probe_s += ms(0, 3) * 1e-3;
+  s->device_s += ms(0, 3) * 1e-3;
+  s->kernel_launches += launches;
+  s->table_bytes = bytes;
+  s->path = FJ_ALGO_SCALAR;
+  s->narrow = 1;
+  s->bloom_kind = 3;
+  s->dense = 1;
+  s->attempts = 1;
+  s->matches = h_ctl->match_count;
+  return FJ_OK;
+}
+
 // ---- multi-GPU drivers (one process per GPU) ---------------------------------------------------
 // BROADCAST (small build side, BASELINE.json configs[3]): the build rows given on `root` are
 // ncclBroadcast to every rank (16*nb bytes — cheaper than shipping the >= 2x larger table), every
@@ -1071,6 +1184,44 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
   if (mode == FJ_DIST_BROADCAST) {
     const bool is_root = dist.rank == root;
     if (is_root && nb && (!bk || !bv)) return set_err(FJ_ERR_BAD_ARG, "root rank must supply the build side");
+    // count on a dense key domain with the global-table path: one kernel per GPU over peer memory, no NCCL call.
+    // The decision uses only what every rank knows identically (flags, nb, configuration).
+    {
+      const bool narrow_cfg = !(jflags & FJ_FLAG_FORCE_WIDE) && cfg["narrow"] != 0;
+      const double table_bytes = (double)nb / ((double)cfg["load_pct"] / 100.0) * 8.0;
+      const bool scalar_path = algo == FJ_ALGO_SCALAR ||
+                               (algo == FJ_ALGO_ADAPTIVE && table_bytes <= (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0);
+      const uint64_t dbits = (peer.ready && cfg["dist_peer"] && cfg["dense_fused"] && !(jflags & FJ_FLAG_MATERIALIZE) && narrow_cfg &&
+                              scalar_path && nb > 0 && nb * 8 <= peer.bytes - peer_staging_offset_bytes())
+                                 ? dense_bitmap_bits(nb) : 0;
+      if (dbits) {
+        const unsigned long long* d_pk;
+        if (dev_in) {
+          d_pk = reinterpret_cast<const unsigned long long*>(pk);
+        } else {
+          FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
+          const double th = now_s();
+          if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+          FJ_CUDA(cudaStreamSynchronize(st));
+          s.h2d_s = now_s() - th;
+          s.h2d_bytes = (uint64_t)((is_root ? nb : 0) + np) * 8;
+          d_pk = in_pk.as<unsigned long long>();
+        }
+        pairs_valid = false;
+        FJ_TRY(attempt_count_peer(dbits, root, reinterpret_cast<const unsigned long long*>(bk), dev_in, nb, d_pk, np, &s));
+        if (!(h_ctl->flags & CTL_NOT_DENSE)) {  // same answer on every rank: the flag depends on the build side only
+          *out_global = h_ctl->global_count;
+          if (out_local) *out_local = s.matches;
+          s.wall_s = now_s() - t0;
+          s.algorithmic_bytes = 8ull * (nb + np);
+          if (out_seconds) *out_seconds = s.device_s;
+          if (stats) *stats = s;
+          return FJ_OK;
+        }
+        // a build key outside the optimistic domain: every rank falls through to the general (NCCL) path
+        s.attempts = 0;
+      }
+    }
     // stage inputs in HBM
     const unsigned long long* d_pk;
     FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
@@ -1369,10 +1520,12 @@ FJ_API fj_status fj_comm_init(int rank, int world, const void* id128) {
   if (!id128 || world < 1 || rank < 0 || rank >= world) return set_err(FJ_ERR_BAD_ARG, "bad rank/world/id");
   FJ_TRY(E().init(-1));
   FJ_CUDA(cudaSetDevice(E().di.device));
-  return dist_init(E().dist, rank, world, id128);
+  FJ_TRY(dist_init(E().dist, rank, world, id128));
+  return E().peer_setup();
 }
 FJ_API fj_status fj_comm_destroy(void) {
   std::lock_guard<std::mutex> lk(E().mu);
+  E().peer_teardown();
   dist_destroy(E().dist);
   return FJ_OK;
 }

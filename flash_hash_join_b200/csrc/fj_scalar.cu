@@ -32,6 +32,7 @@ __global__ void k_init_ctl(Ctl* ctl) {
   ctl->max_key = 0;
   ctl->dense_rows = 0;
   ctl->dense_slots = 0;
+  ctl->global_count = 0;
 }
 void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ctl); }
 
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(512) k_prepare(Ctl* __restrict__ ctl, uint4* _
     ctl->max_key = 0;
     ctl->dense_rows = 0;
     ctl->dense_slots = 0;
+    ctl->global_count = 0;
   }
   const uint4 f = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0u, 0u, 0u, 0u);
   for (uint64_t i = t; i < n_ones; i += stride) ones[i] = f;
@@ -708,6 +710,7 @@ __global__ void __launch_bounds__(THREADS)
     ctl->max_key = 0;
     ctl->dense_rows = 0;
     ctl->dense_slots = 0;
+    ctl->global_count = 0;
   }
   for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0u, 0u, 0u, 0u);
   const uint64_t ntiles = (np + TILE - 1) / TILE;
@@ -822,6 +825,231 @@ bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const u
   return ok;
 }
 
+// ---- the multi-GPU count as ONE kernel per GPU, no NCCL call in the step ------------------------------------------
+// BROADCAST mode (small build side replicated, probe side split over the GPUs; BASELINE.json configs[3] and the
+// contract bench at N > 1): every rank owns a small cudaMalloc'd exchange buffer that every other rank has mapped
+// through CUDA IPC at fj_comm_init (NVLink / NVSwitch peer memory):
+//     word 0            ready : the step number whose build keys the staging area holds (written by the root's kernel)
+//     words 8 + 8 r ..  slot r: { seq, count[2] } written by rank r's kernel (count indexed by step parity)
+//     word 8192 ..      staging area for the build keys (root only)
+// The kernel is k_count_dense_fused plus two exchanges done with system-scope loads / stores over NVLink:
+//   * instead of ncclBroadcast, every rank reads the build keys straight out of the ROOT's staging area;
+//   * instead of ncclAllReduce, the last CTA to finish posts the rank's count into every peer's slot, waits until
+//     all ranks' slots carry this step, and leaves the sum in Ctl::global_count.
+// A rank can be at most one step ahead of another (it needs everybody's slot of step k to finish step k), so
+// two count entries per slot are enough.  Spins give up after 10 s (CTL_PEER_TIMEOUT).
+constexpr int PEER_READY_WORD = 0;
+constexpr int PEER_SLOT_WORD = 8;       // + 8 * rank
+constexpr int PEER_STAGING_WORD = 8192;  // 64 KB into the buffer
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *p >= want (system scope); false after 10 s
+__device__ __forceinline__ bool wait_sys_ge(const unsigned long long* p, unsigned long long want) {
+  if (ld_acquire_sys_u64(p) >= want) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  for (;;) {
+    if (ld_acquire_sys_u64(p) >= want) return true;
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > 10000000000ull) return false;
+  }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    k_count_dense_peer(uint64_t nb, const unsigned long long* __restrict__ pk, uint64_t np, uint32_t* __restrict__ bitmap,
+                       uint32_t dwords /*multiple of 4*/, Ctl* __restrict__ ctl, uint32_t* __restrict__ gsync, int vec_ok,
+                       unsigned long long* const* __restrict__ peers /*[world] exchange buffers, peers[rank] is local*/,
+                       int rank, int world, int root, unsigned long long step) {
+  constexpr uint32_t TILE = THREADS * PROBE_KPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_flag;
+  uint32_t* sbm = reinterpret_cast<uint32_t*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t gtid = blockIdx.x * (uint64_t)THREADS + tid, gthreads = (uint64_t)gridDim.x * THREADS;
+  const unsigned long long dbits = (unsigned long long)dwords * 32ull;
+  unsigned long long* const root_buf = peers[root];
+  unsigned long long* const my_buf = peers[rank];
+
+  // ---- phase 0: control block + empty bitmap; first probe tile in flight; the root announces its staging area
+  // (the copy into it preceded this kernel in the root's stream)
+  if (gtid == 0) {
+    ctl->match_count = 0;
+    ctl->out_cursor = 0;
+    ctl->sentinel_row = EMPTY64;
+    ctl->sentinel_probes = 0;
+    ctl->flags = 0;
+    ctl->pad = 0;
+    ctl->max_key = 0;
+    ctl->dense_rows = 0;
+    ctl->dense_slots = 0;
+    ctl->global_count = 0;
+    if (rank == root) st_release_sys_u64(root_buf + PEER_READY_WORD, step);
+  }
+  for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const uint64_t ntiles = (np + TILE - 1) / TILE;
+  unsigned long long ka[PROBE_KPT], kb[PROBE_KPT];
+  uint32_t va = 0, vb = 0;
+  auto fetch = [&](uint64_t tile, unsigned long long (&k)[PROBE_KPT]) -> uint32_t {
+    const uint64_t tb = tile * TILE;
+    return load_tile<THREADS>(pk, np, tb, vec_ok && tb + TILE <= np, k);
+  };
+  uint64_t tile = blockIdx.x;
+  if (tile < ntiles) va = fetch(tile, ka);
+  grid_barrier(gsync + 0);
+
+  // ---- phase 1: build keys come straight out of the root's staging area (peer memory for every other rank)
+  {
+    if (rank != root) {
+      if (tid == 0) s_flag = wait_sys_ge(root_buf + PEER_READY_WORD, step) ? 1 : 0;
+      __syncthreads();
+      if (!s_flag && tid == 0) atomicOr(&ctl->flags, CTL_PEER_TIMEOUT);
+    }
+    const bool have = rank == root || s_flag;
+    const unsigned long long* bk = root_buf + PEER_STAGING_WORD;
+    bool bad = false;
+    if (have) {
+      for (uint64_t i = gtid; i < nb; i += gthreads) {
+        const unsigned long long k = ld_relaxed_sys_u64(bk + i);
+        if (k >= dbits) bad = true;
+        else atomicOr(bitmap + (uint32_t)(k >> 5), 1u << ((uint32_t)k & 31u));
+      }
+    }
+    if (bad) atomicOr(&ctl->flags, CTL_NOT_DENSE);
+  }
+  grid_barrier(gsync + 1);
+
+  // ---- phase 2: private copy of the bitmap, stream the probe tiles
+  uint32_t cnt = 0;
+  const bool dense = !(*reinterpret_cast<volatile unsigned int*>(&ctl->flags) & (CTL_NOT_DENSE | CTL_PEER_TIMEOUT));
+  if (dense) {
+    for (uint32_t i = tid; i < dwords / 4; i += THREADS) {
+      uint4 v;
+      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(reinterpret_cast<const uint4*>(bitmap) + i));
+      reinterpret_cast<uint4*>(sbm)[i] = v;
+    }
+    __syncthreads();
+    auto do_tile = [&](const unsigned long long (&key)[PROBE_KPT], const uint32_t valid) {
+      uint32_t w[PROBE_KPT];
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) {
+        const bool in = key[q] < dbits;
+        w[q] = sbm[in ? (uint32_t)(key[q] >> 5) : 0u];
+        w[q] = in ? w[q] : 0u;
+      }
+      uint32_t hits = 0;
+#pragma unroll
+      for (int q = 0; q < PROBE_KPT; ++q) hits |= ((w[q] >> ((uint32_t)key[q] & 31u)) & 1u) << q;
+      cnt += __popc(hits & valid);
+    };
+    while (tile < ntiles) {
+      const uint64_t t1 = tile + gridDim.x;
+      if (t1 < ntiles) vb = fetch(t1, kb);
+      do_tile(ka, va);
+      if (t1 >= ntiles) break;
+      const uint64_t t2 = t1 + gridDim.x;
+      if (t2 < ntiles) va = fetch(t2, ka);
+      do_tile(kb, vb);
+      tile = t2;
+    }
+  }
+  unsigned long long total = cnt;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+  if (lane == 0 && total) atomicAdd(&ctl->match_count, total);
+
+  // ---- exit: the last CTA of this rank exchanges the count with every peer and sums (replaces ncclAllReduce)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_flag = atomicAdd(gsync + 2, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flag && tid < 32) {  // warp 0 of the last CTA: lane r talks to rank r (world <= 32)
+    __threadfence();
+    const unsigned long long mine = atomicAdd(&ctl->match_count, 0ull);
+    const int par = (int)(step & 1ull);
+    if (lane < world) {
+      unsigned long long* slot = peers[lane] + PEER_SLOT_WORD + 8 * rank;  // my slot in rank `lane`'s buffer
+      st_relaxed_sys_u64(slot + 1 + par, mine);
+      st_release_sys_u64(slot, step);
+    }
+    unsigned long long got = 0;
+    bool ok = true;
+    if (lane < world) {
+      const unsigned long long* slot = my_buf + PEER_SLOT_WORD + 8 * lane;  // rank `lane`'s slot in my buffer
+      ok = wait_sys_ge(slot, step);
+      got = ok ? ld_relaxed_sys_u64(slot + 1 + par) : 0ull;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) got += __shfl_xor_sync(0xffffffffu, got, d);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+      if (!all_ok) atomicOr(&ctl->flags, CTL_PEER_TIMEOUT);
+      ctl->global_count = got;
+      gsync[0] = 0;
+      gsync[1] = 0;
+      gsync[2] = 0;
+    }
+  }
+}
+
+template <int THREADS>
+static bool launch_count_dense_peer_inst(uint64_t nb, const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords,
+                                         Ctl* ctl, uint32_t* gsync, unsigned long long* const* peers, int rank, int world, int root,
+                                         unsigned long long step, const DeviceInfo& di, cudaStream_t st) {
+  auto kern = k_count_dense_peer<THREADS>;
+  const size_t smem = (size_t)dwords * 4;
+  static size_t smem_set = 0;
+  static int occ_cached = 0;
+  if (smem != smem_set || occ_cached == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) return false;
+    smem_set = smem;
+    occ_cached = occ;
+  }
+  const uint64_t tile = (uint64_t)THREADS * PROBE_KPT;
+  uint64_t grid = (uint64_t)di.sms * occ_cached;  // all CTAs resident (grid barriers)
+  const uint64_t ntiles = (np + tile - 1) / tile;
+  if (grid > ntiles) grid = ntiles ? ntiles : 1;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok, peers, rank, world, root, step);
+  return true;
+}
+size_t peer_staging_offset_bytes() { return (size_t)PEER_STAGING_WORD * 8; }
+bool launch_count_dense_peer(uint64_t nb, const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
+                             uint32_t* gsync, unsigned long long* const* peers, int rank, int world, int root,
+                             unsigned long long step, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  bool ok;
+  if ((size_t)dwords * 4 * 2 + 4096 <= di.smem_optin)
+    ok = launch_count_dense_peer_inst<512>(nb, pk, np, bitmap, dwords, ctl, gsync, peers, rank, world, root, step, di, st);
+  else
+    ok = launch_count_dense_peer_inst<1024>(nb, pk, np, bitmap, dwords, ctl, gsync, peers, rank, world, root, step, di, st);
+  if (ok) ++*launches;
+  return ok;
+}
+
 // Materialize on a dense key domain (global-table path, hash_join.cpp:383-496): the same persistent launch,
 // with a direct-address value table next to the bitmap: direct[key] = build value (8 bytes, L2 resident:
 // 2 MB at C2, 14 MB at 1e6 build rows).  The exact bitmap in shared memory answers "does this probe row
@@ -863,6 +1091,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
     ctl->max_key = 0;
     ctl->dense_rows = 0;
     ctl->dense_slots = 0;
+    ctl->global_count = 0;
   }
   for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0u, 0u, 0u, 0u);
   grid_barrier(gsync + 0);
