@@ -35,7 +35,7 @@ if has tests; then
   tail -5 "$OUT/pytest_gpu.log"
 fi
 if has quick; then
-  timeout 900 python tools/quick_bench.py C2 C3 --reps 5 > "$OUT/quick_bench.jsonl" 2> "$OUT/quick_bench.err"
+  timeout 900 python tools/quick_bench.py C1 C2 C4s C3 --reps 5 > "$OUT/quick_bench.jsonl" 2> "$OUT/quick_bench.err"
   cat "$OUT/quick_bench.jsonl"
 fi
 if has bench; then
@@ -54,7 +54,7 @@ if has launches; then
     python tools/prof_case.py C3 radix mat --reps 2 > "$OUT/launches_c3.log" 2>&1
 fi
 if has ncu_c2; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_probe -s 2 -c 1 -f -o "$OUT/c2_probe" \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_count_dense|k_probe" -s 2 -c 1 -f -o "$OUT/c2_probe" \
     python tools/prof_case.py C2 scalar count bloom --reps 4 > "$OUT/ncu_c2.log" 2>&1
 fi
 if has ncu_c3; then

@@ -14,8 +14,8 @@ echo "dist_check exit $?" >> "$OUT/dist_check.log"
 tail -n 4 "$OUT/dist_check.log"
 timeout 400 $TR --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 > "$OUT/bench_c2_n$N.json" 2> "$OUT/bench_c2_n$N.err"
 echo "bench c2 exit $?"; cat "$OUT/bench_c2_n$N.json"
-timeout 400 $TR --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --config C3 > "$OUT/bench_c3_n$N.json" 2> "$OUT/bench_c3_n$N.err"
+[ -n "${SKIP_C3:-}" ] || timeout 400 $TR --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --config C3 > "$OUT/bench_c3_n$N.json" 2> "$OUT/bench_c3_n$N.err"
 echo "bench c3 exit $?"; cat "$OUT/bench_c3_n$N.json"
-timeout 300 $TR --master-port 29514 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > "$OUT/bench_ref_n$N.json" 2> "$OUT/bench_ref_n$N.err"
+[ -n "${SKIP_REF:-}" ] || timeout 300 $TR --master-port 29514 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > "$OUT/bench_ref_n$N.json" 2> "$OUT/bench_ref_n$N.err"
 echo "bench ref exit $?"; cat "$OUT/bench_ref_n$N.json"
 ls -la "$OUT"
