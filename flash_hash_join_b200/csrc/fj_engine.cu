@@ -735,7 +735,15 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
     dense_bits = lim2 >= nb + 1 ? lim2 : 0;
   }
   DensePlan dplan;
-  if (narrow && path == FJ_ALGO_RADIX) {
+  // the direct-address radix join has no partition-size limit: it also serves build sides that two general scatter
+  // passes cannot cut down to shared-memory size (plan.ok == false, > ~2.6e8 rows), which would otherwise fall back
+  // to one huge global table
+  const bool radix_wanted =
+      path == FJ_ALGO_RADIX ||
+      (!plan.ok && !((flags & FJ_FLAG_PROBE_IDX) && mat) &&
+       (algo == FJ_ALGO_RADIX || (algo == FJ_ALGO_ADAPTIVE && (double)nb / ((double)cfg["load_pct"] / 100.0) * 8.0 >
+                                                                 (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0)));
+  if (narrow && radix_wanted) {
     dplan = plan_dense(flags, nb, np);
     if (dplan.ok && direct.ensure((size_t)djoin_fan() * dplan.rstride * 4) != FJ_OK) dplan.ok = false;  // no room: general path
   }
@@ -746,7 +754,7 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
       if (plan.narrow != narrow) plan = plan_radix(nb, np, narrow);
       if (!plan.ok) { path = FJ_ALGO_SCALAR; }
     }
-    const bool dense_radix = path == FJ_ALGO_RADIX && narrow && dplan.ok;
+    const bool dense_radix = radix_wanted && narrow && dplan.ok;
     const bool dense_scalar = path == FJ_ALGO_SCALAR && narrow && !exact && dense_bits != 0;
     if (dense_radix) FJ_TRY(attempt_dense(flags, dplan, bk, bv, nb, pk, np, s));
     else if (dense_scalar) FJ_TRY(attempt_scalar_dense(flags, dense_bits, bk, bv, nb, pk, np, idx_base, s));

@@ -541,6 +541,32 @@ def test_c3_full_size_golden(fj, golden_cases):
     assert n == c["count"]
 
 
+@pytest.mark.big
+def test_beyond_two_pass_plan_takes_dense_radix(capi):
+    """3e8 x 3e8 rows (G2, generated in HBM): two general scatter passes cannot cut the build side down to shared-memory
+    partitions any more (plan_radix gives up above ~2.6e8 rows); on a dense key domain the direct-address radix join
+    still applies instead of one huge global table.  No CPU oracle finishes in seconds here: the dense radix join and
+    the global-table path are independent algorithms — counts and pair checksums must agree (tools/big_check.py)."""
+    N = 300_000_000
+    bk, bv = capi.generate_g2("build", N, N, 90, 108, 0, N)
+    pk = capi.generate_g2("probe", N, N, 90, 108, 0, N)
+    try:
+        got = []
+        for algo, cfg in ((capi.ALGO_RADIX, {"dense": 1}), (capi.ALGO_SCALAR, {"dense": 0})):
+            capi.config_set(**cfg)
+            n, _, st = capi.join(algo, capi.FLAG_MATERIALIZE, bk, bv, pk)
+            cs = O.checksums(*capi.pairs())
+            got.append((n, cs["sum_keys"], cs["xor_keys"], cs["sum_vals"], st["path"], st["dense"]))
+        assert got[0][:4] == got[1][:4], got
+        assert got[0][4:] == ("radix", 1) and got[1][4:] == ("scalar", 0), got
+        n_adaptive, _, st = capi.join(capi.ALGO_ADAPTIVE, 0, bk, bv, pk)
+        assert n_adaptive == got[0][0]
+    finally:
+        capi.config_set(dense=1)
+        for x in (bk, bv, pk):
+            x.free()
+
+
 # ------------------------------------------------------------------------------------------------ shuffle (1 GPU)
 @pytest.fixture(scope="module")
 def comm1(capi):
