@@ -541,6 +541,52 @@ def test_c3_full_size_golden(fj, golden_cases):
     assert n == c["count"]
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_differential(fj, seed):
+    """Seeded random shapes and key domains through all twelve entry points against the numpy restatement: sizes that
+    straddle tile boundaries, dense and sparse 32- and 64-bit key domains, keys at the edge of the optimistic dense
+    bound, duplicate build keys, 32- and 64-bit values, probe sides with few / many matches.  Whatever layout the
+    engine picks (dense, packed, wide, exact), the result must be the same."""
+    rng = np.random.default_rng(1000 + seed)
+    fj.configure(dense_min_rows=int(rng.choice([1024, 1 << 20])))
+    try:
+        for _ in range(6):
+            nb = int(np.exp(rng.uniform(0, np.log(300_000))))
+            np_ = int(np.exp(rng.uniform(0, np.log(1_500_000))))
+            domain = rng.choice(["dense", "dense_edge", "sparse32", "sparse64"])
+            if domain == "dense":
+                U = max(nb + 1, int(nb * rng.uniform(1.0, 1.9)) + 1)
+            elif domain == "dense_edge":  # the largest key sits exactly at / just past the power-of-two bound above 2 nb
+                U = 1024
+                while U < 2 * nb:
+                    U <<= 1
+                U += int(rng.integers(-1, 2))
+            elif domain == "sparse32":
+                U = 2**32 - 1
+            else:
+                U = 2**64 - 1
+            if U <= 4 * nb + 8:
+                pool = rng.permutation(U)[:nb].astype(np.uint64)  # unique keys in [0, U)
+                if domain == "dense_edge":
+                    pool[0] = U - 1
+            else:
+                pool = np.unique(rng.integers(0, U, nb, dtype=np.uint64, endpoint=True))
+            bk = pool
+            if rng.random() < 0.3 and bk.size > 1:  # duplicate build keys: keep-first decides the value
+                bk = np.concatenate([bk, rng.choice(bk, max(1, bk.size // 10))])
+                rng.shuffle(bk)
+            bv = (rng.integers(0, 2**64 - 1, bk.size, dtype=np.uint64) if rng.random() < 0.3
+                  else rng.integers(0, 100, bk.size).astype(np.uint64))
+            hit = rng.uniform(0, 1)
+            n_hit = int(np_ * hit)
+            miss_hi = int(min(2**64 - 1, max(2 * int(U), 16)))
+            pk = np.concatenate([rng.choice(bk, n_hit), rng.integers(0, miss_hi, np_ - n_hit, dtype=np.uint64, endpoint=True)])
+            rng.shuffle(pk)
+            check_all_entry_points(fj, bk, bv, pk)
+    finally:
+        fj.configure(dense_min_rows=1 << 20)
+
+
 @pytest.mark.big
 def test_beyond_two_pass_plan_takes_dense_radix(capi):
     """3e8 x 3e8 rows (G2, generated in HBM): two general scatter passes cannot cut the build side down to shared-memory
