@@ -129,7 +129,12 @@ FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values,
  *       "radix_sub_rows" (target build rows per shared-memory partition), "radix_optimistic",
  *       "smem_bloom" (0/1), "join3" (0/1: collision-free pipelined partition join for packed rows), "probe_ctas_per_sm", "chunk_rows" (host-input pipelining chunk),
  *       "dense" (0/1: optimistic dense-key-domain fast paths), "dense_min_rows" (smallest build side that takes the
- *       direct-address radix join), "dense_group_mb" (MB of direct-address regions per L2 pipeline stage). */
+ *       direct-address radix join), "dense_group_mb" (MB of direct-address regions per L2 pipeline stage),
+ *       "dense_ring" / "dense_batch" (k_djoin: per-CTA item look-ahead), "dense_delay_b" / "dense_delay_p" (k_djoin: steps
+ *       between zeroing, filling and probing a group of regions), "dense_fused" (0/1: bitmap count / materialize as one
+ *       persistent launch), "dist_peer" (0/1: multi-GPU count over IPC-mapped peer memory instead of NCCL; read at
+ *       fj_comm_init and per call), "dist_spec_allreduce" (0/1: NCCL count all-reduce enqueued behind the first attempt).
+ *       Every key can also be preset from the environment as FJ_CFG_<KEY>=<integer>. */
 FJ_API fj_status fj_config_set(const char* key, int64_t value);
 FJ_API fj_status fj_config_get(const char* key, int64_t* value);
 
@@ -157,7 +162,11 @@ FJ_API fj_status fj_timer_stop(double* seconds);
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) ----------------------------------------
  * No reference counterpart (hash_join.cpp is single-process, std::thread only).  The caller
  * distributes a 128-byte NCCL unique id produced by rank 0 (any transport: torch.distributed,
- * MPI, a file) and every rank calls fj_comm_init.
+ * MPI, a file) and every rank calls fj_comm_init.  fj_comm_init also maps a 16 MB exchange buffer of every
+ * peer GPU through CUDA IPC (GPUs of one node); a broadcast-mode COUNT on a dense key domain then runs as one
+ * kernel per GPU over that peer memory (build keys read from the root GPU, counts exchanged with system-scope
+ * loads/stores over NVLink) with no NCCL call in the join.  Like a collective, a distributed join blocks until
+ * every rank has made the same call.
  *   fj_join_dist_u64, FJ_DIST_BROADCAST: the build side lives on rank `root` (every rank passes the same
  *     nb; bk/bv are only read on root and may be NULL elsewhere) and is ncclBroadcast to all ranks, each
  *     rank builds locally and probes ITS OWN probe slice (pk/np are rank-local); counts are summed with
