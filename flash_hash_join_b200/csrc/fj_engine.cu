@@ -9,6 +9,7 @@
 // The reference allocates every table/partition/result buffer inside each call (std::vector,
 // make_unique through mimalloc); here buffers live in a grow-only device arena reused across calls.
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <chrono>
 #include <cmath>
@@ -19,6 +20,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/flashjoin_b200.h"
@@ -110,6 +112,20 @@ struct Engine {
   bool spec_ar = false, spec_done = false;
   unsigned long long* h_spec = nullptr;  // pinned, sizeof(Ctl): element-wise sum of all ranks' control blocks
   fj_status spec_allreduce();
+  // host -> device copy of one input column.  Page-locked sources (flash_join.pinned_empty, cudaHostRegister'ed
+  // memory) go straight to the DMA engine; large PAGEABLE sources (plain numpy arrays — what a reference user
+  // passes) are staged by a few host threads through a ring of pinned buffers, chunk by chunk, overlapped with
+  // the DMA (cudaMemcpyAsync from pageable memory stages single-threaded: ~12 GB/s here vs 55 GB/s pinned).
+  struct Stager {
+    int threads = 0;
+    size_t chunk = 0;
+    std::vector<char*> bufs;           // [threads][2]
+    std::vector<cudaEvent_t> evs;      // [threads][2] buffer free again
+    std::vector<cudaStream_t> streams; // [threads]
+    std::vector<cudaEvent_t> done;     // [threads]
+  } stager;
+  fj_status h2d(void* dst, const void* src, size_t bytes);
+  void stager_release();
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
   DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush;
   uint64_t pairs_n = 0;
@@ -149,6 +165,8 @@ struct Engine {
     cfg["dense_batch"] = 2;         // k_djoin: tickets per dispatcher round trip
     cfg["dense_delay_b"] = 1;       // k_djoin: steps between zeroing a group of regions and filling it
     cfg["dense_delay_p"] = 3;       // k_djoin: steps between filling a group and probing it (sweep: profiles/r01f_sweep_djoin.jsonl)
+    cfg["stage_threads"] = 8;       // host threads staging large pageable inputs through pinned buffers (0: plain cudaMemcpyAsync)
+    cfg["stage_min_mb"] = 64;       // smallest pageable input column that is staged
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
     cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
     cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
@@ -259,6 +277,7 @@ void Engine::shutdown() {
   h_ctl = nullptr;
   if (h_spec) cudaFreeHost(h_spec);
   h_spec = nullptr;
+  stager_release();
   for (auto& x : ev) { if (x) cudaEventDestroy(x); x = nullptr; }
   if (st) cudaStreamDestroy(st);
   st = nullptr;
@@ -343,6 +362,84 @@ int Engine::choose_path(int algo, unsigned flags, uint64_t nb, bool narrow_guess
   const double l2_budget = (double)di.l2_bytes * (double)cfg.at("adaptive_table_l2_pct") / 100.0;
   if (table_bytes <= l2_budget || !plan.ok) return FJ_ALGO_SCALAR;
   return FJ_ALGO_RADIX;
+}
+
+// ---- host -> device input copy -------------------------------------------------------------------
+void Engine::stager_release() {
+  for (char* b : stager.bufs) if (b) cudaFreeHost(b);
+  for (auto e : stager.evs) if (e) cudaEventDestroy(e);
+  for (auto e : stager.done) if (e) cudaEventDestroy(e);
+  for (auto q : stager.streams) if (q) cudaStreamDestroy(q);
+  stager = Stager();
+}
+
+fj_status Engine::h2d(void* dst, const void* src, size_t bytes) {
+  if (!bytes) return FJ_OK;
+  const int want_threads = (int)std::min<int64_t>(32, std::max<int64_t>(0, cfg["stage_threads"]));
+  bool staged = want_threads > 0 && bytes >= ((size_t)std::max<int64_t>(1, cfg["stage_min_mb"]) << 20);
+  if (staged) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, src) != cudaSuccess) {
+      cudaGetLastError();
+    } else if (pa.type != cudaMemoryTypeUnregistered) {
+      staged = false;  // pinned / registered / managed: the DMA engine reads it directly
+    }
+  }
+  if (!staged) {
+    FJ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return FJ_OK;
+  }
+  const size_t CH = size_t(8) << 20;
+  if (stager.threads != want_threads || stager.chunk != CH) {
+    stager_release();
+    stager.threads = want_threads;
+    stager.chunk = CH;
+    stager.bufs.assign((size_t)want_threads * 2, nullptr);
+    stager.evs.assign((size_t)want_threads * 2, nullptr);
+    stager.streams.assign((size_t)want_threads, nullptr);
+    stager.done.assign((size_t)want_threads, nullptr);
+    for (auto& b : stager.bufs) FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b), CH));
+    for (auto& e : stager.evs) FJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : stager.done) FJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& q : stager.streams) FJ_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  }
+  // the copy streams must not overtake work already queued on the engine's stream that still uses `dst`
+  FJ_CUDA(cudaEventRecord(stager.done[0], st));
+  for (int t = 0; t < want_threads; ++t) FJ_CUDA(cudaStreamWaitEvent(stager.streams[(size_t)t], stager.done[0], 0));
+  const size_t nchunks = (bytes + CH - 1) / CH;
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  const int dev = di.device;
+  auto worker = [&](int t) {
+    if (cudaSetDevice(dev) != cudaSuccess) { failed = 1; return; }
+    int b = 0;
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nchunks || failed.load()) break;
+      const size_t off = i * CH, len = std::min(CH, bytes - off);
+      char* buf = stager.bufs[(size_t)t * 2 + b];
+      cudaEvent_t ev_free = stager.evs[(size_t)t * 2 + b];
+      if (cudaEventSynchronize(ev_free) != cudaSuccess) { failed = 1; break; }  // the DMA out of this buffer is over
+      memcpy(buf, static_cast<const char*>(src) + off, len);
+      if (cudaMemcpyAsync(static_cast<char*>(dst) + off, buf, len, cudaMemcpyHostToDevice, stager.streams[(size_t)t]) != cudaSuccess ||
+          cudaEventRecord(ev_free, stager.streams[(size_t)t]) != cudaSuccess) { failed = 1; break; }
+      b ^= 1;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < want_threads; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  if (failed.load()) {
+    cudaGetLastError();
+    return set_err(FJ_ERR_CUDA, "staged host->device copy failed");
+  }
+  // everything the copy streams did happens-before whatever is queued on the engine's stream next
+  for (int t = 0; t < want_threads; ++t) {
+    FJ_CUDA(cudaEventRecord(stager.done[(size_t)t], stager.streams[(size_t)t]));
+    FJ_CUDA(cudaStreamWaitEvent(st, stager.done[(size_t)t], 0));
+  }
+  return FJ_OK;
 }
 
 fj_status Engine::spec_allreduce() {
@@ -795,10 +892,10 @@ fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint6
     FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
     const double th = now_s();
     if (nb) {
-      FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyHostToDevice, st));
-      FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyHostToDevice, st));
+      FJ_TRY(h2d(in_bk.p, bk, nb * 8));
+      FJ_TRY(h2d(in_bv.p, bv, nb * 8));
     }
-    if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+    if (np) FJ_TRY(h2d(in_pk.p, pk, np * 8));
     FJ_CUDA(cudaStreamSynchronize(st));
     s.h2d_s = now_s() - th;
     s.h2d_bytes = (uint64_t)(2 * nb + np) * 8;
@@ -1209,7 +1306,7 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
         } else {
           FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
           const double th = now_s();
-          if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+          if (np) FJ_TRY(h2d(in_pk.p, pk, np * 8));
           FJ_CUDA(cudaStreamSynchronize(st));
           s.h2d_s = now_s() - th;
           s.h2d_bytes = (uint64_t)((is_root ? nb : 0) + np) * 8;
@@ -1242,10 +1339,10 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
     } else {
       FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
       if (is_root && nb) {
-        FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyHostToDevice, st));
-        FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyHostToDevice, st));
+        FJ_TRY(h2d(in_bk.p, bk, nb * 8));
+        FJ_TRY(h2d(in_bv.p, bv, nb * 8));
       }
-      if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+      if (np) FJ_TRY(h2d(in_pk.p, pk, np * 8));
       FJ_CUDA(cudaStreamSynchronize(st));
       s.h2d_s = now_s() - th;
       s.h2d_bytes = (uint64_t)((is_root ? 2 * nb : 0) + np) * 8;
@@ -1315,10 +1412,10 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
       FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
       const double th = now_s();
       if (nb) {
-        FJ_CUDA(cudaMemcpyAsync(in_bk.p, bk, nb * 8, cudaMemcpyHostToDevice, st));
-        FJ_CUDA(cudaMemcpyAsync(in_bv.p, bv, nb * 8, cudaMemcpyHostToDevice, st));
+        FJ_TRY(h2d(in_bk.p, bk, nb * 8));
+        FJ_TRY(h2d(in_bv.p, bv, nb * 8));
       }
-      if (np) FJ_CUDA(cudaMemcpyAsync(in_pk.p, pk, np * 8, cudaMemcpyHostToDevice, st));
+      if (np) FJ_TRY(h2d(in_pk.p, pk, np * 8));
       FJ_CUDA(cudaStreamSynchronize(st));
       s.h2d_s = now_s() - th;
       s.h2d_bytes = (uint64_t)(2 * nb + np) * 8;

@@ -541,6 +541,25 @@ def test_c3_full_size_golden(fj, golden_cases):
     assert n == c["count"]
 
 
+def test_pageable_inputs_staged(fj):
+    """Plain (pageable) numpy columns above `stage_min_mb` travel through the multi-threaded pinned staging ring
+    (Engine::h2d): three 8 MB chunks, the last one partial, three host threads; page-locked columns bypass it."""
+    bk, bv, pk = g1(3_000_000, 50_000, 50)  # 24 MB probe column
+    expect = O.np_join(bk, bv, pk)
+    fj.configure(stage_min_mb=1, stage_threads=3)
+    try:
+        check_all_entry_points(fj, bk, bv, pk, expect=expect, algos=("scalar",))
+        hp = fj.pinned_empty(pk.size)
+        hp[:] = pk
+        n, _ = fj.hash_join_count(bk, bv, hp)
+        assert n == expect[0]
+        fj.configure(stage_threads=0)  # plain cudaMemcpyAsync
+        n, _ = fj.hash_join_count(bk, bv, pk)
+        assert n == expect[0]
+    finally:
+        fj.configure(stage_min_mb=64, stage_threads=8)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_randomized_differential(fj, seed):
     """Seeded random shapes and key domains through all twelve entry points against the numpy restatement: sizes that
