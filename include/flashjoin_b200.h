@@ -134,6 +134,8 @@ FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values,
  *       between zeroing, filling and probing a group of regions), "dense_fused" (0/1: bitmap count / materialize as one
  *       persistent launch), "dist_peer" (0/1: multi-GPU count over IPC-mapped peer memory instead of NCCL; read at
  *       fj_comm_init and per call), "dist_spec_allreduce" (0/1: NCCL count all-reduce enqueued behind the first attempt).
+ *       "stage_threads" / "stage_min_mb" (host threads that stage pageable input columns of at least that many MB through
+ *       pinned buffers; 0 threads = plain cudaMemcpyAsync).
  *       Every key can also be preset from the environment as FJ_CFG_<KEY>=<integer>. */
 FJ_API fj_status fj_config_set(const char* key, int64_t value);
 FJ_API fj_status fj_config_get(const char* key, int64_t* value);
