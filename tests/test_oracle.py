@@ -134,3 +134,45 @@ def test_c_oracle_matches_compiled_reference():
     pk = np.array([0, 2**64 - 1, 8, 7, 7], dtype=np.uint64)
     for name in ("hash_join_count", "hash_join_count_bloom", "hash_join_count_radix"):
         assert getattr(plain, name)(bk, bv, pk)[0] == 4 == O.join("scalar", False, False, bk, bv, pk)[0]
+
+
+@pytest.mark.skipif(not O.reference_available("pairs"), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(8))
+def test_numpy_restatement_vs_compiled_reference_randomized(seed):
+    """np_join is the checker of most GPU parity tests: pin IT against the compiled reference on seeded random shapes
+    and key domains (dense / sparse 32- and 64-bit, edge keys 0 and 2^64-1).  Unique build keys: every reference
+    entry point must agree.  Duplicate build keys: only the reference's radix path is deterministic (keep-first,
+    hash_join.cpp:125 + :226-234), so duplicates are checked against that path alone."""
+    plain, pairs = O.load_reference("plain"), O.load_reference("pairs")
+    rng = np.random.default_rng(500 + seed)
+    for _ in range(4):
+        nb = int(np.exp(rng.uniform(0, np.log(60_000))))
+        np_ = int(np.exp(rng.uniform(0, np.log(300_000))))
+        U = [max(nb + 1, 2 * nb), 2**32 - 1, 2**64 - 1][int(rng.integers(0, 3))]
+        if U <= 4 * nb + 8:
+            bk = rng.permutation(U)[:nb].astype(np.uint64)
+        else:
+            bk = np.unique(rng.integers(0, U, nb, dtype=np.uint64, endpoint=True))
+        if rng.random() < 0.5:
+            bk = np.concatenate([bk, np.array([0, 2**64 - 1], dtype=np.uint64)])
+            bk = np.unique(bk)
+        dup = rng.random() < 0.4 and bk.size > 1
+        if dup:
+            bk = np.concatenate([bk, rng.choice(bk, max(1, bk.size // 7))])
+        rng.shuffle(bk)
+        bv = rng.integers(0, 2**64 - 1, bk.size, dtype=np.uint64)
+        n_hit = int(np_ * rng.uniform(0, 1))
+        pk = np.concatenate([rng.choice(bk, n_hit), rng.integers(0, min(2**64 - 1, max(2 * U, 16)), np_ - n_hit, dtype=np.uint64, endpoint=True)])
+        rng.shuffle(pk)
+        n0, k0, v0 = O.np_join(bk, bv, pk)
+        sp0 = O.sorted_pairs(k0, v0)
+        for algo, bloom, mat in ALL:
+            if dup and algo != "radix":
+                continue
+            name = O.entry_point_name(algo, bloom, mat)
+            if mat:
+                r = getattr(pairs, name)(bk, bv, pk)
+                assert r[0] == n0, (name, nb, np_, U)
+                assert np.array_equal(O.sorted_pairs(r[2], r[3]), sp0), (name, nb, np_, U)
+            else:
+                assert getattr(plain, name)(bk, bv, pk)[0] == n0, (name, nb, np_, U)
