@@ -210,7 +210,10 @@ def main() -> None:
             "config": {"workload": w["desc"], "entry_point": w["entry"], "rows_probe": w["N"], "rows_build": w["ny"],
                        "note": "reference CPU implementation on the host cores of this box; time = its own core seconds"},
             "cpu_baseline": {"value": value, "unit": "rows/s", "cores": r["cores"], "kind": r["kind"],
-                             "sample": f"full workload ({w['N']} probe rows) x {args.steps} steps"},
+                             "sample": f"full workload ({w['N']} probe rows) x {args.steps} steps",
+                             "build": "unmodified hash_join.cpp, g++ -O3 -msse4.2 -mavx2, glibc malloc (mimalloc stubbed out: its "
+                                      "malloc override crashes next to torch in this image; it matters for the allocation-heavy "
+                                      "radix-materialize shapes, not for this count)"},
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "matches": r["matches"],
         }
@@ -453,7 +456,8 @@ def main() -> None:
         try:
             r = run_cpu_worker(args.config, 5, 1)
             cpu = {"value": r["rows"] / r["core_s_mean"], "unit": "rows/s", "cores": r["cores"], "kind": r["kind"],
-                   "sample": f"full workload ({r['rows']} probe rows) x 5 steps, time = reference core seconds", "matches": r["matches"]}
+                   "sample": f"full workload ({r['rows']} probe rows) x 5 steps, time = reference core seconds", "matches": r["matches"],
+                   "build": "unmodified hash_join.cpp, g++ -O3 -msse4.2 -mavx2, glibc malloc (mimalloc stubbed out)"}
             if r["matches"] != matches:
                 cpu["MISMATCH"] = f"reference counted {r['matches']}, engine counted {matches}"
         except Exception as e:  # the baseline is reported, never required for the engine number
