@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # tools/gpu_round.sh <tag> [steps...] — one gpurun call's worth of work; everything lands in gpurun_out/<tag>/.
-# steps: sanity tests quick bench ref launches ncu_c2 ncu_c3 ncu_general sanitize   (default: all but ncu_general, sanitize)
+# steps: sanity tests quick bench ref launches ncu_c2 ncu_c3 ncu_general ubench2 sanitize   (default: all but ncu_general, sanitize)
 set -u
 TAG=${1:-r1}
 shift || true
@@ -66,6 +66,11 @@ if has ncu_general; then  # the general hash path of the same two workloads (den
     python tools/prof_case.py C2 scalar count bloom --reps 4 --set dense=0 > "$OUT/ncu_c2_general.log" 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_scatter2|k_join" -s 5 -c 5 -f -o "$OUT/c3_radix_general" \
     python tools/prof_case.py C3 radix mat --reps 3 --set dense=0 > "$OUT/ncu_c3_general.log" 2>&1
+fi
+if has ubench2; then  # design inputs for DESIGN.md §8 item 1 (L2 vs DSMEM vs shared memory for the random accesses)
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 tools/ubench2.cu -o "$OUT/ubench2.bin" > "$OUT/ubench2.build.log" 2>&1 \
+    && timeout 300 "$OUT/ubench2.bin" > "$OUT/ubench2.jsonl" 2> "$OUT/ubench2.err"
+  cat "$OUT/ubench2.jsonl"
 fi
 if has sanitize; then
   timeout 900 compute-sanitizer --tool memcheck python tools/prof_case.py S scalar mat bloom --reps 1 > "$OUT/memcheck.log" 2>&1
