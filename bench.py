@@ -294,39 +294,38 @@ def main() -> None:
         d_bk, d_bv = capi.generate_g2("build", n_total, ny, pct, SEED, b0, nb_local)
         d_pk = capi.generate_g2("probe", n_total, ny, pct, SEED, p0, N)
 
-        # argument objects are made once: the timed loop is the C-ABI call and nothing else
-        n, nl, sec, st = C.c_uint64(0), C.c_uint64(0), C.c_double(0), capi.Stats()
-        p_n, p_nl, p_sec, p_st = C.byref(n), C.byref(nl), C.byref(sec), C.byref(st)
+        # argument objects are made once (one stats block per timed step): the timed loop is the C-ABI call and nothing else
+        n, nl, sec = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+        sts = [capi.Stats() for _ in range(max(steps, 1))]
+        p_n, p_nl, p_sec = C.byref(n), C.byref(nl), C.byref(sec)
+        p_sts = [C.byref(x) for x in sts]
         dflags = flags | capi.FLAG_DEVICE_INPUTS
         a_bk, a_bv, a_pk = d_bk.ptr, d_bv.ptr, d_pk.ptr
 
-        def step_device():
+        def step_device(i=0):
             if world == 1:
-                rc = L.fj_join_u64(algo, dflags, a_bk, a_bv, ny, a_pk, N, p_n, p_sec, p_st)
+                rc = L.fj_join_u64(algo, dflags, a_bk, a_bv, ny, a_pk, N, p_n, p_sec, p_sts[i])
             else:
-                rc = L.fj_join_dist_u64(mode, algo, dflags, 0, a_bk, a_bv, nb_local, a_pk, N, p_n, p_nl, p_sec, p_st)
+                rc = L.fj_join_dist_u64(mode, algo, dflags, 0, a_bk, a_bv, nb_local, a_pk, N, p_n, p_nl, p_sec, p_sts[i])
             if rc:
                 capi.check(rc)
-            return n.value, st
+            return n.value
 
         for _ in range(warmup):
-            matches, _ = step_device()
+            matches = step_device()
         barrier()
         capi.check(L.fj_timer_start())
-        launches = 0
-        dom_s = []
-        phases = {"clear_s": 0.0, "build_s": 0.0, "partition_s": 0.0, "probe_s": 0.0, "comm_s": 0.0}
-        for _ in range(steps):
-            matches, st = step_device()
-            launches += st.kernel_launches
-            dom_s.append(st.probe_s)
-            for k in phases:
-                phases[k] += getattr(st, k)
+        for i in range(steps):
+            matches = step_device(i)
         t = C.c_double(0)
         capi.check(L.fj_timer_stop(C.byref(t)))
         barrier()
         elapsed = max_over_ranks(t.value)
         value = n_total * steps / elapsed
+        launches = sum(x.kernel_launches for x in sts[:steps])
+        dom_s = [x.probe_s for x in sts[:steps]]
+        phases = {k: sum(getattr(x, k) for x in sts[:steps]) for k in ("clear_s", "build_s", "partition_s", "probe_s", "comm_s")}
+        st = sts[steps - 1]
         last = st.as_dict()
 
         # roofline of the dominant kernel (the probe / partition-join kernel of the step)
