@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 ROOT = PKG.parent
 OBJ = PKG / "_obj"
 LIB = PKG / "libflashjoin_b200.so"
-CU_SOURCES = ["fj_scalar.cu", "fj_radix.cu", "fj_engine.cu", "fj_dist.cu"]
+CU_SOURCES = ["fj_scalar.cu", "fj_radix.cu", "fj_part.cu", "fj_engine.cu", "fj_dist.cu"]
 HEADERS = ["fj_common.cuh", "fj_kernels.h", "fj_dist.h", "../../include/flashjoin_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

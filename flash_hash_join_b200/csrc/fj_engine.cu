@@ -170,6 +170,9 @@ struct Engine {
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
     cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
     cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
+    cfg["dense16"] = 1;             // radix path, dense key domain: one high-fan-out pass + shared-memory direct-address join (k_part / k_sjoin)
+    cfg["dense16_logp"] = 0;        // 0 = derive the partition count from the build size; else log2(partitions), 8..11
+    cfg["part_tma_store"] = 0;      // k_part: flush sectors with cp.async.bulk shared -> global instead of LDS + STG
     // FJ_CFG_<KEY>=<integer> in the environment overrides a default (e.g. FJ_CFG_DENSE=0)
     for (auto& kv : cfg) {
       std::string name = "FJ_CFG_";
@@ -193,6 +196,11 @@ struct Engine {
   fj_status attempt_dense(unsigned flags, const DensePlan& dp, const unsigned long long* bk, const unsigned long long* bv,
                           uint64_t nb, const unsigned long long* pk, uint64_t np, fj_stats* s);
   DevBuf direct;
+  // dense key domain, radix path, round 2: ONE partition pass (k_part) + shared-memory direct-address join (k_sjoin)
+  struct Dense16Plan { bool ok = false; int logp = 0; uint64_t klimit = 0; uint32_t slots = 0; uint64_t cap_b = 0, cap_p = 0; };
+  Dense16Plan plan_dense16(unsigned flags, uint64_t nb, uint64_t np) const;
+  fj_status attempt_dense16(unsigned flags, const Dense16Plan& dp, const unsigned long long* bk, const unsigned long long* bv,
+                            uint64_t nb, const unsigned long long* pk, uint64_t np, fj_stats* s);
   // dense key domain, count only: exact membership bitmap in shared memory instead of table + filter
   uint64_t dense_bitmap_bits(uint64_t nb) const;
   fj_status attempt_scalar_dense(unsigned flags, uint64_t dbits, const unsigned long long* bk, const unsigned long long* bv,
@@ -791,6 +799,96 @@ fj_status Engine::attempt_dense(unsigned flags, const DensePlan& dp, const unsig
   return FJ_OK;
 }
 
+// ---- one attempt on the dense-key-domain radix path, round 2 (k_part + k_sjoin) -------------------
+// Optimistic: every build key < klimit (<= 65528 direct-address slots per partition) and, for a materialize, every
+// build value <= 65534.  Partition count: enough that a partition's slice of the key domain fits the shared-memory
+// region of k_sjoin, and enough partitions to balance the SMs.
+static uint64_t round16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
+Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t np) const {
+  Dense16Plan dp;
+  if (!cfg.at("dense") || !cfg.at("dense16") || !cfg.at("narrow") || (flags & (FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX))) return dp;
+  if (nb < (uint64_t)std::max<int64_t>(cfg.at("dense_min_rows"), 1024) || np == 0) return dp;
+  const uint64_t maxslots = sjoin_max_slots(di);
+  const uint64_t need = nb + nb / 5 + 1024;  // h2o ids are 1..1.1*n
+  int logp = (int)cfg.at("dense16_logp");
+  if (logp <= 0) {
+    logp = nb >= (1ull << 23) ? 11 : (nb >= (1ull << 21) ? 10 : 9);
+    while (logp < 11 && (maxslots << logp) < need) ++logp;
+  }
+  if (logp < 8 || logp > 11 || (maxslots << logp) < need) return dp;
+  if (part_smem_bytes(logp) + 256 > di.smem_optin) return dp;
+  const uint64_t P = 1ull << logp;
+  uint64_t k = 1024;
+  while (k < 4 * nb) k <<= 1;
+  dp.klimit = std::min<uint64_t>(maxslots << logp, k);
+  dp.slots = (uint32_t)std::min<uint64_t>(maxslots, ((dp.klimit + P - 1) / P + 7) & ~uint64_t(7));
+  dp.logp = logp;
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
+  // every CTA of the pass leaves one (padded) sector per partition behind
+  dp.cap_b = round16(cap_build(nb, P) + ((uint64_t)part_grid(nb, di) + 2) * part_sector_elems(mat));
+  dp.cap_p = round16(cap_probe(np, P) + ((uint64_t)part_grid(np, di) + 2) * part_sector_elems(false));
+  if (dp.cap_b > 0xfffffff0ull || dp.cap_p > 0xfffffff0ull) return dp;
+  dp.ok = true;
+  return dp;
+}
+
+fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const unsigned long long* bk,
+                                  const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
+                                  fj_stats* s) {
+  const bool mat = flags & FJ_FLAG_MATERIALIZE;
+  const uint32_t P = 1u << dp.logp;
+  const size_t eb = mat ? 4 : 2;
+  FJ_TRY(part_a_b.ensure((size_t)P * dp.cap_b * eb));
+  FJ_TRY(part_a_p.ensure((size_t)P * dp.cap_p * 2));
+  FJ_TRY(cursors.ensure(2 * (size_t)P * 4));
+  uint32_t* cur_b = cursors.as<uint32_t>();
+  uint32_t* cur_p = cur_b + P;
+  Ctl* d_ctl = ctl.as<Ctl>();
+  int launches = 0;
+  FJ_CUDA(cudaEventRecord(ev[0], st));
+  launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * 4, di, st);
+  ++launches;
+  FJ_CUDA(cudaEventRecord(ev[1], st));
+  PartArgs a;
+  a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = a.lpo = dp.logp; a.world = 1; a.nsub = 1; a.sub = 0;
+  a.tma_store = cfg["part_tma_store"] != 0;
+  a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.outs[0] = part_a_b.p; a.strict = true;
+  bool launched = launch_part(mat, a, di, st, &launches);
+  a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.outs[0] = part_a_p.p; a.strict = false;
+  launched = launched && launch_part(false, a, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[2], st));
+  if (launched) {
+    SjoinArgs j;
+    j.build = part_a_b.p; j.bcnt = cur_b; j.cap_b = dp.cap_b;
+    j.probe = part_a_p.p; j.pcnt = cur_p; j.cap_p = dp.cap_p;
+    j.cnt_stride = 0; j.p_first = 0; j.p_count = P; j.logp = dp.logp; j.nsub = 1; j.slots_alloc = dp.slots;
+    j.ctl = d_ctl;
+    j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
+    j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
+    launched = launch_sjoin(mat, j, di, st, &launches);
+  }
+  FJ_CUDA(cudaEventRecord(ev[3], st));
+  if (launched) FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
+  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  FJ_CUDA(cudaGetLastError());
+  if (!launched) h_ctl->flags |= CTL_NOT_DENSE16;  // no launch configuration: the next layout answers
+  s->clear_s += ms(0, 1) * 1e-3;
+  s->partition_s += ms(1, 2) * 1e-3;
+  s->probe_s += ms(2, 3) * 1e-3;
+  s->device_s += ms(0, 3) * 1e-3;
+  s->kernel_launches += launches;
+  s->table_bytes = (uint64_t)P * (dp.cap_b * eb + dp.cap_p * 2);
+  s->path = FJ_ALGO_RADIX;
+  s->narrow = 1;
+  s->bloom_kind = 0;
+  s->dedup_exact = 0;
+  s->radix_bits1 = dp.logp;
+  s->radix_bits2 = 0;
+  s->dense = 2;
+  return FJ_OK;
+}
+
 fj_status Engine::finish_attempt(unsigned flags, fj_stats* s) {
   s->matches = h_ctl->match_count;
   if (flags & FJ_FLAG_MATERIALIZE) {
@@ -840,24 +938,33 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
       (!plan.ok && !((flags & FJ_FLAG_PROBE_IDX) && mat) &&
        (algo == FJ_ALGO_RADIX || (algo == FJ_ALGO_ADAPTIVE && (double)nb / ((double)cfg["load_pct"] / 100.0) * 8.0 >
                                                                  (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0)));
+  Dense16Plan d16;
   if (narrow && radix_wanted) {
+    d16 = plan_dense16(flags, nb, np);
     dplan = plan_dense(flags, nb, np);
-    if (dplan.ok && direct.ensure((size_t)djoin_fan() * dplan.rstride * 4) != FJ_OK) dplan.ok = false;  // no room: general path
   }
-  for (int attempt = 1; attempt <= 6; ++attempt) {
+  for (int attempt = 1; attempt <= 7; ++attempt) {
     s->attempts = attempt;
     s->dense = 0;
     if (path == FJ_ALGO_RADIX) {
       if (plan.narrow != narrow) plan = plan_radix(nb, np, narrow);
       if (!plan.ok) { path = FJ_ALGO_SCALAR; }
     }
-    const bool dense_radix = radix_wanted && narrow && dplan.ok;
+    const bool dense16 = radix_wanted && narrow && d16.ok;
+    // the L2-resident direct-address regions of the round-1 path are only allocated when that path is really taken
+    if (!dense16 && radix_wanted && narrow && dplan.ok && direct.ensure((size_t)djoin_fan() * dplan.rstride * 4) != FJ_OK) {
+      cudaGetLastError();
+      dplan.ok = false;  // no room: general path
+    }
+    const bool dense_radix = !dense16 && radix_wanted && narrow && dplan.ok;
     const bool dense_scalar = path == FJ_ALGO_SCALAR && narrow && !exact && dense_bits != 0;
-    if (dense_radix) FJ_TRY(attempt_dense(flags, dplan, bk, bv, nb, pk, np, s));
+    if (dense16) FJ_TRY(attempt_dense16(flags, d16, bk, bv, nb, pk, np, s));
+    else if (dense_radix) FJ_TRY(attempt_dense(flags, dplan, bk, bv, nb, pk, np, s));
     else if (dense_scalar) FJ_TRY(attempt_scalar_dense(flags, dense_bits, bk, bv, nb, pk, np, idx_base, s));
     else if (path == FJ_ALGO_RADIX) FJ_TRY(attempt_radix(flags, plan, bk, bv, nb, pk, np, s));
     else FJ_TRY(attempt_scalar(flags, narrow, exact, bk, bv, nb, pk, np, idx_base, s));
     const unsigned f = h_ctl->flags;
+    if (dense16 && (f & (CTL_NOT_DENSE16 | CTL_OVERFLOW))) { d16.ok = false; continue; }  // wider layouts answer
     if (f & CTL_NOT_DENSE) { dplan.ok = false; dense_bits = 0; continue; }
     if ((f & CTL_OVERFLOW) && dense_radix) { dplan.ok = false; continue; }  // skewed low key bits: hash partitioning instead
     if ((f & CTL_NEED_WIDE) && narrow) { narrow = false; continue; }
@@ -865,7 +972,7 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
     if ((f & CTL_DUP) && !exact) { exact = true; narrow = false; path = FJ_ALGO_SCALAR; continue; }
     return finish_attempt(flags, s);
   }
-  return set_err(FJ_ERR_STATE, "internal: join did not converge after 6 attempts (flags %u)", h_ctl->flags);
+  return set_err(FJ_ERR_STATE, "internal: join did not converge after 7 attempts (flags %u)", h_ctl->flags);
 }
 
 fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint64_t* bv, size_t nb, const uint64_t* pk,

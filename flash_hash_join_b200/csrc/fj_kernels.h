@@ -161,6 +161,49 @@ struct DjoinArgs {
 size_t djoin_sync_words();
 uint32_t djoin_fan();
 bool launch_djoin(bool mat, const DjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
+// dense key domain, round 2 (fj_part.cu): ONE partition pass by the low `logp` key bits with per-SM write-combining
+// sector buffers (k_part), rows reduced to idx = key >> logp (build: idx | value << 16, 4 bytes; probe: idx, 2 bytes),
+// then a direct-address join whose region lives in shared memory (k_sjoin).  The same kernels serve the multi-GPU
+// shuffle: a partition's owner GPU is d >> lpo, `outs[owner]` its (peer-mapped) partition buffer, and every source
+// writes its own sub-region, so no cursor is shared between GPUs.
+struct PartArgs {
+  const unsigned long long* in_keys = nullptr;
+  const unsigned long long* in_vals = nullptr;  // val == true only
+  uint64_t n = 0;
+  uint64_t klimit = 0;   // keys >= klimit are outside the domain (strict: CTL_NOT_DENSE16; else the row is dropped)
+  uint64_t cap = 0;      // elements per (partition, sub-region), multiple of 16
+  uint32_t* cursor = nullptr;  // [2^logp], zeroed: elements reserved per partition by THIS source
+  Ctl* ctl = nullptr;
+  void* outs[8] = {};    // [world] base of every owner's partition buffer
+  int world = 1;
+  int logp = 11, lpo = 11;  // log2(partitions), log2(partitions per owner)
+  int nsub = 1, sub = 0;    // sub-regions per partition (= sources), this source's index
+  bool strict = false;
+  bool tma_store = false;   // sectors leave with cp.async.bulk shared -> global instead of LDS + STG
+};
+size_t part_smem_bytes(int logp);
+uint32_t part_sector_elems(bool val);
+uint32_t part_grid(uint64_t n, const DeviceInfo& di);
+bool launch_part(bool val, const PartArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
+struct SjoinArgs {
+  const void* build = nullptr;     // regions [(l * nsub + sub) * cap_b, +bcnt): mat: 4-byte idx | value << 16; count: 2-byte idx
+  const uint32_t* bcnt = nullptr;  // bcnt[sub * cnt_stride + p]
+  uint64_t cap_b = 0;
+  const void* probe = nullptr;     // 2-byte idx
+  const uint32_t* pcnt = nullptr;
+  uint64_t cap_p = 0;
+  uint32_t cnt_stride = 0;
+  uint32_t p_first = 0, p_count = 0;  // global ids of the partitions joined by this GPU
+  int logp = 11, nsub = 1;
+  uint32_t slots_alloc = 0;           // shared-memory direct-address slots (>= klimit >> logp), multiple of 8, <= sjoin_max_slots
+  Ctl* ctl = nullptr;                 // Ctl::max_key = largest build key over ALL sources
+  unsigned long long* out_keys = nullptr;
+  unsigned long long* out_vals = nullptr;
+};
+size_t sjoin_smem_bytes(uint32_t slots_alloc);
+uint32_t sjoin_max_slots(const DeviceInfo& di);
+bool launch_sjoin(bool mat, const SjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
+
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
                           unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);
 

@@ -25,6 +25,7 @@ CONFIGS = {
     "C4": (1_000_000_000, 1_000_000, 90),
     "C5": (1_000_000_000, 1_000_000_000, 90),
     "C4s": (125_000_000, 1_000_000, 90),  # shape of one GPU's share of C4 on 8 GPUs (probe split, build replicated)
+    "T": (200_000, 150_000, 90),  # tiny radix-shaped case for compute-sanitizer racecheck
     "S": (2_000_000, 1_500_000, 90),  # small radix-shaped case for sanitizer / sanity runs (not a BASELINE config)
 }
 

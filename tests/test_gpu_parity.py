@@ -435,9 +435,11 @@ def test_dense_direct_materialize(fj):
 
 @pytest.fixture()
 def dense_small(fj):
-    fj.configure(dense_min_rows=1024)
+    """The round-1 dense radix path (k_scatter2 by the low 8 key bits + L2-resident k_djoin); the round-2 path
+    (k_part + k_sjoin) is switched off here and has its own tests below."""
+    fj.configure(dense_min_rows=1024, dense16=0)
     yield fj
-    fj.configure(dense_min_rows=1 << 20, dense_group_mb=8, dense_ring=4, dense_batch=2, dense_delay_b=1, dense_delay_p=3, dense=1)
+    fj.configure(dense_min_rows=1 << 20, dense_group_mb=8, dense_ring=4, dense_batch=2, dense_delay_b=1, dense_delay_p=3, dense=1, dense16=1)
 
 
 @pytest.mark.parametrize("group_mb,ring,batch,delay_b,delay_p", [(8, 4, 2, 1, 3), (1, 4, 2, 1, 3), (1, 1, 1, 1, 1), (1, 16, 8, 2, 4),
@@ -505,6 +507,106 @@ def test_dense_radix_edges(dense_small):
     # all probe rows carry one key
     bk7 = np.arange(1, 50_001, dtype=np.uint64)
     check_all_entry_points(fj, bk7, bk7 * np.uint64(7), np.full(600_000, 4242, dtype=np.uint64), algos=("radix",))
+
+
+# ------------------------------------------------------------------------------------------------ dense key domain, round 2
+@pytest.fixture()
+def dense16_small(fj):
+    fj.configure(dense_min_rows=1024, dense16=1, dense16_logp=0, part_tma_store=0)
+    yield fj
+    fj.configure(dense_min_rows=1 << 20, dense16=1, dense16_logp=0, part_tma_store=0, dense=1)
+
+
+@pytest.mark.parametrize("logp,tma_store", [(0, 0), (8, 0), (11, 0), (0, 1), (11, 1)])
+def test_dense16_partition_join(dense16_small, logp, tma_store):
+    """Radix entry points on a dense key domain, round 2: ONE partition pass by the low key bits with per-SM
+    write-combining sector buffers (k_part; rows shrink to idx16 | value16 and idx16) + the direct-address join in
+    shared memory (k_sjoin).  The partition count and the way sectors leave shared memory (LDS + STG or TMA bulk
+    store) must not change the result."""
+    fj = dense16_small
+    fj.configure(dense16_logp=logp, part_tma_store=tma_store)
+    for N, ny, pct in ((400_000, 300_000, 90), (3_000_000, 2_000_000, 90), (1_000_000, 70_000, 10), (5_001, 2_049, 50)):
+        bk, bv, pk = g1(N, ny, pct)
+        expect = O.np_join(bk, bv, pk)
+        check_all_entry_points(fj, bk, bv, pk, expect=expect, algos=("radix",))
+        st = fj.last_stats()
+        assert st["dense"] == 2 and st["path"] == "radix" and st["attempts"] == 1 and st["radix_bits"][1] == 0, st
+        if logp:
+            assert st["radix_bits"] == (logp, 0), st
+
+
+def test_dense16_edges(dense16_small):
+    fj = dense16_small
+    rng = np.random.default_rng(12)
+    # key 0, the largest value the 16-bit slot holds, probe keys beyond the domain and beyond 32 bits
+    bk = rng.permutation(60_000).astype(np.uint64)
+    bv = rng.integers(0, 65535, bk.size).astype(np.uint64)
+    bv[:3] = (0, 65534, 65533)
+    pk = np.concatenate([rng.integers(0, 140_000, 500_000).astype(np.uint64),
+                         np.array([2**17 - 1, 2**17, 2**27, 2**31, 2**32 - 1, 2**32, 2**63, 2**64 - 1], dtype=np.uint64)])
+    check_all_entry_points(fj, bk, bv, pk, algos=("radix",))
+    assert fj.last_stats()["dense"] == 2
+    # a value that does not fit 16 bits (value + 1 is stored): the round-1 layout (32-bit values) answers
+    bv2 = bv.copy(); bv2[100] = 65535
+    check_all_entry_points(fj, bk, bv2, pk, algos=("radix",))
+    st = fj.last_stats()
+    assert st["dense"] == 1 and st["attempts"] == 2, st
+    n, _ = fj.hash_join_count_radix(bk, bv2, pk)  # a count never reads the values
+    assert n == O.np_join(bk, bv2, pk)[0] and fj.last_stats()["dense"] == 2
+    # a build key outside the optimistic domain
+    bk3 = bk.copy(); bk3[5] = 2**30
+    check_all_entry_points(fj, bk3, bv, pk, algos=("radix",))
+    assert fj.last_stats()["dense"] == 0
+    # duplicate build keys: the slot is already taken -> exact keep-first path (materialize); a count is a set operation
+    bk5 = rng.integers(0, 50_000, 120_000).astype(np.uint64)
+    bv5 = np.arange(bk5.size, dtype=np.uint64) % np.uint64(60_000)
+    pk5 = rng.integers(0, 60_000, 300_000).astype(np.uint64)
+    n0, k0, v0 = O.join("radix", False, True, bk5, bv5, pk5)
+    n, _ = fj.hash_join_radix(bk5, bv5, pk5)
+    assert n == n0 and fj.last_stats()["dedup_exact"] is True
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(k0, v0))
+    n, _ = fj.hash_join_count_radix(bk5, bv5, pk5)
+    assert n == n0 and fj.last_stats()["dense"] == 2
+    # skewed low key bits (only 100 of 512 residues occur): those partitions overflow their regions -> other layouts
+    allk = np.arange(262_144, dtype=np.uint64)
+    bk6 = rng.permutation(allk[(allk & np.uint64(511)) < 100])[:50_000]
+    pk6 = rng.choice(allk, 400_000)
+    check_all_entry_points(fj, bk6, bk6 % np.uint64(999), pk6, algos=("radix",))
+    assert fj.last_stats()["dense"] != 2
+    # all probe rows carry one key: one partition's ring fills again and again within a round (retry iterations)
+    bk7 = np.arange(1, 50_001, dtype=np.uint64)
+    check_all_entry_points(fj, bk7, bk7 % np.uint64(65_000), np.full(600_000, 4242, dtype=np.uint64), algos=("radix",))
+    # empty intersection; build side of one partition only
+    check_all_entry_points(fj, bk7, bk7 % np.uint64(7), bk7 + np.uint64(100_000), algos=("radix",))
+    bk8 = (np.arange(3_000, dtype=np.uint64) << np.uint64(9)) + np.uint64(5)
+    check_all_entry_points(fj, bk8, bk8 % np.uint64(11), rng.integers(0, 3_000 << 9, 100_000).astype(np.uint64), algos=("radix",))
+
+
+def test_dense16_ragged_and_unaligned(capi):
+    """C ABI, device-resident inputs whose base is only 8-byte aligned and whose lengths are not multiples of the
+    2048-row round: the TMA key ring needs 16-byte alignment, so these rounds take the direct-load path."""
+    capi.config_set(dense_min_rows=1024, dense16=1)
+    try:
+        for N, ny in ((10_001, 4_097), (300_001, 200_003), (2_047, 1_025)):
+            bk, bv, pk = g1(N, ny, 90)
+            n0, k0, v0 = O.np_join(bk, bv, pk)
+            big = [capi.DeviceArray.from_host(np.concatenate([[np.uint64(7)], x])) for x in (bk, bv, pk)]
+            views = []
+            for d, x in zip(big, (bk, bv, pk)):
+                v = capi.DeviceArray.__new__(capi.DeviceArray)
+                v.n, v.ptr = x.size, d.ptr + 8
+                views.append(v)
+            for flags in (0, capi.FLAG_MATERIALIZE):
+                n, _, st = capi.join(capi.ALGO_RADIX, flags, *views)
+                assert n == n0 and st["dense"] == 2, (N, ny, flags, n, n0, st)
+                if flags:
+                    assert np.array_equal(O.sorted_pairs(*capi.pairs()), O.sorted_pairs(k0, v0))
+            for v in views:
+                v.ptr = None  # borrowed
+            for d in big:
+                d.free()
+    finally:
+        capi.config_set(dense_min_rows=1 << 20)
 
 
 # ------------------------------------------------------------------------------------------------ full sizes

@@ -10,7 +10,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from flash_hash_join_b200 import capi  # noqa: E402
 from flash_hash_join_b200.datagen import CONFIGS  # noqa: E402
 
-PEAK = 6542.1  # GB/s, MEASURED_PEAKS.json
+PEAK = 6468.3  # GB/s, MEASURED_PEAKS.json
 
 
 def run(name, algo, flags, d, reps, N, cfg=None):
@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["C2", "C3"])
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--full", action="store_true", help="also the slower alternative paths of the large-build configs")
     a = ap.parse_args()
     S, R, A = capi.ALGO_SCALAR, capi.ALGO_RADIX, capi.ALGO_ADAPTIVE
     B, M, W = capi.FLAG_BLOOM, capi.FLAG_MATERIALIZE, capi.FLAG_FORCE_WIDE
@@ -63,10 +64,23 @@ def main():
             run(f"{c} adaptive count", A, 0, d, a.reps, N)
             capi.config_set(dense=1)
         else:
-            run(f"{c} radix mat (dense, direct-address)", R, M, d, a.reps, N)
-            run(f"{c} radix count (dense, direct-address)", R, 0, d, a.reps, N)
-            run(f"{c} adaptive mat (dense)", A, M, d, a.reps, N)
+            run(f"{c} radix mat (dense16: k_part + k_sjoin)", R, M, d, a.reps, N)
+            run(f"{c} radix count (dense16)", R, 0, d, a.reps, N)
+            run(f"{c} radix mat (dense16, TMA bulk stores)", R, M, d, a.reps, N, {"part_tma_store": 1})
+            run(f"{c} radix count (dense16, TMA bulk stores)", R, 0, d, a.reps, N)
+            capi.config_set(part_tma_store=0)
+            run(f"{c} adaptive mat (dense16)", A, M, d, a.reps, N)
+            if a.full:
+                run(f"{c} radix mat (dense, L2 direct-address k_djoin)", R, M, d, a.reps, N, {"dense16": 0})
+                run(f"{c} radix count (dense, L2 direct-address k_djoin)", R, 0, d, a.reps, N)
+                capi.config_set(dense16=1)
             capi.config_set(dense=0)
+            if not a.full:
+                run(f"{c} radix mat", R, M, d, a.reps, N)
+                capi.config_set(dense=1)
+                for x in d:
+                    x.free()
+                continue
             run(f"{c} radix mat", R, M, d, a.reps, N)
             run(f"{c} radix count", R, 0, d, a.reps, N)
             run(f"{c} radix mat 2^16 parts", R, M, d, a.reps, N, {"radix_sub_rows": 2400})
