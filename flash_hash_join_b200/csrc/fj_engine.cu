@@ -825,8 +825,8 @@ Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t n
   dp.logp = logp;
   const bool mat = flags & FJ_FLAG_MATERIALIZE;
   // every CTA of the pass leaves one (padded) sector per partition behind
-  dp.cap_b = round16(cap_build(nb, P) + ((uint64_t)part_grid(nb, di) + 2) * part_sector_elems(mat));
-  dp.cap_p = round16(cap_probe(np, P) + ((uint64_t)part_grid(np, di) + 2) * part_sector_elems(false));
+  dp.cap_b = round16(cap_build(nb, P) + ((uint64_t)part_grid(mat, nb, di) + 2) * part_sector_elems(mat));
+  dp.cap_p = round16(cap_probe(np, P) + ((uint64_t)part_grid(false, np, di) + 2) * part_sector_elems(false));
   if (dp.cap_b > 0xfffffff0ull || dp.cap_p > 0xfffffff0ull) return dp;
   dp.ok = true;
   return dp;

@@ -183,7 +183,7 @@ struct PartArgs {
 };
 size_t part_smem_bytes(int logp);
 uint32_t part_sector_elems(bool val);
-uint32_t part_grid(uint64_t n, const DeviceInfo& di);
+uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di);
 bool launch_part(bool val, const PartArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 struct SjoinArgs {
   const void* build = nullptr;     // regions [(l * nsub + sub) * cap_b, +bcnt): mat: 4-byte idx | value << 16; count: 2-byte idx
@@ -196,7 +196,7 @@ struct SjoinArgs {
   uint32_t p_first = 0, p_count = 0;  // global ids of the partitions joined by this GPU
   int logp = 11, nsub = 1;
   uint32_t slots_alloc = 0;           // shared-memory direct-address slots (>= klimit >> logp), multiple of 8, <= sjoin_max_slots
-  Ctl* ctl = nullptr;                 // Ctl::max_key = largest build key over ALL sources
+  Ctl* ctl = nullptr;
   unsigned long long* out_keys = nullptr;
   unsigned long long* out_vals = nullptr;
 };

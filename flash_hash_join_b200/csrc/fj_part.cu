@@ -46,9 +46,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // ================================================================================= k_part
 constexpr int PT_THREADS = 1024;
-constexpr int PT_IPT = 2;
-constexpr int PT_ROWS = PT_THREADS * PT_IPT;  // rows per round
-constexpr int PT_STAGES = 4;                  // key ring: 4 x 16 KB
+constexpr int PT_STAGE_BYTES = 16384;         // one ring stage: 2048 keys, or 1024 keys + 1024 values
+constexpr int PT_STAGES = 5;
+constexpr int PT_RS = 2;                      // ring stages per round
 constexpr int PT_SECTOR = 32;                 // bytes per flush
 constexpr int PT_RINGB = 2 * PT_SECTOR;       // bytes of staging per partition
 constexpr int PT_MAXP = 2048;
@@ -58,77 +58,98 @@ struct PartParams {
   const unsigned long long* in_keys;
   const unsigned long long* in_vals;
   uint64_t n;
-  uint64_t klimit;     // keys >= klimit are outside the domain
-  uint64_t cap;        // elements per (partition, sub-region); multiple of 16
+  uint32_t klimit;     // keys >= klimit are outside the domain (klimit <= 2^32 - 1)
+  uint32_t cap;        // elements per (partition, sub-region); multiple of 16
   uint32_t* cursor;    // [P] elements reserved per partition (this source)
   Ctl* ctl;
   void* outs[PT_MAXW]; // base of every owner's partition buffer (peer-mapped for remote owners)
   int logp;            // log2(partitions)
   int lpo;             // log2(partitions per owner)
   int nsub, sub;       // sub-regions per partition on the owner (= sources) and this source's index
-  int strict;          // build side: a key >= klimit (or a value > 65534) raises CTL_NOT_DENSE16
-  int tma_store;       // flush sectors with cp.async.bulk shared -> global instead of LDS/STG
 };
 
-template <bool VAL>
+// VAL: rows carry a value (element = idx | value << 16, 4 bytes) else keys only (element = idx, 2 bytes)
+// STRICT: build side — a key >= klimit or a value > 65534 abandons the attempt (CTL_NOT_DENSE16); else such rows are dropped
+// TMAST: sectors leave shared memory with cp.async.bulk shared -> global instead of LDS.128 + STG.128
+template <bool VAL, bool STRICT, bool TMAST>
 __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   using ET = std::conditional_t<VAL, uint32_t, uint16_t>;
-  constexpr uint32_t EPS = PT_SECTOR / sizeof(ET);  // elements per sector: 8 | 16
+  constexpr uint32_t ES = sizeof(ET);
+  constexpr uint32_t EPS = PT_SECTOR / ES;            // elements per sector: 8 | 16
+  constexpr uint32_t LOG_EPS = VAL ? 3 : 4;
   constexpr uint32_t SLOTS = 2 * EPS;
+  constexpr uint32_t SROWS = VAL ? 1024 : 2048;       // rows per ring stage
+  constexpr uint32_t ROUND = PT_RS * SROWS;           // rows per round: 2048 | 4096
+  constexpr int IPT = ROUND / PT_THREADS;             // rows per thread and round: 2 | 4
   constexpr ET HOLE = (ET)~(ET)0;
+  constexpr uint32_t NOPLACE = 0xFFFFu;               // nextg: the reservation lies beyond the region
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = 1u << a.logp;
-  unsigned char* buf = smem;                                             // P x 64 B
+  unsigned char* buf = smem;                                               // P x 64 B: two sectors per partition
   uint32_t* w = reinterpret_cast<uint32_t*>(smem + (size_t)P * PT_RINGB);  // P: elements in the ring << 1 | first sector
-  uint32_t* nextg = w + P;                                               // P: element offset reserved for the next flush
-  uint16_t* list = reinterpret_cast<uint16_t*>(nextg + P);               // P: partitions with a complete sector
-  unsigned long long* ring = reinterpret_cast<unsigned long long*>(smem + (size_t)P * (PT_RINGB + 10));  // key ring
+  uint16_t* nextg = reinterpret_cast<uint16_t*>(w + P);                    // P: sector (in the sub-region) reserved for the next flush
+  uint16_t* list = nextg + P;                                              // P: partitions with a complete sector
+  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 8);                 // PT_STAGES x 16 KB
   __shared__ __align__(8) uint64_t s_full[PT_STAGES];
   __shared__ uint32_t s_ln[2];
   __shared__ unsigned char* s_outs[PT_MAXW];
 
-  const int tid = threadIdx.x;
-  const uint64_t rounds = (a.n + PT_ROWS - 1) / PT_ROWS;
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.in_keys) & 15u) == 0;
+  const uint32_t tid = threadIdx.x;
   const uint32_t G = gridDim.x;
+  const uint32_t rounds = (uint32_t)((a.n + ROUND - 1) / ROUND);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a.in_keys) | (VAL ? reinterpret_cast<uintptr_t>(a.in_vals) : 0)) & 15u) == 0;
+  const uint32_t nfull = aligned ? (uint32_t)(a.n / ROUND) : 0u;  // rounds below nfull arrive through the TMA ring
   const uint32_t lpo_mask = (1u << a.lpo) - 1u;
+  const uint32_t capsec = a.cap >> LOG_EPS;
+  const uint32_t pmask = P - 1u;
 
-  if (tid < PT_MAXW) s_outs[tid] = static_cast<unsigned char*>(a.outs[tid]);
   if (tid < 2) s_ln[tid] = 0;
   if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < PT_MAXW; ++i) s_outs[i] = static_cast<unsigned char*>(a.outs[i]);  // static indices: no local copy
 #pragma unroll
     for (int s = 0; s < PT_STAGES; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
+  // reservation -> sector index inside the (partition, source) sub-region; NOPLACE when it does not fit
+  auto to_sector = [&](uint32_t g) -> uint16_t { return g + EPS <= a.cap ? (uint16_t)(g >> LOG_EPS) : (uint16_t)NOPLACE; };
   // every (CTA, partition) holds one sector reserved in advance
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
     w[d] = 0;
-    nextg[d] = atomicAdd(a.cursor + d, EPS);
+    nextg[d] = to_sector(atomicAdd(a.cursor + d, EPS));
   }
   __syncthreads();
 
-  auto tma_round = [&](uint64_t R) { return aligned && (R + 1) * (uint64_t)PT_ROWS <= a.n; };
-  auto issue = [&](uint64_t R, int s) {  // thread 0
-    if (R < rounds && tma_round(R)) {
-      mbar_expect_tx(&s_full[s], PT_ROWS * 8u);
-      bulk_g2s(ring + (size_t)s * PT_ROWS, a.in_keys + R * PT_ROWS, PT_ROWS * 8u, &s_full[s]);
+  // local ring stage c (c = 0, 1, 2, ... in consumption order) <-> round blockIdx + (c / RS) * G, stage c % RS of it
+  auto issue = [&](uint32_t c) {  // thread 0
+    const uint32_t R = blockIdx.x + (c / PT_RS) * G;
+    if (R >= nfull) return;
+    const int s = c % PT_STAGES;
+    const uint64_t row0 = (uint64_t)R * ROUND + (uint64_t)(c % PT_RS) * SROWS;
+    unsigned char* dst = ring + (size_t)s * PT_STAGE_BYTES;
+    mbar_expect_tx(&s_full[s], PT_STAGE_BYTES);
+    if constexpr (VAL) {
+      bulk_g2s(dst, a.in_keys + row0, SROWS * 8u, &s_full[s]);
+      bulk_g2s(dst + SROWS * 8u, a.in_vals + row0, SROWS * 8u, &s_full[s]);
+    } else {
+      bulk_g2s(dst, a.in_keys + row0, SROWS * 8u, &s_full[s]);
     }
   };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < PT_STAGES; ++s) issue(blockIdx.x + (uint64_t)s * G, s);
+    for (uint32_t c = 0; c < PT_STAGES; ++c) issue(c);
   }
 
-  // one 32-byte sector of partition d: shared memory -> its reserved place in the owner's buffer
-  auto store_sector = [&](uint32_t d, uint32_t sec, uint32_t g) {
-    if ((uint64_t)g + EPS > a.cap) {
+  // one 32-byte sector of partition d: shared memory -> sector gs of its sub-region in the owner's buffer
+  auto store_sector = [&](uint32_t d, uint32_t sec, uint32_t gs) {
+    if (gs == NOPLACE) {
       atomicOr(&a.ctl->flags, CTL_OVERFLOW);
       return;
     }
-    const unsigned char* src = buf + (size_t)d * PT_RINGB + sec * PT_SECTOR;
-    const uint64_t region = (uint64_t)(d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
-    unsigned char* dst = s_outs[d >> a.lpo] + (region * a.cap + g) * sizeof(ET);
-    if (a.tma_store) {
+    const unsigned char* src = buf + d * PT_RINGB + sec * PT_SECTOR;
+    const uint32_t region = (d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
+    unsigned char* dst = s_outs[d >> a.lpo] + (((uint64_t)region * capsec + gs) << 5);
+    if constexpr (TMAST) {
       bulk_s2g(dst, src, PT_SECTOR);
     } else {
       const uint4 x = reinterpret_cast<const uint4*>(src)[0], y = reinterpret_cast<const uint4*>(src)[1];
@@ -137,169 +158,198 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     }
   };
 
-  unsigned long long vcur[PT_IPT], vnxt[PT_IPT];
-  auto load_vals = [&](uint64_t R, unsigned long long(&v)[PT_IPT]) {
+  struct Rows {
+    uint32_t d[IPT];
+    uint32_t e[IPT];
+    uint32_t pend;
+  };
+  bool bad = false;
+  // the rows of round R (local round k): digit, element, validity
+  auto load_round = [&](uint32_t R, uint32_t k, Rows& r) {
+    r.pend = 0;
+    const bool tma = R < nfull;
+    if (tma) {
 #pragma unroll
-    for (int i = 0; i < PT_IPT; ++i) {
-      const uint64_t row = R * PT_ROWS + (uint64_t)i * PT_THREADS + tid;
-      v[i] = (VAL && row < a.n) ? ld_stream1(a.in_vals + row) : 0ull;
+      for (int j = 0; j < PT_RS; ++j) {
+        const uint32_t c = k * PT_RS + j;
+        mbar_wait_bounded(&s_full[c % PT_STAGES], (c / PT_STAGES) & 1u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      // TMA rounds: stage j = i / (IPT / RS), row (i % (IPT / RS)) * 1024 + tid of it
+      constexpr int PER = IPT / PT_RS;
+      const uint32_t c = k * PT_RS + i / PER;
+      const uint32_t sr = (i % PER) * PT_THREADS + tid;
+      uint2 kk, vv = make_uint2(0u, 0u);
+      bool ok = true;
+      if (tma) {
+        const unsigned char* st = ring + (size_t)(c % PT_STAGES) * PT_STAGE_BYTES;
+        kk = reinterpret_cast<const uint2*>(st)[sr];
+        if constexpr (VAL) vv = reinterpret_cast<const uint2*>(st + SROWS * 8u)[sr];
+      } else {
+        const uint64_t row = (uint64_t)R * ROUND + (uint64_t)i * PT_THREADS + tid;
+        ok = row < a.n;
+        unsigned long long k64 = ~0ull, v64 = 0;
+        if (ok) {
+          k64 = ld_stream1(a.in_keys + row);
+          if constexpr (VAL) v64 = ld_stream1(a.in_vals + row);
+        }
+        kk = make_uint2((uint32_t)k64, (uint32_t)(k64 >> 32));
+        vv = make_uint2((uint32_t)v64, (uint32_t)(v64 >> 32));
+      }
+      bool in = (kk.y == 0u) & (kk.x < a.klimit);
+      if constexpr (VAL) in &= (vv.y == 0u) & (vv.x <= 65534u);
+      if constexpr (STRICT) bad |= ok & !in;
+      ok &= in;
+      r.d[i] = kk.x & pmask;
+      r.e[i] = (kk.x >> a.logp) | (VAL ? vv.x << 16 : 0u);
+      r.pend |= ok ? (1u << i) : 0u;
     }
   };
-  if (VAL && blockIdx.x < rounds) load_vals(blockIdx.x, vcur);
 
-  uint32_t pd[2] = {0, 0}, pg[2] = {0, 0};  // reservations in flight: partition, reserved offset
+  uint32_t pd[2] = {0, 0}, pg[2] = {0, 0};  // reservations in flight: partition, reserved element offset
   uint32_t pvalid = 0;
-  uint32_t kmax = 0;
-  bool bad = false;
   uint32_t it = 0;  // place/flush iterations so far (selects the flush list counter)
+
+  // ---- place: one shared-memory atomic hands out the slot; a row that finds the ring full stays pending
+  auto place = [&](Rows& r, uint32_t par) {
+    uint32_t old[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+      if ((r.pend >> i) & 1u) old[i] = atomicAdd(&w[r.d[i]], 2u);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if ((r.pend >> i) & 1u) {
+        const uint32_t cnt = old[i] >> 1;
+        if (cnt < SLOTS) {
+          const uint32_t slot = (cnt + ((old[i] & 1u) << LOG_EPS)) & (SLOTS - 1u);
+          reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + slot] = (ET)r.e[i];
+          if (cnt == EPS - 1u) list[atomicAdd(&s_ln[par], 1u)] = (uint16_t)r.d[i];  // first sector complete
+          r.pend &= ~(1u << i);
+        }
+      }
+    }
+    // the reservations issued in the previous flush phase have returned by now: publish them
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
+    pvalid = 0;
+    if constexpr (TMAST) fence_proxy_async();  // staged rows become visible to the bulk-copy engine
+  };
+  // ---- flush the listed partitions: full sectors, each to the place reserved for it
+  auto flush = [&](uint32_t par) {
+    const uint32_t nl = s_ln[par];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t j = tid + (uint32_t)q * PT_THREADS;
+      if (j < nl) {
+        const uint32_t d = list[j];
+        const uint32_t ww = w[d];
+        const uint32_t gs = nextg[d];
+        pg[q] = atomicAdd(a.cursor + d, EPS);  // place of this partition's NEXT flush (consumed an iteration later)
+        pd[q] = d;
+        pvalid |= 1u << q;
+        uint32_t cnt = ww >> 1;
+        if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
+        const uint32_t tog = ww & 1u;
+        const uint32_t nsec = cnt >> LOG_EPS;  // 1 or 2
+        store_sector(d, tog, gs);
+        if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d, EPS)));  // rare: both sectors filled at once
+        w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
+      }
+    }
+    if constexpr (TMAST) {
+      bulk_commit();
+      bulk_wait_read0();  // the sectors have been read: their slots may be overwritten
+    }
+  };
+
+  Rows cur, nxt;
   uint32_t k = 0;
-  for (uint64_t R = blockIdx.x; R < rounds; R += G, ++k) {
-    const int s = k % PT_STAGES;
-    const bool tma = tma_round(R);
-    if (VAL && R + G < rounds) load_vals(R + G, vnxt);
-    if (tma) mbar_wait_bounded(&s_full[s], (k / PT_STAGES) & 1u);
-
-    uint32_t dd[PT_IPT];
-    ET ee[PT_IPT];
-    uint32_t pend = 0;
-#pragma unroll
-    for (int i = 0; i < PT_IPT; ++i) {
-      const uint64_t row = R * PT_ROWS + (uint64_t)i * PT_THREADS + tid;
-      bool ok = row < a.n;
-      unsigned long long key;
-      if (tma) key = ring[(size_t)s * PT_ROWS + i * PT_THREADS + tid];
-      else key = ok ? ld_stream1(a.in_keys + row) : ~0ull;
-      const bool in = key < a.klimit;
-      bad |= (a.strict != 0) & ok & !in;
-      ok &= in;
-      uint32_t e = (uint32_t)(key >> a.logp);
-      if constexpr (VAL) {
-        const bool vok = vcur[i] <= 65534ull;
-        bad |= ok & !vok;
-        ok &= vok;
-        e |= (uint32_t)vcur[i] << 16;
-      }
-      kmax = max(kmax, ok ? (uint32_t)key : 0u);
-      dd[i] = (uint32_t)key & (P - 1u);
-      ee[i] = (ET)e;
-      pend |= ok ? (1u << i) : 0u;
+  uint32_t R = blockIdx.x;
+  if (R < rounds) load_round(R, 0, cur);
+  while (R < rounds) {
+    const uint32_t par = it & 1u;
+    place(cur, par);
+    __syncthreads();  // #1: every row of this iteration is staged
+    if (tid == 0) {
+      // the ring stages of THIS round were read before the previous barrier #2: refill them
+      issue(k * PT_RS + PT_STAGES);
+      issue(k * PT_RS + 1 + PT_STAGES);
+      s_ln[par ^ 1u] = 0;
     }
-
-    bool first = true;
-    for (;;) {
-      const uint32_t par = it & 1u;
-      // ---- place: one shared-memory atomic hands out the slot; rows that find the ring full wait for the flush
-#pragma unroll
-      for (int i = 0; i < PT_IPT; ++i) {
-        if ((pend >> i) & 1u) {
-          const uint32_t old = atomicAdd(&w[dd[i]], 2u);
-          const uint32_t cnt = old >> 1;
-          if (cnt < SLOTS) {
-            const uint32_t slot = ((old & 1u) * EPS + cnt) & (SLOTS - 1u);
-            reinterpret_cast<ET*>(buf)[(size_t)dd[i] * SLOTS + slot] = ee[i];
-            if (cnt == EPS - 1u) list[atomicAdd(&s_ln[par], 1u)] = (uint16_t)dd[i];  // first sector complete
-            pend &= ~(1u << i);
-          }
-        }
-      }
-      // the reservations issued in the previous flush phase have returned by now: publish them
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        if ((pvalid >> q) & 1u) nextg[pd[q]] = pg[q];
-      pvalid = 0;
-      if (a.tma_store) fence_proxy_async();  // staged rows become visible to the bulk-copy engine
-      __syncthreads();  // #1: every row of this iteration is staged; ring stage s has been read
-      if (tid == 0) {
-        if (first) issue(R + (uint64_t)PT_STAGES * G, s);
-        s_ln[par ^ 1u] = 0;
-      }
-      // ---- flush the listed partitions: full sectors, each to the place reserved for it
-      const uint32_t nl = s_ln[par];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint32_t j = (uint32_t)tid + (uint32_t)q * PT_THREADS;
-        if (j < nl) {
-          const uint32_t d = list[j];
-          const uint32_t ww = w[d];
-          uint32_t cnt = ww >> 1;
-          if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
-          const uint32_t tog = ww & 1u;
-          const uint32_t nsec = cnt / EPS;  // 1 or 2
-          const uint32_t g0 = nextg[d];
-          uint32_t g1 = 0;
-          if (nsec == 2) g1 = atomicAdd(a.cursor + d, EPS);  // rare: both sectors filled within one iteration
-          pg[q] = atomicAdd(a.cursor + d, EPS);              // place of this partition's NEXT flush
-          pd[q] = d;
-          pvalid |= 1u << q;
-          store_sector(d, tog, g0);
-          if (nsec == 2) store_sector(d, tog ^ 1u, g1);
-          w[d] = ((cnt - nsec * EPS) << 1) | ((tog + nsec) & 1u);
-        }
-      }
-      if (a.tma_store) {
-        bulk_commit();
-        bulk_wait_read0();  // the sectors have been read: their slots may be overwritten
-      }
-      const int any = __syncthreads_or(pend != 0);  // #2
+    flush(par);
+    // the rows of the next round are fetched and decoded while the few flushing warps are busy
+    const uint32_t Rn = R + G;
+    if (Rn < rounds) load_round(Rn, k + 1, nxt);
+    int any = __syncthreads_or(cur.pend != 0);  // #2
+    ++it;
+    while (any) {  // some ring was full (more than a ring's worth of rows for one partition within a round): retry
+      const uint32_t par2 = it & 1u;
+      place(cur, par2);
+      __syncthreads();
+      if (tid == 0) s_ln[par2 ^ 1u] = 0;
+      flush(par2);
+      any = __syncthreads_or(cur.pend != 0);
       ++it;
-      first = false;
-      if (!any) break;
     }
-    if constexpr (VAL) {
-#pragma unroll
-      for (int i = 0; i < PT_IPT; ++i) vcur[i] = vnxt[i];
-    }
+    cur = nxt;
+    R = Rn;
+    ++k;
   }
 
   // ---- drain: pad every partial sector with holes and flush it into the sector held in reserve
 #pragma unroll
   for (int q = 0; q < 2; ++q)
-    if ((pvalid >> q) & 1u) nextg[pd[q]] = pg[q];
+    if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
   __syncthreads();
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
     const uint32_t ww = w[d];
     const uint32_t cnt = ww >> 1, tog = ww & 1u;  // cnt < EPS after the last flush phase
-    ET* sec = reinterpret_cast<ET*>(buf + (size_t)d * PT_RINGB + tog * PT_SECTOR);
+    ET* sec = reinterpret_cast<ET*>(buf + d * PT_RINGB + tog * PT_SECTOR);
     for (uint32_t j = cnt; j < EPS; ++j) sec[j] = HOLE;
-    if (a.tma_store) fence_proxy_async();
+    if constexpr (TMAST) fence_proxy_async();
     store_sector(d, tog, nextg[d]);
   }
-  if (a.tma_store) {
+  if constexpr (TMAST) {
     bulk_commit();
     bulk_wait0();
   }
-  if (a.strict) {
-    kmax = __reduce_max_sync(0xffffffffu, kmax);
-    if ((tid & 31) == 0 && kmax) atomicMax(&a.ctl->max_key, (unsigned long long)kmax);
+  if constexpr (STRICT) {
     if (bad) atomicOr(&a.ctl->flags, CTL_NOT_DENSE16);
   }
 }
 
-size_t part_smem_bytes(int logp) {
-  return ((size_t)1 << logp) * (PT_RINGB + 10) + (size_t)PT_STAGES * PT_ROWS * 8;
-}
+size_t part_smem_bytes(int logp) { return ((size_t)1 << logp) * (PT_RINGB + 8) + (size_t)PT_STAGES * PT_STAGE_BYTES; }
 uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
-uint32_t part_grid(uint64_t n, const DeviceInfo& di) {
-  const uint64_t rounds = (n + PT_ROWS - 1) / PT_ROWS;
+uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
+  const uint64_t round = val ? 2048 : 4096;
+  const uint64_t rounds = (n + round - 1) / round;
   return (uint32_t)(rounds < (uint64_t)di.sms ? (rounds ? rounds : 1) : (uint64_t)di.sms);
 }
 
 bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (x.logp < 4 || (1 << x.logp) > PT_MAXP || x.world > PT_MAXW || x.n == 0) return false;
+  if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= 0xFFFFull) return false;
+  if ((x.n + 2047) / 2048 > 0xFFFFFFF0ull / 8) return false;
   PartParams a;
-  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = x.klimit; a.cap = x.cap; a.cursor = x.cursor; a.ctl = x.ctl;
+  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor;
+  a.ctl = x.ctl;
   for (int i = 0; i < PT_MAXW; ++i) a.outs[i] = i < x.world ? x.outs[i] : nullptr;
-  a.logp = x.logp; a.lpo = x.lpo; a.nsub = x.nsub; a.sub = x.sub; a.strict = x.strict ? 1 : 0; a.tma_store = x.tma_store ? 1 : 0;
+  a.logp = x.logp; a.lpo = x.lpo; a.nsub = x.nsub; a.sub = x.sub;
   const size_t smem = part_smem_bytes(x.logp);
   if (smem + 256 > di.smem_optin) return false;
-  const uint32_t grid = part_grid(x.n, di);
-  if (val) {
-    cudaFuncSetAttribute(k_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_part<true><<<grid, PT_THREADS, smem, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(k_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_part<false><<<grid, PT_THREADS, smem, st>>>(a);
-  }
+  const uint32_t grid = part_grid(val, x.n, di);
+#define FJ_PART(V, S, T)                                                                            \
+  do {                                                                                              \
+    cudaFuncSetAttribute(k_part<V, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_part<V, S, T><<<grid, PT_THREADS, smem, st>>>(a);                                            \
+  } while (0)
+  if (val) { if (x.tma_store) FJ_PART(true, true, true); else FJ_PART(true, true, false); }  // rows with values are a build side
+  else if (x.strict) { if (x.tma_store) FJ_PART(false, true, true); else FJ_PART(false, true, false); }
+  else { if (x.tma_store) FJ_PART(false, false, true); else FJ_PART(false, false, false); }
+#undef FJ_PART
   ++*launches;
   return true;
 }
@@ -321,7 +371,7 @@ struct SjoinParams {
   uint32_t cnt_stride;
   uint32_t p_first, p_count;   // partitions joined here: global ids p_first .. p_first + p_count - 1
   int logp, nsub;
-  uint32_t slots_alloc;        // direct-address slots the shared-memory region can hold (multiple of 8)
+  uint32_t slots;              // direct-address slots of the shared-memory region (multiple of 8, >= klimit >> logp)
   Ctl* ctl;
   unsigned long long* out_keys;
   unsigned long long* out_vals;
@@ -329,20 +379,26 @@ struct SjoinParams {
 
 __device__ __forceinline__ void sj_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"r"(SJ_CONS) : "memory"); }
 
+// MAT: the probe rows of a partition stream through TWICE.  Pass 1 only counts the matches, so that the
+// partition's output range is reserved with ONE global atomic (a per-warp reservation on the single output
+// cursor serialises in L2: 41 % of all stall samples of the first version, profiles/r02a_c3_dense16_ncu_summary.txt);
+// pass 2 (an L2 hit) looks the rows up again and writes the pairs, warps sub-allocating from the reserved range
+// with a shared-memory atomic.
 template <bool MAT>
 __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   constexpr uint32_t EB = MAT ? 4u : 2u;  // bytes per build element
   extern __shared__ __align__(128) unsigned char smem[];
   uint16_t* region16 = reinterpret_cast<uint16_t*>(smem);
   uint32_t* region32 = reinterpret_cast<uint32_t*>(smem);
-  unsigned char* ring = smem + (((size_t)a.slots_alloc * 2 + 127) & ~(size_t)127);
+  unsigned char* ring = smem + (((size_t)a.slots * 2 + 127) & ~(size_t)127);
   __shared__ __align__(8) uint64_t s_full[SJ_STAGES], s_empty[SJ_STAGES];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_total, s_cur;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // an earlier kernel of this attempt gave up: nothing to do (uniform; before any copy is in flight)
   if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_NOT_DENSE16 | CTL_OVERFLOW)) return;
-  uint32_t reff = (uint32_t)(((*reinterpret_cast<volatile unsigned long long*>(&a.ctl->max_key) >> a.logp) + 8ull) & ~7ull);
-  if (reff > a.slots_alloc) reff = a.slots_alloc;
+  const uint32_t reff = a.slots;
 
   if (tid == 0) {
 #pragma unroll
@@ -351,6 +407,8 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
       mbar_init(&s_empty[s], SJ_CWARPS);
     }
     mbar_fence_init();
+    s_total = 0;
+    s_cur = 0;
   }
   __syncthreads();
 
@@ -363,6 +421,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     }
     return t;
   };
+  constexpr int NPASS = MAT ? 3 : 2;  // build, probe (count), probe (emit)
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
@@ -370,7 +429,8 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     uint32_t it = 0;
     for (uint32_t l = blockIdx.x; l < a.p_count; l += gridDim.x) {
       if (side_total(a.bcnt, a.cap_b, l) == 0 || side_total(a.pcnt, a.cap_p, l) == 0) continue;
-      for (int side = 0; side < 2; ++side) {
+      for (int pass = 0; pass < NPASS; ++pass) {
+        const int side = pass ? 1 : 0;
         const uint32_t* cnt = side ? a.pcnt : a.bcnt;
         const uint64_t cap = side ? a.cap_p : a.cap_b;
         const uint32_t eb = side ? 2u : EB;
@@ -399,6 +459,20 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   unsigned long long local_count = 0;
   bool dup = false;
   uint32_t it = 0;
+  // the eight 16-bit indices of this thread's piece of a probe chunk -> direct-address values (0 = no match)
+  auto lookup8 = [&](const uint4& v, uint32_t (&idx)[8], uint32_t (&val)[8]) -> uint32_t {
+    const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      idx[r] = (e[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+      val[r] = idx[r] < reff ? (uint32_t)region16[idx[r]] : 0u;  // hole (0xFFFF) / beyond the domain: no match
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) hitmask |= val[r] ? (1u << r) : 0u;
+    return hitmask;
+  };
+
   for (uint32_t l = blockIdx.x; l < a.p_count; l += gridDim.x) {
     if (side_total(a.bcnt, a.cap_b, l) == 0 || side_total(a.pcnt, a.cap_p, l) == 0) continue;
     const unsigned long long plow = (unsigned long long)(a.p_first + l);  // the key bits the partition implies
@@ -413,11 +487,11 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     for (int sub = 0; sub < a.nsub; ++sub) {
       uint64_t c = a.bcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
       if (c > a.cap_b) c = a.cap_b;
-      const uint64_t bytes_total = c * EB;
-      for (uint64_t off = 0; off < bytes_total; off += SJ_CH) {
+      const uint32_t bytes_total = (uint32_t)(c * EB);
+      for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
         const int s = it % SJ_STAGES;
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
-        const uint32_t bytes = (uint32_t)(bytes_total - off < (uint64_t)SJ_CH ? bytes_total - off : (uint64_t)SJ_CH);
+        const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
         if (ct * 16u < bytes) {
           const uint4 v = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH)[ct];
           const uint32_t e[4] = {v.x, v.y, v.z, v.w};
@@ -446,33 +520,57 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
       }
     }
     sj_bar_consumers();
-    // ---- probe
+    // ---- probe, pass 1: count
+    uint32_t mine = 0;
     for (int sub = 0; sub < a.nsub; ++sub) {
       uint64_t c = a.pcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
       if (c > a.cap_p) c = a.cap_p;
-      const uint64_t bytes_total = c * 2u;
-      for (uint64_t off = 0; off < bytes_total; off += SJ_CH) {
+      const uint32_t bytes_total = (uint32_t)(c * 2u);
+      for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
         const int s = it % SJ_STAGES;
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
-        const uint32_t bytes = (uint32_t)(bytes_total - off < (uint64_t)SJ_CH ? bytes_total - off : (uint64_t)SJ_CH);
+        const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
         uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (ct * 16u < bytes) v = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH)[ct];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[s]);  // the rows are in registers: the stage can be refilled
-        ++it;
-        const uint32_t e[4] = {v.x, v.y, v.z, v.w};
         uint32_t idx[8], val[8];
-        uint32_t hitmask = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          idx[r] = (e[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
-          val[r] = idx[r] < reff ? (uint32_t)region16[idx[r]] : 0u;  // hole / beyond every build key: no match
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) hitmask |= val[r] ? (1u << r) : 0u;
-        if constexpr (!MAT) {
-          local_count += __popc(hitmask);
-        } else {
+        mine += __popc(lookup8(v, idx, val));  // the lookups depend on v: the stage has been read before it is released
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
+        ++it;
+      }
+    }
+    if constexpr (!MAT) {
+      local_count += mine;
+    } else {
+      // one reservation of the partition's output range
+      mine = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicAdd(&s_total, mine);
+      sj_bar_consumers();
+      if (ct == 0) {
+        const uint32_t t = s_total;
+        s_base = t ? atomicAdd(&a.ctl->out_cursor, (unsigned long long)t) : 0ull;
+        local_count += t;
+        s_total = 0;
+        s_cur = 0;
+      }
+      sj_bar_consumers();
+      const unsigned long long base0 = s_base;
+      // ---- probe, pass 2: emit
+      for (int sub = 0; sub < a.nsub; ++sub) {
+        uint64_t c = a.pcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
+        if (c > a.cap_p) c = a.cap_p;
+        const uint32_t bytes_total = (uint32_t)(c * 2u);
+        for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
+          const int s = it % SJ_STAGES;
+          mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
+          const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
+          uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (ct * 16u < bytes) v = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH)[ct];
+          uint32_t idx[8], val[8];
+          const uint32_t hitmask = lookup8(v, idx, val);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[s]);
+          ++it;
           uint32_t offs[8];
           uint32_t wtot = 0;
 #pragma unroll
@@ -481,17 +579,16 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
             offs[r] = wtot + __popc(bal & lanemask_lt());
             wtot += __popc(bal);
           }
-          unsigned long long base = 0;
-          if (lane == 0 && wtot) {
-            base = atomicAdd(&a.ctl->out_cursor, (unsigned long long)wtot);
-            local_count += wtot;
-          }
-          base = __shfl_sync(0xffffffffu, base, 0);
+          uint32_t wbase = 0;
+          if (lane == 0 && wtot) wbase = atomicAdd(&s_cur, wtot);
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          unsigned long long* ok = a.out_keys + base0 + wbase;
+          unsigned long long* ov = a.out_vals + base0 + wbase;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             if ((hitmask >> r) & 1u) {
-              st_stream(a.out_keys + base + offs[r], ((unsigned long long)idx[r] << a.logp) | plow);
-              st_stream(a.out_vals + base + offs[r], (unsigned long long)(val[r] - 1u));
+              st_stream(ok + offs[r], ((unsigned long long)idx[r] << a.logp) | plow);
+              st_stream(ov + offs[r], (unsigned long long)(val[r] - 1u));
             }
           }
         }
@@ -505,9 +602,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   if (dup) atomicOr(&a.ctl->flags, CTL_DUP);
 }
 
-size_t sjoin_smem_bytes(uint32_t slots_alloc) {
-  return (((size_t)slots_alloc * 2 + 127) & ~(size_t)127) + (size_t)SJ_STAGES * SJ_CH;
-}
+size_t sjoin_smem_bytes(uint32_t slots) { return (((size_t)slots * 2 + 127) & ~(size_t)127) + (size_t)SJ_STAGES * SJ_CH; }
 uint32_t sjoin_max_slots(const DeviceInfo& di) {
   const size_t room = di.smem_optin - 512 - (size_t)SJ_STAGES * SJ_CH;
   uint64_t s = room / 2;
@@ -521,9 +616,10 @@ bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream
   a.build = static_cast<const unsigned char*>(x.build); a.bcnt = x.bcnt; a.cap_b = x.cap_b;
   a.probe = static_cast<const unsigned char*>(x.probe); a.pcnt = x.pcnt; a.cap_p = x.cap_p;
   a.cnt_stride = x.cnt_stride; a.p_first = x.p_first; a.p_count = x.p_count; a.logp = x.logp; a.nsub = x.nsub;
-  a.slots_alloc = x.slots_alloc; a.ctl = x.ctl; a.out_keys = x.out_keys; a.out_vals = x.out_vals;
+  a.slots = x.slots_alloc; a.ctl = x.ctl; a.out_keys = x.out_keys; a.out_vals = x.out_vals;
   const size_t smem = sjoin_smem_bytes(x.slots_alloc);
   if (smem + 256 > di.smem_optin || (x.slots_alloc & 7u) || x.slots_alloc > 65528u) return false;
+  if (x.cap_b * 4 > 0xFFFFFFF0ull || x.cap_p * 2 > 0xFFFFFFF0ull) return false;
   const uint32_t grid = x.p_count < (uint32_t)di.sms ? x.p_count : (uint32_t)di.sms;
   if (mat) {
     cudaFuncSetAttribute(k_sjoin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
