@@ -45,7 +45,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // ================================================================================= k_part
-constexpr int PT_THREADS = 1024;
+constexpr int PT_THREADS = 512;               // 16 warps x 4 | 8 rows per thread and round: per-warp overheads (waits, barriers,
+                                              // flush-list checks) are paid once per 128 | 256 rows (profiles/r02b: 1024 x 2 rows was issue bound)
 constexpr int PT_STAGE_BYTES = 16384;         // one ring stage: 2048 keys, or 1024 keys + 1024 values
 constexpr int PT_STAGES = 5;
 constexpr int PT_RS = 2;                      // ring stages per round
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   constexpr uint32_t SLOTS = 2 * EPS;
   constexpr uint32_t SROWS = VAL ? 1024 : 2048;       // rows per ring stage
   constexpr uint32_t ROUND = PT_RS * SROWS;           // rows per round: 2048 | 4096
-  constexpr int IPT = ROUND / PT_THREADS;             // rows per thread and round: 2 | 4
+  constexpr int IPT = ROUND / PT_THREADS;             // rows per thread and round: 4 | 8
+  constexpr int PER = IPT / PT_RS;                    // rows per thread and ring stage
+  constexpr int NQ = PT_MAXP / PT_THREADS;            // flush-list entries per thread, worst case
   constexpr ET HOLE = (ET)~(ET)0;
   constexpr uint32_t NOPLACE = 0xFFFFu;               // nextg: the reservation lies beyond the region
   extern __shared__ __align__(128) unsigned char smem[];
@@ -164,51 +167,51 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     uint32_t pend;
   };
   bool bad = false;
-  // the rows of round R (local round k): digit, element, validity
+  // digit, element and validity of one row
+  auto decode = [&](uint2 kk, uint2 vv, bool ok, int i, Rows& r) {
+    bool in = (kk.y == 0u) & (kk.x < a.klimit);
+    if constexpr (VAL) in &= (vv.y == 0u) & (vv.x <= 65534u);
+    if constexpr (STRICT) bad |= ok & !in;
+    ok &= in;
+    r.d[i] = kk.x & pmask;
+    r.e[i] = (kk.x >> a.logp) | (VAL ? vv.x << 16 : 0u);
+    r.pend |= ok ? (1u << i) : 0u;
+  };
+  // the rows of round R (local round k).  Full rounds of 16-byte aligned inputs come out of the TMA ring: stage
+  // j = i / PER of the round, row (i % PER) * 512 + tid of it; the ragged tail / unaligned inputs are loaded directly.
   auto load_round = [&](uint32_t R, uint32_t k, Rows& r) {
     r.pend = 0;
-    const bool tma = R < nfull;
-    if (tma) {
+    if (R < nfull) {
 #pragma unroll
       for (int j = 0; j < PT_RS; ++j) {
         const uint32_t c = k * PT_RS + j;
         mbar_wait_bounded(&s_full[c % PT_STAGES], (c / PT_STAGES) & 1u);
-      }
-    }
+        const uint2* st = reinterpret_cast<const uint2*>(ring + (c % PT_STAGES) * PT_STAGE_BYTES);
+        uint2 kk[PER], vv[PER];
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      // TMA rounds: stage j = i / (IPT / RS), row (i % (IPT / RS)) * 1024 + tid of it
-      constexpr int PER = IPT / PT_RS;
-      const uint32_t c = k * PT_RS + i / PER;
-      const uint32_t sr = (i % PER) * PT_THREADS + tid;
-      uint2 kk, vv = make_uint2(0u, 0u);
-      bool ok = true;
-      if (tma) {
-        const unsigned char* st = ring + (size_t)(c % PT_STAGES) * PT_STAGE_BYTES;
-        kk = reinterpret_cast<const uint2*>(st)[sr];
-        if constexpr (VAL) vv = reinterpret_cast<const uint2*>(st + SROWS * 8u)[sr];
-      } else {
+        for (int q = 0; q < PER; ++q) {
+          kk[q] = st[q * PT_THREADS + tid];
+          vv[q] = VAL ? st[SROWS + q * PT_THREADS + tid] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) decode(kk[q], vv[q], true, j * PER + q, r);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
         const uint64_t row = (uint64_t)R * ROUND + (uint64_t)i * PT_THREADS + tid;
-        ok = row < a.n;
+        const bool ok = row < a.n;
         unsigned long long k64 = ~0ull, v64 = 0;
         if (ok) {
           k64 = ld_stream1(a.in_keys + row);
           if constexpr (VAL) v64 = ld_stream1(a.in_vals + row);
         }
-        kk = make_uint2((uint32_t)k64, (uint32_t)(k64 >> 32));
-        vv = make_uint2((uint32_t)v64, (uint32_t)(v64 >> 32));
+        decode(make_uint2((uint32_t)k64, (uint32_t)(k64 >> 32)), make_uint2((uint32_t)v64, (uint32_t)(v64 >> 32)), ok, i, r);
       }
-      bool in = (kk.y == 0u) & (kk.x < a.klimit);
-      if constexpr (VAL) in &= (vv.y == 0u) & (vv.x <= 65534u);
-      if constexpr (STRICT) bad |= ok & !in;
-      ok &= in;
-      r.d[i] = kk.x & pmask;
-      r.e[i] = (kk.x >> a.logp) | (VAL ? vv.x << 16 : 0u);
-      r.pend |= ok ? (1u << i) : 0u;
     }
   };
 
-  uint32_t pd[2] = {0, 0}, pg[2] = {0, 0};  // reservations in flight: partition, reserved element offset
+  uint32_t pd[NQ], pg[NQ];  // reservations in flight: partition, reserved element offset
   uint32_t pvalid = 0;
   uint32_t it = 0;  // place/flush iterations so far (selects the flush list counter)
 
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     }
     // the reservations issued in the previous flush phase have returned by now: publish them
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < NQ; ++q)
       if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
     pvalid = 0;
     if constexpr (TMAST) fence_proxy_async();  // staged rows become visible to the bulk-copy engine
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   auto flush = [&](uint32_t par) {
     const uint32_t nl = s_ln[par];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const uint32_t j = tid + (uint32_t)q * PT_THREADS;
       if (j < nl) {
         const uint32_t d = list[j];
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
 
   // ---- drain: pad every partial sector with holes and flush it into the sector held in reserve
 #pragma unroll
-  for (int q = 0; q < 2; ++q)
+  for (int q = 0; q < NQ; ++q)
     if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
   __syncthreads();
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
@@ -358,8 +361,10 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
 constexpr int SJ_THREADS = 1024;
 constexpr int SJ_CONS = SJ_THREADS - 32;  // consumer threads (warps 1..31)
 constexpr int SJ_CWARPS = SJ_CONS / 32;
-constexpr int SJ_CH = SJ_CONS * 16;       // bytes per ring stage: one 16-byte piece per consumer thread
-constexpr int SJ_STAGES = 5;
+constexpr int SJ_NPC = 2;                 // 16-byte pieces per consumer thread and chunk
+constexpr int SJ_CH = SJ_CONS * 16 * SJ_NPC;  // bytes per ring stage
+constexpr int SJ_STAGES = 3;
+constexpr uint32_t SJ_SLOTS = 65536;      // direct-address slots: every 16-bit index has one (0xFFFF = hole: never set)
 
 struct SjoinParams {
   const unsigned char* build;  // regions of cap_b elements (MAT: 4 bytes idx | value << 16; count: 2 bytes idx)
@@ -371,7 +376,7 @@ struct SjoinParams {
   uint32_t cnt_stride;
   uint32_t p_first, p_count;   // partitions joined here: global ids p_first .. p_first + p_count - 1
   int logp, nsub;
-  uint32_t slots;              // direct-address slots of the shared-memory region (multiple of 8, >= klimit >> logp)
+  uint32_t slots;              // slots a build row can address (multiple of 8): only these are zeroed
   Ctl* ctl;
   unsigned long long* out_keys;
   unsigned long long* out_vals;
@@ -383,14 +388,15 @@ __device__ __forceinline__ void sj_bar_consumers() { asm volatile("bar.sync 1, %
 // partition's output range is reserved with ONE global atomic (a per-warp reservation on the single output
 // cursor serialises in L2: 41 % of all stall samples of the first version, profiles/r02a_c3_dense16_ncu_summary.txt);
 // pass 2 (an L2 hit) looks the rows up again and writes the pairs, warps sub-allocating from the reserved range
-// with a shared-memory atomic.
+// with a shared-memory atomic.  The region has a slot for EVERY 16-bit index, so a lookup needs no bounds check:
+// slot 0xFFFF (the hole marker) and the slots beyond the build side's domain are zero.
 template <bool MAT>
 __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   constexpr uint32_t EB = MAT ? 4u : 2u;  // bytes per build element
   extern __shared__ __align__(128) unsigned char smem[];
   uint16_t* region16 = reinterpret_cast<uint16_t*>(smem);
   uint32_t* region32 = reinterpret_cast<uint32_t*>(smem);
-  unsigned char* ring = smem + (((size_t)a.slots * 2 + 127) & ~(size_t)127);
+  unsigned char* ring = smem + (size_t)SJ_SLOTS * 2;
   __shared__ __align__(8) uint64_t s_full[SJ_STAGES], s_empty[SJ_STAGES];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_total, s_cur;
@@ -398,7 +404,6 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // an earlier kernel of this attempt gave up: nothing to do (uniform; before any copy is in flight)
   if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_NOT_DENSE16 | CTL_OVERFLOW)) return;
-  const uint32_t reff = a.slots;
 
   if (tid == 0) {
 #pragma unroll
@@ -410,6 +415,8 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     s_total = 0;
     s_cur = 0;
   }
+  // the slots no build row can address stay zero for the whole kernel
+  for (uint32_t i = a.slots / 8u + (uint32_t)tid; i < SJ_SLOTS / 8u; i += SJ_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
   // elements of one side of partition l (local index), summed over the sub-regions
@@ -459,27 +466,28 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   unsigned long long local_count = 0;
   bool dup = false;
   uint32_t it = 0;
-  // the eight 16-bit indices of this thread's piece of a probe chunk -> direct-address values (0 = no match)
+  // the eight 16-bit indices of one 16-byte piece of a probe chunk -> direct-address values (0 = no match)
   auto lookup8 = [&](const uint4& v, uint32_t (&idx)[8], uint32_t (&val)[8]) -> uint32_t {
     const uint32_t e[4] = {v.x, v.y, v.z, v.w};
     uint32_t hitmask = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      idx[r] = (e[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
-      val[r] = idx[r] < reff ? (uint32_t)region16[idx[r]] : 0u;  // hole (0xFFFF) / beyond the domain: no match
+      idx[r] = (r & 1) ? (e[r >> 1] >> 16) : (e[r >> 1] & 0xffffu);
+      val[r] = region16[idx[r]];
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) hitmask |= val[r] ? (1u << r) : 0u;
     return hitmask;
   };
+  const uint4 HOLES = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
 
   for (uint32_t l = blockIdx.x; l < a.p_count; l += gridDim.x) {
     if (side_total(a.bcnt, a.cap_b, l) == 0 || side_total(a.pcnt, a.cap_p, l) == 0) continue;
-    const unsigned long long plow = (unsigned long long)(a.p_first + l);  // the key bits the partition implies
-    // ---- zero the region
+    const uint32_t plow = a.p_first + l;  // the key bits the partition implies
+    // ---- zero the addressable part of the region
     {
       uint4* r4 = reinterpret_cast<uint4*>(smem);
-      const uint32_t n4 = reff / 8u;
+      const uint32_t n4 = a.slots / 8u;
       for (uint32_t i = ct; i < n4; i += SJ_CONS) r4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     sj_bar_consumers();
@@ -492,25 +500,31 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         const int s = it % SJ_STAGES;
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
         const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
-        if (ct * 16u < bytes) {
-          const uint4 v = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH)[ct];
-          const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+        const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
+        uint4 v[SJ_NPC];
+#pragma unroll
+        for (int q = 0; q < SJ_NPC; ++q) {
+          const uint32_t piece = (uint32_t)q * SJ_CONS + ct;
+          v[q] = piece * 16u < bytes ? st[piece] : HOLES;
+        }
+#pragma unroll
+        for (int q = 0; q < SJ_NPC; ++q) {
+          const uint32_t e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
           if constexpr (MAT) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const uint32_t idx = e[r] & 0xffffu;
-              if (idx < reff) {  // a hole (0xFFFF) never is: reff <= 65528
-                const uint32_t sh = (idx & 1u) * 16u;
-                const uint32_t old = atomicOr(&region32[idx >> 1], ((e[r] >> 16) + 1u) << sh);
-                dup |= ((old >> sh) & 0xffffu) != 0u;  // the slot was taken: duplicate build key
-              }
+              const uint32_t sh = (idx & 1u) * 16u;
+              // a hole (idx 0xFFFF, value field 0xFFFF) ORs a zero into slot 0xFFFF
+              const uint32_t old = atomicOr(&region32[idx >> 1], (((e[r] >> 16) + 1u) & 0xffffu) << sh);
+              dup |= ((old >> sh) & 0xffffu) != 0u;  // the slot was taken: duplicate build key
             }
           } else {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const uint32_t i0 = e[r] & 0xffffu, i1 = e[r] >> 16;
-              if (i0 < reff) region16[i0] = 1;
-              if (i1 < reff) region16[i1] = 1;
+              region16[i0] = i0 != 0xffffu;
+              region16[i1] = i1 != 0xffffu;
             }
           }
         }
@@ -530,10 +544,14 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         const int s = it % SJ_STAGES;
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
         const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
-        uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (ct * 16u < bytes) v = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH)[ct];
-        uint32_t idx[8], val[8];
-        mine += __popc(lookup8(v, idx, val));  // the lookups depend on v: the stage has been read before it is released
+        const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
+#pragma unroll
+        for (int q = 0; q < SJ_NPC; ++q) {
+          const uint32_t piece = (uint32_t)q * SJ_CONS + ct;
+          const uint4 v = piece * 16u < bytes ? st[piece] : HOLES;
+          uint32_t idx[8], val[8];
+          mine += __popc(lookup8(v, idx, val));  // the lookups depend on v: the stage has been read before it is released
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);
         ++it;
@@ -554,7 +572,8 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         s_cur = 0;
       }
       sj_bar_consumers();
-      const unsigned long long base0 = s_base;
+      unsigned long long* const okp = a.out_keys + s_base;
+      unsigned long long* const ovp = a.out_vals + s_base;
       // ---- probe, pass 2: emit
       for (int sub = 0; sub < a.nsub; ++sub) {
         uint64_t c = a.pcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
@@ -564,33 +583,42 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
           const int s = it % SJ_STAGES;
           mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
           const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
-          uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-          if (ct * 16u < bytes) v = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH)[ct];
-          uint32_t idx[8], val[8];
-          const uint32_t hitmask = lookup8(v, idx, val);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[s]);
-          ++it;
-          uint32_t offs[8];
-          uint32_t wtot = 0;
+          const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
+          uint4 v[SJ_NPC];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> r) & 1u);
-            offs[r] = wtot + __popc(bal & lanemask_lt());
-            wtot += __popc(bal);
+          for (int q = 0; q < SJ_NPC; ++q) {
+            const uint32_t piece = (uint32_t)q * SJ_CONS + ct;
+            v[q] = piece * 16u < bytes ? st[piece] : HOLES;
           }
-          uint32_t wbase = 0;
-          if (lane == 0 && wtot) wbase = atomicAdd(&s_cur, wtot);
-          wbase = __shfl_sync(0xffffffffu, wbase, 0);
-          unsigned long long* ok = a.out_keys + base0 + wbase;
-          unsigned long long* ov = a.out_vals + base0 + wbase;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            if ((hitmask >> r) & 1u) {
-              st_stream(ok + offs[r], ((unsigned long long)idx[r] << a.logp) | plow);
-              st_stream(ov + offs[r], (unsigned long long)(val[r] - 1u));
+          for (int q = 0; q < SJ_NPC; ++q) {
+            uint32_t idx[8], val[8];
+            const uint32_t hitmask = lookup8(v[q], idx, val);
+            if (q == SJ_NPC - 1) {  // every piece of the stage is in registers and looked up
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s_empty[s]);
+            }
+            uint32_t offs[8];
+            uint32_t wtot = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> r) & 1u);
+              offs[r] = wtot + __popc(bal & lanemask_lt());
+              wtot += __popc(bal);
+            }
+            uint32_t wbase = 0;
+            if (lane == 0 && wtot) wbase = atomicAdd(&s_cur, wtot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if ((hitmask >> r) & 1u) {
+                const uint32_t o = wbase + offs[r];
+                st_stream(okp + o, (unsigned long long)((idx[r] << a.logp) | plow));  // keys of this path are < 2^32
+                st_stream(ovp + o, (unsigned long long)(val[r] - 1u));
+              }
             }
           }
+          ++it;
         }
       }
     }
@@ -602,13 +630,8 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   if (dup) atomicOr(&a.ctl->flags, CTL_DUP);
 }
 
-size_t sjoin_smem_bytes(uint32_t slots) { return (((size_t)slots * 2 + 127) & ~(size_t)127) + (size_t)SJ_STAGES * SJ_CH; }
-uint32_t sjoin_max_slots(const DeviceInfo& di) {
-  const size_t room = di.smem_optin - 512 - (size_t)SJ_STAGES * SJ_CH;
-  uint64_t s = room / 2;
-  if (s > 65528) s = 65528;  // idx 0xFFFF is the hole marker
-  return (uint32_t)(s & ~uint64_t(7));
-}
+size_t sjoin_smem_bytes(uint32_t) { return (size_t)SJ_SLOTS * 2 + (size_t)SJ_STAGES * SJ_CH; }
+uint32_t sjoin_max_slots(const DeviceInfo&) { return 65528; }  // idx 0xFFFF is the hole marker
 
 bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (x.p_count == 0) return false;

@@ -62,4 +62,17 @@ assert n == 3, f"expected 3 materialize returns, patched {n}"
 open(p, 'w').write('\n'.join(out))
 PYEOF
 g++ $CXXFLAGS $INC -I"$TMP/stub" -I"$(dirname "$REF")" "$TMP/hash_join_pairs.cpp" -o "$OUT/pairs/flash_join_pairs$EXT"
+# timing variant: the reference linked against its own vendored allocator with the malloc override on, as its
+# CMakeLists.txt configures it (MI_OVERRIDE / MI_MALLOC_OVERRIDE, :9-16, :23-28) — mimalloc's single-file build
+# (src/static.c) compiled where it lies; the reference's CMake itself is not run.  This module interposes
+# malloc/operator new: it is only ever loaded FIRST in a numpy-only subprocess (bench.py's CPU worker), as the
+# reference's benchmark.py:13 demands; next to torch/pandas it crashes, so parity uses "plain".
+MI="$(dirname "$REF")/mimalloc"
+if [ -f "$MI/src/static.c" ]; then
+  mkdir -p "$OUT/mimalloc"
+  gcc -O3 -DNDEBUG -DMI_MALLOC_OVERRIDE -DMI_STATIC_LIB -fPIC -fvisibility=hidden -std=gnu11 -fno-builtin-malloc \
+      -ftls-model=initial-exec -I"$MI/include" -c "$MI/src/static.c" -o "$TMP/mimalloc_static.o"
+  g++ $CXXFLAGS $INC -I"$MI/include" "$REF" "$TMP/mimalloc_static.o" -o "$OUT/mimalloc/flash_join$EXT"
+  echo "built: $OUT/mimalloc/flash_join$EXT"
+fi
 echo "built: $OUT/plain/flash_join$EXT $OUT/pairs/flash_join_pairs$EXT"

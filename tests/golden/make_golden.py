@@ -25,16 +25,25 @@ HERE = Path(__file__).resolve().parent
 G1_CASES = [(10**6, 10**3, 90), (10**6, 10**6, 90), (10**6, 10**4, 10), (10**7, 10, 90), (10**7, 10**4, 90), (10**7, 10**7, 90)]
 G1_BIG = [(10**8, 10**5, 10), (10**8, 10**8, 90)]
 G2_CASES = [(10**6, 10**5, 10), (10**6, 10**6, 90), (10**7, 10**4, 90)]
+# the bench workloads (bench.py generates G2 in HBM): C2, C3, the C4 per-GPU slice, and the weak-scaling C2 totals
+# at 2 / 4 / 8 GPUs (probe rows [0, G * 1e8) against the same 1e5-row build side; counts only)
+G2_BIG = [(10**8, 10**5, 10), (10**8, 10**8, 90), (125 * 10**6, 10**6, 90)]
+G2_WEAK = [(2 * 10**8, 10**5, 10), (4 * 10**8, 10**5, 10), (8 * 10**8, 10**5, 10)]
 
 
-def run_case(gen, N, ny, pct, plain, pairs, skip_scalar_above=2 * 10**7):
+def run_case(gen, N, ny, pct, plain, pairs, skip_scalar_above=2 * 10**7, count_only=False):
     bk, bv, pk = gen(N, ny, pct)
     counts = {}
     for (algo, bloom, mat), name in O.ENTRY_POINTS.items():
         if algo == "scalar" and ny > skip_scalar_above:
             continue  # 8.6 GB table with a serial clear at 1e8 — skipped
+        if count_only and (mat or algo == "radix"):
+            continue
         counts[name] = int(getattr(plain, name)(bk, bv, pk)[0])
     assert len(set(counts.values())) == 1, counts
+    if count_only:
+        return {"N": N, "ny": ny, "match_pct": pct, "seed": 108, "count": next(iter(counts.values())), "sum_keys": None, "xor_keys": None,
+                "sum_vals": None, "entry_points_agreed": sorted(counts), "pairs_from": None}
     entry = "hash_join_radix" if ny >= 10**6 else "hash_join"
     r = getattr(pairs, entry)(bk, bv, pk)
     cs = O.checksums(r[2], r[3])
@@ -83,10 +92,12 @@ def main():
         rows = json.loads(path.read_text())["cases"]
         existing = {(r["gen"], r["N"], r["ny"], r["match_pct"]) for r in rows}
     todo = [("g1", c) for c in G1_CASES] + [("g2", c) for c in G2_CASES] + ([("g1", c) for c in G1_BIG] if a.big else [])
+    if a.big:
+        todo += [("g2", c) for c in G2_BIG] + [("g2", c) for c in G2_WEAK]
     for gname, (N, ny, pct) in todo:
         if (gname, N, ny, pct) in existing:
             continue
-        row = run_case(g1 if gname == "g1" else g2, N, ny, pct, plain, pairs)
+        row = run_case(g1 if gname == "g1" else g2, N, ny, pct, plain, pairs, count_only=(N, ny, pct) in G2_WEAK)
         row["gen"] = gname
         print(row, flush=True)
         rows.append(row)
