@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   constexpr uint32_t ROUND = PT_RS * SROWS;           // rows per round: 2048 | 4096
   constexpr int IPT = ROUND / PT_THREADS;             // rows per thread and round: 4 | 8
   constexpr int PER = IPT / PT_RS;                    // rows per thread and ring stage
-  constexpr int NQ = PT_MAXP / PT_THREADS;            // flush-list entries per thread, worst case
+  constexpr int WCAP = 128;                           // flush-list entries per warp
+  constexpr int NQ = WCAP / 32;                       // flush-list entries per lane
   constexpr ET HOLE = (ET)~(ET)0;
   constexpr uint32_t NOPLACE = 0xFFFFu;               // nextg: the reservation lies beyond the region
   extern __shared__ __align__(128) unsigned char smem[];
@@ -91,10 +92,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   unsigned char* buf = smem;                                               // P x 64 B: two sectors per partition
   uint32_t* w = reinterpret_cast<uint32_t*>(smem + (size_t)P * PT_RINGB);  // P: elements in the ring << 1 | first sector
   uint16_t* nextg = reinterpret_cast<uint16_t*>(w + P);                    // P: sector (in the sub-region) reserved for the next flush
-  uint16_t* list = nextg + P;                                              // P: partitions with a complete sector
-  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 8);                 // PT_STAGES x 16 KB
+  uint16_t* wlist = nextg + P + (threadIdx.x >> 5) * WCAP;                 // per warp: partitions whose first sector its rows completed
+  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 6) + (PT_THREADS / 32) * WCAP * 2;  // PT_STAGES x 16 KB
   __shared__ __align__(8) uint64_t s_full[PT_STAGES];
-  __shared__ uint32_t s_ln[2];
   __shared__ unsigned char* s_outs[PT_MAXW];
 
   const uint32_t tid = threadIdx.x;
@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   const uint32_t capsec = a.cap >> LOG_EPS;
   const uint32_t pmask = P - 1u;
 
-  if (tid < 2) s_ln[tid] = 0;
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < PT_MAXW; ++i) s_outs[i] = static_cast<unsigned char*>(a.outs[i]);  // static indices: no local copy
@@ -213,25 +212,34 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
 
   uint32_t pd[NQ], pg[NQ];  // reservations in flight: partition, reserved element offset
   uint32_t pvalid = 0;
-  uint32_t it = 0;  // place/flush iterations so far (selects the flush list counter)
+  const uint32_t lane = tid & 31u;
 
-  // ---- place: one shared-memory atomic hands out the slot; a row that finds the ring full stays pending
-  auto place = [&](Rows& r, uint32_t par) {
+  // ---- place: one shared-memory atomic hands out the slot; a row that finds the ring full stays pending.  The row
+  // that completes a partition's first sector puts the partition on its WARP's flush list (ballot + prefix: no
+  // atomics, no cross-warp list); `ovf` = rows whose partition did not fit the list (flushed by the thread itself).
+  auto place = [&](Rows& r, uint32_t& ovf) -> uint32_t {
     uint32_t old[IPT];
 #pragma unroll
-    for (int i = 0; i < IPT; ++i)
-      if ((r.pend >> i) & 1u) old[i] = atomicAdd(&w[r.d[i]], 2u);
+    for (int i = 0; i < IPT; ++i) old[i] = ((r.pend >> i) & 1u) ? atomicAdd(&w[r.d[i]], 2u) : 0xFFFFFFFEu;
+    uint32_t wn = 0;
+    ovf = 0;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      if ((r.pend >> i) & 1u) {
-        const uint32_t cnt = old[i] >> 1;
-        if (cnt < SLOTS) {
-          const uint32_t slot = (cnt + ((old[i] & 1u) << LOG_EPS)) & (SLOTS - 1u);
-          reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + slot] = (ET)r.e[i];
-          if (cnt == EPS - 1u) list[atomicAdd(&s_ln[par], 1u)] = (uint16_t)r.d[i];  // first sector complete
-          r.pend &= ~(1u << i);
-        }
+      const uint32_t cnt = old[i] >> 1;
+      const bool placed = cnt < SLOTS;  // rows that are not pending carry cnt = 0x7FFFFFFF
+      if (placed) {
+        const uint32_t slot = (cnt + ((old[i] & 1u) << LOG_EPS)) & (SLOTS - 1u);
+        reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + slot] = (ET)r.e[i];
+        r.pend &= ~(1u << i);
       }
+      const bool full = cnt == EPS - 1u;  // first sector complete
+      const unsigned m = __ballot_sync(0xffffffffu, full);
+      if (full) {
+        const uint32_t pos = wn + __popc(m & lanemask_lt());
+        if (pos < (uint32_t)WCAP) wlist[pos] = (uint16_t)r.d[i];
+        else ovf |= 1u << i;
+      }
+      wn += __popc(m);
     }
     // the reservations issued in the previous flush phase have returned by now: publish them
 #pragma unroll
@@ -239,28 +247,41 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
       if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
     pvalid = 0;
     if constexpr (TMAST) fence_proxy_async();  // staged rows become visible to the bulk-copy engine
+    return wn < (uint32_t)WCAP ? wn : (uint32_t)WCAP;
   };
-  // ---- flush the listed partitions: full sectors, each to the place reserved for it
-  auto flush = [&](uint32_t par) {
-    const uint32_t nl = s_ln[par];
+  // one listed partition: its full sector(s) leave for the place reserved in advance; the reservation of the NEXT
+  // flush is issued here and consumed an iteration later (q >= 0), or waited for (q < 0: the rare overflow path)
+  auto flush_one = [&](uint32_t d, int q) {
+    const uint32_t ww = w[d];
+    const uint32_t gs = nextg[d];
+    const uint32_t g = atomicAdd(a.cursor + d, EPS);
+    uint32_t cnt = ww >> 1;
+    if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
+    const uint32_t tog = ww & 1u;
+    const uint32_t nsec = cnt >> LOG_EPS;  // 1 or 2
+    store_sector(d, tog, gs);
+    if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d, EPS)));  // rare: both sectors filled at once
+    w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
+    if (q >= 0) {
+      pg[q] = g;
+      pd[q] = d;
+      pvalid |= 1u << q;
+    } else {
+      nextg[d] = to_sector(g);
+    }
+  };
+  // ---- flush: every warp flushes the partitions on its own list, one per lane
+  auto flush = [&](const Rows& r, uint32_t wn, uint32_t ovf) {
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const uint32_t j = tid + (uint32_t)q * PT_THREADS;
-      if (j < nl) {
-        const uint32_t d = list[j];
-        const uint32_t ww = w[d];
-        const uint32_t gs = nextg[d];
-        pg[q] = atomicAdd(a.cursor + d, EPS);  // place of this partition's NEXT flush (consumed an iteration later)
-        pd[q] = d;
-        pvalid |= 1u << q;
-        uint32_t cnt = ww >> 1;
-        if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
-        const uint32_t tog = ww & 1u;
-        const uint32_t nsec = cnt >> LOG_EPS;  // 1 or 2
-        store_sector(d, tog, gs);
-        if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d, EPS)));  // rare: both sectors filled at once
-        w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
-      }
+      const uint32_t j = (uint32_t)q * 32u + lane;
+      if (j < wn) flush_one(wlist[j], q);
+    }
+    if (ovf) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i)
+        if ((ovf >> i) & 1u) flush_one(r.d[i], -1);
     }
     if constexpr (TMAST) {
       bulk_commit();
@@ -273,29 +294,24 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   uint32_t R = blockIdx.x;
   if (R < rounds) load_round(R, 0, cur);
   while (R < rounds) {
-    const uint32_t par = it & 1u;
-    place(cur, par);
+    uint32_t ovf;
+    uint32_t wn = place(cur, ovf);
     __syncthreads();  // #1: every row of this iteration is staged
     if (tid == 0) {
       // the ring stages of THIS round were read before the previous barrier #2: refill them
       issue(k * PT_RS + PT_STAGES);
       issue(k * PT_RS + 1 + PT_STAGES);
-      s_ln[par ^ 1u] = 0;
     }
-    flush(par);
-    // the rows of the next round are fetched and decoded while the few flushing warps are busy
+    flush(cur, wn, ovf);
+    // the rows of the next round are fetched and decoded before the barrier: warps that finish their flush early go ahead
     const uint32_t Rn = R + G;
     if (Rn < rounds) load_round(Rn, k + 1, nxt);
-    int any = __syncthreads_or(cur.pend != 0);  // #2
-    ++it;
+    int any = __syncthreads_or(cur.pend != 0);  // #2: the flushed rings are consistent again
     while (any) {  // some ring was full (more than a ring's worth of rows for one partition within a round): retry
-      const uint32_t par2 = it & 1u;
-      place(cur, par2);
+      wn = place(cur, ovf);
       __syncthreads();
-      if (tid == 0) s_ln[par2 ^ 1u] = 0;
-      flush(par2);
+      flush(cur, wn, ovf);
       any = __syncthreads_or(cur.pend != 0);
-      ++it;
     }
     cur = nxt;
     R = Rn;
@@ -324,7 +340,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   }
 }
 
-size_t part_smem_bytes(int logp) { return ((size_t)1 << logp) * (PT_RINGB + 8) + (size_t)PT_STAGES * PT_STAGE_BYTES; }
+size_t part_smem_bytes(int logp) {
+  return ((size_t)1 << logp) * (PT_RINGB + 6) + (PT_THREADS / 32) * 128 * 2 + (size_t)PT_STAGES * PT_STAGE_BYTES;
+}
 uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
 uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
   const uint64_t round = val ? 2048 : 4096;
