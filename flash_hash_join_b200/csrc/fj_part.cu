@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     for (uint32_t c = 0; c < PT_STAGES; ++c) issue(c);
   }
 
+  unsigned char* const out0 = static_cast<unsigned char*>(a.outs[0]);  // owner 0 (the only one on a single GPU): no table lookup
   // one 32-byte sector of partition d: shared memory -> sector gs of its sub-region in the owner's buffer
   auto store_sector = [&](uint32_t d, uint32_t sec, uint32_t gs) {
     if (gs == NOPLACE) {
@@ -150,7 +151,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     }
     const unsigned char* src = buf + d * PT_RINGB + sec * PT_SECTOR;
     const uint32_t region = (d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
-    unsigned char* dst = s_outs[d >> a.lpo] + (((uint64_t)region * capsec + gs) << 5);
+    const uint32_t owner = d >> a.lpo;
+    unsigned char* dst = (owner ? s_outs[owner] : out0) + (((uint64_t)region * capsec + gs) << 5);
     if constexpr (TMAST) {
       bulk_s2g(dst, src, PT_SECTOR);
     } else {
@@ -254,7 +256,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   auto flush_one = [&](uint32_t d, int q) {
     const uint32_t ww = w[d];
     const uint32_t gs = nextg[d];
-    const uint32_t g = atomicAdd(a.cursor + d, EPS);
     uint32_t cnt = ww >> 1;
     if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
     const uint32_t tog = ww & 1u;
@@ -263,11 +264,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d, EPS)));  // rare: both sectors filled at once
     w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
     if (q >= 0) {
-      pg[q] = g;
+      // The reservation's round trip through L2 (1 - 2 us under load) must not be waited for in this phase: the
+      // atomic writes straight into the register that is read an iteration later (a C++ temporary made ptxas
+      // park the warp on a MOV right here: 12 % of all stall samples, profiles/r02d_c3_dense16_ncu_summary.txt)
+      asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[q]) : "l"(a.cursor + d), "r"(EPS) : "memory");
       pd[q] = d;
       pvalid |= 1u << q;
     } else {
-      nextg[d] = to_sector(g);
+      nextg[d] = to_sector(atomicAdd(a.cursor + d, EPS));
     }
   };
   // ---- flush: every warp flushes the partitions on its own list, one per lane
