@@ -26,7 +26,8 @@ class Stats(C.Structure):
         ("matches", C.c_uint64), ("table_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
         ("path", C.c_int32), ("narrow", C.c_int32), ("bloom_kind", C.c_int32), ("attempts", C.c_int32),
         ("dedup_exact", C.c_int32), ("kernel_launches", C.c_int32), ("radix_bits1", C.c_int32), ("radix_bits2", C.c_int32),
-        ("n_gpus", C.c_int32), ("dense", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("n_gpus", C.c_int32), ("dense", C.c_int32), ("part_build_us", C.c_int32), ("part_probe_us", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
     def as_dict(self) -> dict:

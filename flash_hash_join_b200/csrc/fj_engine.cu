@@ -104,7 +104,7 @@ struct Engine {
   bool inited = false;
   DeviceInfo di;
   cudaStream_t st = nullptr;
-  cudaEvent_t ev[12] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases
+  cudaEvent_t ev[13] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases, 12 build | probe partition pass
   Ctl* h_ctl = nullptr;  // pinned
   // multi-GPU count: the ncclAllReduce of the control block is enqueued right behind the first attempt's kernels
   // (before the host has seen the flags), so a step has ONE host synchronisation instead of two.  The summed
@@ -840,20 +840,23 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   const size_t eb = mat ? 4 : 2;
   FJ_TRY(part_a_b.ensure((size_t)P * dp.cap_b * eb));
   FJ_TRY(part_a_p.ensure((size_t)P * dp.cap_p * 2));
-  FJ_TRY(cursors.ensure(2 * (size_t)P * 4));
+  const uint32_t cs = part_cursor_stride();
+  FJ_TRY(cursors.ensure(2 * (size_t)P * cs * 4));
   uint32_t* cur_b = cursors.as<uint32_t>();
-  uint32_t* cur_p = cur_b + P;
+  uint32_t* cur_p = cur_b + (size_t)P * cs;
   Ctl* d_ctl = ctl.as<Ctl>();
   int launches = 0;
   FJ_CUDA(cudaEventRecord(ev[0], st));
-  launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * 4, di, st);
+  launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st);
   ++launches;
   FJ_CUDA(cudaEventRecord(ev[1], st));
   PartArgs a;
   a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = a.lpo = dp.logp; a.world = 1; a.nsub = 1; a.sub = 0;
   a.tma_store = cfg["part_tma_store"] != 0;
+  a.cursor_stride = cs;
   a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.outs[0] = part_a_b.p; a.strict = true;
   bool launched = launch_part(mat, a, di, st, &launches);
+  FJ_CUDA(cudaEventRecord(ev[12], st));
   a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.outs[0] = part_a_p.p; a.strict = false;
   launched = launched && launch_part(false, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[2], st));
@@ -861,7 +864,7 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
     SjoinArgs j;
     j.build = part_a_b.p; j.bcnt = cur_b; j.cap_b = dp.cap_b;
     j.probe = part_a_p.p; j.pcnt = cur_p; j.cap_p = dp.cap_p;
-    j.cnt_stride = 0; j.p_first = 0; j.p_count = P; j.logp = dp.logp; j.nsub = 1; j.slots_alloc = dp.slots;
+    j.cnt_stride = 0; j.cursor_stride = cs; j.p_first = 0; j.p_count = P; j.logp = dp.logp; j.nsub = 1; j.slots_alloc = dp.slots;
     j.ctl = d_ctl;
     j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
     j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
@@ -886,6 +889,8 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   s->radix_bits1 = dp.logp;
   s->radix_bits2 = 0;
   s->dense = 2;
+  s->part_build_us = (int32_t)(ms(1, 12) * 1e3f);
+  s->part_probe_us = (int32_t)(ms(12, 2) * 1e3f);
   return FJ_OK;
 }
 

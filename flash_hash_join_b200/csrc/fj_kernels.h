@@ -172,7 +172,8 @@ struct PartArgs {
   uint64_t n = 0;
   uint64_t klimit = 0;   // keys >= klimit are outside the domain (strict: CTL_NOT_DENSE16; else the row is dropped)
   uint64_t cap = 0;      // elements per (partition, sub-region), multiple of 16
-  uint32_t* cursor = nullptr;  // [2^logp], zeroed: elements reserved per partition by THIS source
+  uint32_t* cursor = nullptr;  // [2^logp * cursor_stride], zeroed: elements reserved per partition by THIS source
+  uint32_t cursor_stride = 1;  // 32-bit words between two cursors
   Ctl* ctl = nullptr;
   void* outs[8] = {};    // [world] base of every owner's partition buffer
   int world = 1;
@@ -183,6 +184,7 @@ struct PartArgs {
 };
 size_t part_smem_bytes(int logp);
 uint32_t part_sector_elems(bool val);
+uint32_t part_cursor_stride();
 uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di);
 bool launch_part(bool val, const PartArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 struct SjoinArgs {
@@ -193,6 +195,7 @@ struct SjoinArgs {
   const uint32_t* pcnt = nullptr;
   uint64_t cap_p = 0;
   uint32_t cnt_stride = 0;
+  uint32_t cursor_stride = 1;         // cursor of (sub, p) = cnt[(sub * cnt_stride + p) * cursor_stride]
   uint32_t p_first = 0, p_count = 0;  // global ids of the partitions joined by this GPU
   int logp = 11, nsub = 1;
   uint32_t slots_alloc = 0;           // shared-memory direct-address slots (>= klimit >> logp), multiple of 8, <= sjoin_max_slots

@@ -61,7 +61,8 @@ struct PartParams {
   uint64_t n;
   uint32_t klimit;     // keys >= klimit are outside the domain (klimit <= 2^32 - 1)
   uint32_t cap;        // elements per (partition, sub-region); multiple of 16
-  uint32_t* cursor;    // [P] elements reserved per partition (this source)
+  uint32_t* cursor;    // [P * cstride] elements reserved per partition (this source)
+  uint32_t cstride;    // 32-bit words between two cursors (see fj_kernels.h: part_cursor_stride)
   Ctl* ctl;
   void* outs[PT_MAXW]; // base of every owner's partition buffer (peer-mapped for remote owners)
   int logp;            // log2(partitions)
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   // every (CTA, partition) holds one sector reserved in advance
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
     w[d] = 0;
-    nextg[d] = to_sector(atomicAdd(a.cursor + d, EPS));
+    nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
   }
   __syncthreads();
 
@@ -261,17 +262,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     const uint32_t tog = ww & 1u;
     const uint32_t nsec = cnt >> LOG_EPS;  // 1 or 2
     store_sector(d, tog, gs);
-    if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d, EPS)));  // rare: both sectors filled at once
+    if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d * a.cstride, EPS)));  // rare: both sectors filled at once
     w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
     if (q >= 0) {
       // The reservation's round trip through L2 (1 - 2 us under load) must not be waited for in this phase: the
       // atomic writes straight into the register that is read an iteration later (a C++ temporary made ptxas
       // park the warp on a MOV right here: 12 % of all stall samples, profiles/r02d_c3_dense16_ncu_summary.txt)
-      asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[q]) : "l"(a.cursor + d), "r"(EPS) : "memory");
+      asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[q]) : "l"(a.cursor + d * a.cstride), "r"(EPS) : "memory");
       pd[q] = d;
       pvalid |= 1u << q;
     } else {
-      nextg[d] = to_sector(atomicAdd(a.cursor + d, EPS));
+      nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
     }
   };
   // ---- flush: every warp flushes the partitions on its own list, one per lane
@@ -348,6 +349,10 @@ size_t part_smem_bytes(int logp) {
   return ((size_t)1 << logp) * (PT_RINGB + 6) + (PT_THREADS / 32) * 128 * 2 + (size_t)PT_STAGES * PT_STAGE_BYTES;
 }
 uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
+// One cursor per 256 bytes: 2048 adjacent 4-byte cursors live in 64 cache lines, i.e. on a handful of L2 slices, and the
+// 1.2e7 reservation atomics of a 1e8-row pass saturated exactly those (lts__throughput max 105 %, avg 33 %;
+// lts__d_atomic_input_cycles_active max 58 %: profiles/r02e_c3_dense16_ncu_summary.txt)
+uint32_t part_cursor_stride() { return 64u; }
 uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
   const uint64_t round = val ? 2048 : 4096;
   const uint64_t rounds = (n + round - 1) / round;
@@ -359,7 +364,7 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= 0xFFFFull) return false;
   if ((x.n + 2047) / 2048 > 0xFFFFFFF0ull / 8) return false;
   PartParams a;
-  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor;
+  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor; a.cstride = x.cursor_stride;
   a.ctl = x.ctl;
   for (int i = 0; i < PT_MAXW; ++i) a.outs[i] = i < x.world ? x.outs[i] : nullptr;
   a.logp = x.logp; a.lpo = x.lpo; a.nsub = x.nsub; a.sub = x.sub;
@@ -395,7 +400,7 @@ struct SjoinParams {
   const unsigned char* probe;  // regions of cap_p 2-byte elements
   const uint32_t* pcnt;
   uint64_t cap_p;
-  uint32_t cnt_stride;
+  uint32_t cnt_stride, cstride;  // cursor of (sub, p) = cnt[(sub * cnt_stride + p) * cstride]
   uint32_t p_first, p_count;   // partitions joined here: global ids p_first .. p_first + p_count - 1
   int logp, nsub;
   uint32_t slots;              // slots a build row can address (multiple of 8): only these are zeroed
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   auto side_total = [&](const uint32_t* cnt, uint64_t cap, uint32_t l) -> uint64_t {
     uint64_t t = 0;
     for (int sub = 0; sub < a.nsub; ++sub) {
-      uint64_t c = cnt[(size_t)sub * a.cnt_stride + a.p_first + l];
+      uint64_t c = cnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
       t += c < cap ? c : cap;
     }
     return t;
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         const uint32_t eb = side ? 2u : EB;
         const unsigned char* base = side ? a.probe : a.build;
         for (int sub = 0; sub < a.nsub; ++sub) {
-          uint64_t c = cnt[(size_t)sub * a.cnt_stride + a.p_first + l];
+          uint64_t c = cnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
           if (c > cap) c = cap;
           const uint64_t bytes_total = c * eb;  // multiple of 32 (sectors)
           const unsigned char* src = base + ((uint64_t)l * (uint32_t)a.nsub + (uint32_t)sub) * cap * eb;
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     sj_bar_consumers();
     // ---- fill: region[idx] = value + 1
     for (int sub = 0; sub < a.nsub; ++sub) {
-      uint64_t c = a.bcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
+      uint64_t c = a.bcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
       if (c > a.cap_b) c = a.cap_b;
       const uint32_t bytes_total = (uint32_t)(c * EB);
       for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     // ---- probe, pass 1: count
     uint32_t mine = 0;
     for (int sub = 0; sub < a.nsub; ++sub) {
-      uint64_t c = a.pcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
+      uint64_t c = a.pcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
       if (c > a.cap_p) c = a.cap_p;
       const uint32_t bytes_total = (uint32_t)(c * 2u);
       for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
       unsigned long long* const ovp = a.out_vals + s_base;
       // ---- probe, pass 2: emit
       for (int sub = 0; sub < a.nsub; ++sub) {
-        uint64_t c = a.pcnt[(size_t)sub * a.cnt_stride + a.p_first + l];
+        uint64_t c = a.pcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
         if (c > a.cap_p) c = a.cap_p;
         const uint32_t bytes_total = (uint32_t)(c * 2u);
         for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
@@ -660,7 +665,7 @@ bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream
   SjoinParams a;
   a.build = static_cast<const unsigned char*>(x.build); a.bcnt = x.bcnt; a.cap_b = x.cap_b;
   a.probe = static_cast<const unsigned char*>(x.probe); a.pcnt = x.pcnt; a.cap_p = x.cap_p;
-  a.cnt_stride = x.cnt_stride; a.p_first = x.p_first; a.p_count = x.p_count; a.logp = x.logp; a.nsub = x.nsub;
+  a.cnt_stride = x.cnt_stride; a.cstride = x.cursor_stride; a.p_first = x.p_first; a.p_count = x.p_count; a.logp = x.logp; a.nsub = x.nsub;
   a.slots = x.slots_alloc; a.ctl = x.ctl; a.out_keys = x.out_keys; a.out_vals = x.out_vals;
   const size_t smem = sjoin_smem_bytes(x.slots_alloc);
   if (smem + 256 > di.smem_optin || (x.slots_alloc & 7u) || x.slots_alloc > 65528u) return false;

@@ -85,6 +85,8 @@ py::dict last_stats() {
   d["radix_bits"] = py::make_tuple(s.radix_bits1, s.radix_bits2);
   d["n_gpus"] = s.n_gpus;
   d["dense"] = s.dense;
+  d["part_build_us"] = s.part_build_us;
+  d["part_probe_us"] = s.part_probe_us;
   return d;
 }
 

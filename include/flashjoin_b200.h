@@ -87,8 +87,11 @@ typedef struct fj_stats {
   int32_t radix_bits1, radix_bits2; /* fan-out of the radix passes (0 = pass not run)              */
   int32_t n_gpus;
   int32_t dense;       /* 1 = a dense-key-domain fast path produced the result (bitmap count or     */
-                       /* direct-address radix join); 0 = the general hash path                    */
-  int32_t reserved[6];
+                       /* L2-resident direct-address radix join), 2 = the one-pass partition +     */
+                       /* shared-memory direct-address join (k_part / k_sjoin); 0 = general path   */
+  int32_t part_build_us; /* radix path: device time of the build-side partition pass(es), microseconds         */
+  int32_t part_probe_us; /* radix path: device time of the probe-side partition pass(es), microseconds         */
+  int32_t reserved[4];
 } fj_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------
