@@ -174,6 +174,7 @@ struct PartArgs {
   uint64_t cap = 0;      // elements per (partition, sub-region), multiple of 16
   uint32_t* cursor = nullptr;  // [2^logp * cursor_stride], zeroed: elements reserved per partition by THIS source
   uint32_t cursor_stride = 1;  // 32-bit words between two cursors
+  unsigned long long* trace = nullptr;  // developer aid: 8 device counters (cycles per phase), nullptr = off
   Ctl* ctl = nullptr;
   void* outs[8] = {};    // [world] base of every owner's partition buffer
   int world = 1;

@@ -63,6 +63,7 @@ struct PartParams {
   uint32_t cap;        // elements per (partition, sub-region); multiple of 16
   uint32_t* cursor;    // [P * cstride] elements reserved per partition (this source)
   uint32_t cstride;    // 32-bit words between two cursors (see fj_kernels.h: part_cursor_stride)
+  unsigned long long* trace;  // developer aid: 8 cycle counters summed over lane 0 of every warp (nullptr = off)
   Ctl* ctl;
   void* outs[PT_MAXW]; // base of every owner's partition buffer (peer-mapped for remote owners)
   int logp;            // log2(partitions)
@@ -84,8 +85,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   constexpr uint32_t ROUND = PT_RS * SROWS;           // rows per round: 2048 | 4096
   constexpr int IPT = ROUND / PT_THREADS;             // rows per thread and round: 4 | 8
   constexpr int PER = IPT / PT_RS;                    // rows per thread and ring stage
-  constexpr int WCAP = 128;                           // flush-list entries per warp
-  constexpr int NQ = WCAP / 32;                       // flush-list entries per lane
+  constexpr int WCAP = 64;                            // flush-list entries per warp (16 expected)
+  constexpr int NQ = WCAP / 16;                       // flush steps: a pair of lanes per entry, 16 entries per step
   constexpr ET HOLE = (ET)~(ET)0;
   constexpr uint32_t NOPLACE = 0xFFFFu;               // nextg: the reservation lies beyond the region
   extern __shared__ __align__(128) unsigned char smem[];
@@ -144,10 +145,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   }
 
   unsigned char* const out0 = static_cast<unsigned char*>(a.outs[0]);  // owner 0 (the only one on a single GPU): no table lookup
-  // one 32-byte sector of partition d: shared memory -> sector gs of its sub-region in the owner's buffer
-  auto store_sector = [&](uint32_t d, uint32_t sec, uint32_t gs) {
+  // half h (16 bytes) of one 32-byte sector of partition d: shared memory -> sector gs of its sub-region in the owner's
+  // buffer.  Two lanes share a sector, so a warp moves 16 sectors with ONE 128-bit load and ONE 128-bit store (a lane
+  // per sector took two of each, and every such instruction costs the LSU one pass per sector it touches).
+  auto store_half = [&](uint32_t d, uint32_t sec, uint32_t gs, uint32_t h) {
     if (gs == NOPLACE) {
-      atomicOr(&a.ctl->flags, CTL_OVERFLOW);
+      if (h == 0) atomicOr(&a.ctl->flags, CTL_OVERFLOW);
       return;
     }
     const unsigned char* src = buf + d * PT_RINGB + sec * PT_SECTOR;
@@ -155,11 +158,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     const uint32_t owner = d >> a.lpo;
     unsigned char* dst = (owner ? s_outs[owner] : out0) + (((uint64_t)region * capsec + gs) << 5);
     if constexpr (TMAST) {
-      bulk_s2g(dst, src, PT_SECTOR);
+      if (h == 0) bulk_s2g(dst, src, PT_SECTOR);
     } else {
-      const uint4 x = reinterpret_cast<const uint4*>(src)[0], y = reinterpret_cast<const uint4*>(src)[1];
-      reinterpret_cast<uint4*>(dst)[0] = x;
-      reinterpret_cast<uint4*>(dst)[1] = y;
+      reinterpret_cast<uint4*>(dst)[h] = reinterpret_cast<const uint4*>(src)[h];
     }
   };
 
@@ -252,41 +253,53 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     if constexpr (TMAST) fence_proxy_async();  // staged rows become visible to the bulk-copy engine
     return wn < (uint32_t)WCAP ? wn : (uint32_t)WCAP;
   };
-  // one listed partition: its full sector(s) leave for the place reserved in advance; the reservation of the NEXT
-  // flush is issued here and consumed an iteration later (q >= 0), or waited for (q < 0: the rare overflow path)
-  auto flush_one = [&](uint32_t d, int q) {
+  // one listed partition: its full sector(s) leave for the place reserved in advance.  Executed by a PAIR of lanes
+  // (h = 0, 1: one half of the sector each; `solo`: one lane does both halves — the rare list-overflow path).  Lane
+  // h == 0 also issues the reservation of the partition's NEXT flush, consumed an iteration later (q >= 0) or
+  // waited for (solo).
+  auto flush_entry = [&](uint32_t d, int q, uint32_t h, bool solo) {
     const uint32_t ww = w[d];
     const uint32_t gs = nextg[d];
     uint32_t cnt = ww >> 1;
     if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
     const uint32_t tog = ww & 1u;
     const uint32_t nsec = cnt >> LOG_EPS;  // 1 or 2
-    store_sector(d, tog, gs);
-    if (nsec == 2) store_sector(d, tog ^ 1u, to_sector(atomicAdd(a.cursor + d * a.cstride, EPS)));  // rare: both sectors filled at once
-    w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
-    if (q >= 0) {
-      // The reservation's round trip through L2 (1 - 2 us under load) must not be waited for in this phase: the
-      // atomic writes straight into the register that is read an iteration later (a C++ temporary made ptxas
-      // park the warp on a MOV right here: 12 % of all stall samples, profiles/r02d_c3_dense16_ncu_summary.txt)
-      asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[q]) : "l"(a.cursor + d * a.cstride), "r"(EPS) : "memory");
-      pd[q] = d;
-      pvalid |= 1u << q;
-    } else {
-      nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
+    store_half(d, tog, gs, h);
+    if (solo) store_half(d, tog, gs, 1u);
+    if (nsec == 2) {  // rare: both sectors filled within one iteration
+      uint32_t g1 = 0;
+      if (h == 0) g1 = atomicAdd(a.cursor + d * a.cstride, EPS);
+      if (!solo) g1 = __shfl_sync(3u << (lane & 30u), g1, lane & 30u);  // both lanes of the pair are here (same d, same ww)
+      const uint32_t gs1 = to_sector(g1);
+      store_half(d, tog ^ 1u, gs1, h);
+      if (solo) store_half(d, tog ^ 1u, gs1, 1u);
+    }
+    if (h == 0) {
+      w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
+      if (!solo) {
+        // The reservation's round trip through L2 (1 - 2 us under load) must not be waited for in this phase: the
+        // atomic writes straight into the register that is read an iteration later (a C++ temporary made ptxas
+        // park the warp on a MOV right here: 12 % of all stall samples, profiles/r02d_c3_dense16_ncu_summary.txt)
+        asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[q]) : "l"(a.cursor + d * a.cstride), "r"(EPS) : "memory");
+        pd[q] = d;
+        pvalid |= 1u << q;
+      } else {
+        nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
+      }
     }
   };
-  // ---- flush: every warp flushes the partitions on its own list, one per lane
+  // ---- flush: every warp flushes the partitions on its own list, sixteen per step
   auto flush = [&](const Rows& r, uint32_t wn, uint32_t ovf) {
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const uint32_t j = (uint32_t)q * 32u + lane;
-      if (j < wn) flush_one(wlist[j], q);
+      const uint32_t j = (uint32_t)q * 16u + (lane >> 1);
+      if (j < wn) flush_entry(wlist[j], q, lane & 1u, false);
     }
     if (ovf) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
-        if ((ovf >> i) & 1u) flush_one(r.d[i], -1);
+        if ((ovf >> i) & 1u) flush_entry(r.d[i], 0, 0u, true);
     }
     if constexpr (TMAST) {
       bulk_commit();
@@ -297,30 +310,51 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   Rows cur, nxt;
   uint32_t k = 0;
   uint32_t R = blockIdx.x;
+  long long tr[6] = {0, 0, 0, 0, 0, 0};
+  auto tick = [&](long long& t0, int seg) {
+    if (a.trace) {
+      const long long t1 = clock64();
+      tr[seg] += t1 - t0;
+      t0 = t1;
+    }
+  };
   if (R < rounds) load_round(R, 0, cur);
+  long long t0 = a.trace ? clock64() : 0;
   while (R < rounds) {
     uint32_t ovf;
     uint32_t wn = place(cur, ovf);
+    tick(t0, 0);
     __syncthreads();  // #1: every row of this iteration is staged
+    tick(t0, 1);
     if (tid == 0) {
       // the ring stages of THIS round were read before the previous barrier #2: refill them
       issue(k * PT_RS + PT_STAGES);
       issue(k * PT_RS + 1 + PT_STAGES);
     }
     flush(cur, wn, ovf);
+    tick(t0, 2);
     // the rows of the next round are fetched and decoded before the barrier: warps that finish their flush early go ahead
     const uint32_t Rn = R + G;
     if (Rn < rounds) load_round(Rn, k + 1, nxt);
+    tick(t0, 3);
     int any = __syncthreads_or(cur.pend != 0);  // #2: the flushed rings are consistent again
+    tick(t0, 4);
     while (any) {  // some ring was full (more than a ring's worth of rows for one partition within a round): retry
       wn = place(cur, ovf);
       __syncthreads();
       flush(cur, wn, ovf);
       any = __syncthreads_or(cur.pend != 0);
+      tick(t0, 5);
     }
     cur = nxt;
     R = Rn;
     ++k;
+  }
+  if (a.trace && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) atomicAdd(a.trace + i, (unsigned long long)tr[i]);
+    atomicAdd(a.trace + 6, (unsigned long long)k);
+    atomicAdd(a.trace + 7, 1ull);
   }
 
   // ---- drain: pad every partial sector with holes and flush it into the sector held in reserve
@@ -334,7 +368,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     ET* sec = reinterpret_cast<ET*>(buf + d * PT_RINGB + tog * PT_SECTOR);
     for (uint32_t j = cnt; j < EPS; ++j) sec[j] = HOLE;
     if constexpr (TMAST) fence_proxy_async();
-    store_sector(d, tog, nextg[d]);
+    store_half(d, tog, nextg[d], 0u);
+    store_half(d, tog, nextg[d], 1u);
   }
   if constexpr (TMAST) {
     bulk_commit();
@@ -346,7 +381,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
 }
 
 size_t part_smem_bytes(int logp) {
-  return ((size_t)1 << logp) * (PT_RINGB + 6) + (PT_THREADS / 32) * 128 * 2 + (size_t)PT_STAGES * PT_STAGE_BYTES;
+  return ((size_t)1 << logp) * (PT_RINGB + 6) + (PT_THREADS / 32) * 64 * 2 + (size_t)PT_STAGES * PT_STAGE_BYTES;
 }
 uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
 // One cursor per 256 bytes: 2048 adjacent 4-byte cursors live in 64 cache lines, i.e. on a handful of L2 slices, and the
@@ -364,7 +399,7 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= 0xFFFFull) return false;
   if ((x.n + 2047) / 2048 > 0xFFFFFFF0ull / 8) return false;
   PartParams a;
-  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor; a.cstride = x.cursor_stride;
+  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor; a.cstride = x.cursor_stride; a.trace = x.trace;
   a.ctl = x.ctl;
   for (int i = 0; i < PT_MAXW; ++i) a.outs[i] = i < x.world ? x.outs[i] : nullptr;
   a.logp = x.logp; a.lpo = x.lpo; a.nsub = x.nsub; a.sub = x.sub;
