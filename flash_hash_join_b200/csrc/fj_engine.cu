@@ -172,8 +172,6 @@ struct Engine {
     cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
     cfg["dense16"] = 1;             // radix path, dense key domain: one high-fan-out pass + shared-memory direct-address join (k_part / k_sjoin)
     cfg["dense16_logp"] = 0;        // 0 = derive the partition count from the build size; else log2(partitions), 8..11
-    cfg["part_trace"] = 0;          // developer aid: print k_part phase cycle counters to stderr
-    cfg["part_tma_store"] = 0;      // k_part: flush sectors with cp.async.bulk shared -> global instead of LDS + STG
     // FJ_CFG_<KEY>=<integer> in the environment overrides a default (e.g. FJ_CFG_DENSE=0)
     for (auto& kv : cfg) {
       std::string name = "FJ_CFG_";
@@ -853,19 +851,10 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   FJ_CUDA(cudaEventRecord(ev[1], st));
   PartArgs a;
   a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = a.lpo = dp.logp; a.world = 1; a.nsub = 1; a.sub = 0;
-  a.tma_store = cfg["part_tma_store"] != 0;
   a.cursor_stride = cs;
-  unsigned long long* d_trace = nullptr;
-  if (cfg["part_trace"]) {
-    FJ_TRY(dist_scratch.ensure(256));
-    d_trace = dist_scratch.as<unsigned long long>();
-    FJ_CUDA(cudaMemsetAsync(d_trace, 0, 128, st));
-  }
-  a.trace = d_trace;
   a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.outs[0] = part_a_b.p; a.strict = true;
   bool launched = launch_part(mat, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[12], st));
-  if (d_trace) a.trace = d_trace + 8;
   a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.outs[0] = part_a_p.p; a.strict = false;
   launched = launched && launch_part(false, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[2], st));
@@ -885,17 +874,6 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
   if (!launched) h_ctl->flags |= CTL_NOT_DENSE16;  // no launch configuration: the next layout answers
-  if (d_trace) {
-    unsigned long long h[16];
-    FJ_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int side = 0; side < 2; ++side) {
-      const unsigned long long* t = h + 8 * side;
-      const double rounds = t[7] ? (double)t[6] / (double)t[7] : 0.0, w = t[7] ? (double)t[7] : 1.0;
-      fprintf(stderr, "k_part trace %s: rounds/warp %.1f; cycles per round: place %.0f bar1 %.0f flush %.0f load %.0f bar2 %.0f retry %.0f\n",
-              side ? "probe" : "build", rounds, t[0] / w / rounds, t[1] / w / rounds, t[2] / w / rounds, t[3] / w / rounds, t[4] / w / rounds,
-              t[5] / w / rounds);
-    }
-  }
   s->clear_s += ms(0, 1) * 1e-3;
   s->partition_s += ms(1, 2) * 1e-3;
   s->probe_s += ms(2, 3) * 1e-3;

@@ -174,14 +174,12 @@ struct PartArgs {
   uint64_t cap = 0;      // elements per (partition, sub-region), multiple of 16
   uint32_t* cursor = nullptr;  // [2^logp * cursor_stride], zeroed: elements reserved per partition by THIS source
   uint32_t cursor_stride = 1;  // 32-bit words between two cursors
-  unsigned long long* trace = nullptr;  // developer aid: 8 device counters (cycles per phase), nullptr = off
   Ctl* ctl = nullptr;
   void* outs[8] = {};    // [world] base of every owner's partition buffer
   int world = 1;
   int logp = 11, lpo = 11;  // log2(partitions), log2(partitions per owner)
   int nsub = 1, sub = 0;    // sub-regions per partition (= sources), this source's index
   bool strict = false;
-  bool tma_store = false;   // sectors leave with cp.async.bulk shared -> global instead of LDS + STG
 };
 size_t part_smem_bytes(int logp);
 uint32_t part_sector_elems(bool val);

@@ -45,15 +45,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // ================================================================================= k_part
-constexpr int PT_THREADS = 512;               // 16 warps x 4 | 8 rows per thread and round: per-warp overheads (waits, barriers,
-                                              // flush-list checks) are paid once per 128 | 256 rows (profiles/r02b: 1024 x 2 rows was issue bound)
-constexpr int PT_STAGE_BYTES = 16384;         // one ring stage: 2048 keys, or 1024 keys + 1024 values
-constexpr int PT_STAGES = 5;
-constexpr int PT_RS = 2;                      // ring stages per round
+constexpr int PT_THREADS = 512;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_SLOT_BYTES = 2048;           // one batch of one warp: 256 keys, or 128 keys + 128 values
+constexpr int PT_WSLOTS = 2;                  // input ring slots per warp
 constexpr int PT_SECTOR = 32;                 // bytes per flush
 constexpr int PT_RINGB = 2 * PT_SECTOR;       // bytes of staging per partition
-constexpr int PT_MAXP = 2048;
+constexpr int PT_MAXP = 2048;                 // flush-list entries keep the partition in 11 bits
 constexpr int PT_MAXW = 8;                    // owners (GPUs) a pass can store to
+constexpr int PT_KEEP = 32;                   // flush-list entries a warp may carry into its next batch
+constexpr int PT_WCAP = 32 * 8 + PT_KEEP;     // flush-list entries per warp: every row of a batch may complete a sector
+constexpr int PT_NQ = 4;                      // sector reservations in flight per lane pair
+constexpr uint32_t PT_NOPLACE = 0xFFFFu;      // nextg: the reservation lies beyond the region
+constexpr uint32_t PT_INFLIGHT = 0xFFFEu;     // nextg: the reservation has been issued, its answer is not published yet
 
 struct PartParams {
   const unsigned long long* in_keys;
@@ -63,7 +67,6 @@ struct PartParams {
   uint32_t cap;        // elements per (partition, sub-region); multiple of 16
   uint32_t* cursor;    // [P * cstride] elements reserved per partition (this source)
   uint32_t cstride;    // 32-bit words between two cursors (see fj_kernels.h: part_cursor_stride)
-  unsigned long long* trace;  // developer aid: 8 cycle counters summed over lane 0 of every warp (nullptr = off)
   Ctl* ctl;
   void* outs[PT_MAXW]; // base of every owner's partition buffer (peer-mapped for remote owners)
   int logp;            // log2(partitions)
@@ -71,39 +74,79 @@ struct PartParams {
   int nsub, sub;       // sub-regions per partition on the owner (= sources) and this source's index
 };
 
+__device__ __forceinline__ uint32_t lds_v32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_v16(const void* p) {
+  uint16_t v;
+  asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v128(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+// does a 16-byte piece of a staged sector still hold an unwritten (all-ones) element?
+template <bool VAL>
+__device__ __forceinline__ bool piece_has_hole(const uint4& v) {
+  if constexpr (VAL) {
+    return max(max(v.x, v.y), max(v.z, v.w)) == 0xFFFFFFFFu;
+  } else {
+    const uint32_t m = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
+    return (m & 0xFFFFu) == 0xFFFFu || (m >> 16) == 0xFFFFu;
+  }
+}
+
 // VAL: rows carry a value (element = idx | value << 16, 4 bytes) else keys only (element = idx, 2 bytes)
 // STRICT: build side — a key >= klimit or a value > 65534 abandons the attempt (CTL_NOT_DENSE16); else such rows are dropped
-// TMAST: sectors leave shared memory with cp.async.bulk shared -> global instead of LDS.128 + STG.128
-template <bool VAL, bool STRICT, bool TMAST>
+//
+// Staging protocol (no block barrier in the main loop; the 16 warps run independently):
+//   * w[d] = tail << 16 | count.  tail = elements of partition d flushed so far (mod 2^16, a multiple of the sector size),
+//     count = elements claimed and not flushed.  A row claims ticket T = tail + count with ONE shared-memory atomicAdd and
+//     owns ring slot T mod 16|32 (two sectors).  count < two sectors: the slot is free, the row is stored at once;
+//     otherwise the row keeps its ticket and is stored as soon as the tail has advanced far enough (`pending`).
+//   * A free slot holds the all-ones hole marker (no valid element equals it).  The row whose ticket is the LAST of a
+//     sector (the closer) puts (d, sector number) on its warp's flush list.  A listed sector leaves when it is the oldest
+//     of its partition (tail == its first ticket: sectors of a partition leave in order), holds no hole marker any more
+//     (every claimed row has been stored) and the partition's next global sector is known.  The flusher resets the
+//     sector to hole markers, THEN advances the tail (one atomicAdd: tail += sector, count -= sector), and issues the
+//     reservation of the partition's next global sector, whose answer is published a batch later.
+//   * Entries that cannot leave yet stay on the list; a warp never blocks (on input data, on a pending row) without
+//     servicing its list, so the oldest sector of every partition can always make progress.
+template <bool VAL, bool STRICT>
 __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   using ET = std::conditional_t<VAL, uint32_t, uint16_t>;
   constexpr uint32_t ES = sizeof(ET);
   constexpr uint32_t EPS = PT_SECTOR / ES;            // elements per sector: 8 | 16
   constexpr uint32_t LOG_EPS = VAL ? 3 : 4;
   constexpr uint32_t SLOTS = 2 * EPS;
-  constexpr uint32_t SROWS = VAL ? 1024 : 2048;       // rows per ring stage
-  constexpr uint32_t ROUND = PT_RS * SROWS;           // rows per round: 2048 | 4096
-  constexpr int IPT = ROUND / PT_THREADS;             // rows per thread and round: 4 | 8
-  constexpr int PER = IPT / PT_RS;                    // rows per thread and ring stage
-  constexpr int WCAP = 64;                            // flush-list entries per warp (16 expected)
-  constexpr int NQ = WCAP / 16;                       // flush steps: a pair of lanes per entry, 16 entries per step
-  constexpr ET HOLE = (ET)~(ET)0;
-  constexpr uint32_t NOPLACE = 0xFFFFu;               // nextg: the reservation lies beyond the region
+  constexpr uint32_t BROWS = PT_SLOT_BYTES / (VAL ? 16 : 8);  // rows per warp batch: 128 | 256
+  constexpr int IPT = BROWS / 32;                     // rows per thread and batch: 4 | 8
+  constexpr uint32_t FLUSH_ADD = (EPS << 16) - EPS;   // tail += EPS, count -= EPS (count >= EPS: no borrow)
+  constexpr uint32_t SPIN_LIMIT = 1u << 22;           // a protocol error must trap, not hang the GPU
+  static_assert(32 * IPT + PT_KEEP <= PT_WCAP, "flush list too small");
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = 1u << a.logp;
   unsigned char* buf = smem;                                               // P x 64 B: two sectors per partition
-  uint32_t* w = reinterpret_cast<uint32_t*>(smem + (size_t)P * PT_RINGB);  // P: elements in the ring << 1 | first sector
+  uint32_t* w = reinterpret_cast<uint32_t*>(smem + (size_t)P * PT_RINGB);  // P: tail << 16 | count
   uint16_t* nextg = reinterpret_cast<uint16_t*>(w + P);                    // P: sector (in the sub-region) reserved for the next flush
-  uint16_t* wlist = nextg + P + (threadIdx.x >> 5) * WCAP;                 // per warp: partitions whose first sector its rows completed
-  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 6) + (PT_THREADS / 32) * WCAP * 2;  // PT_STAGES x 16 KB
-  __shared__ __align__(8) uint64_t s_full[PT_STAGES];
+  uint32_t* wl = reinterpret_cast<uint32_t*>(nextg + P) + (threadIdx.x >> 5) * PT_WCAP;  // this warp's flush list: d | sector number << 11
+  // every warp streams its own batches through its own PT_WSLOTS x 2 KB input ring (a ring shared by the CTA is refilled
+  // only when the slowest warp has read a stage: the warps starved, profiles/r02h_c3_dense16_ncu_summary.txt)
+  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 6) + (size_t)PT_WARPS * PT_WCAP * 4 + (size_t)(threadIdx.x >> 5) * PT_WSLOTS * PT_SLOT_BYTES;
+  __shared__ __align__(8) uint64_t s_full[PT_WARPS * PT_WSLOTS];
   __shared__ unsigned char* s_outs[PT_MAXW];
 
-  const uint32_t tid = threadIdx.x;
-  const uint32_t G = gridDim.x;
-  const uint32_t rounds = (uint32_t)((a.n + ROUND - 1) / ROUND);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wv = tid >> 5, h = tid & 1u;
+  const uint32_t GW = gridDim.x * PT_WARPS;          // warps of the grid
+  const uint32_t gw = blockIdx.x * PT_WARPS + wv;    // this warp: batches gw, gw + GW, gw + 2 GW, ...
+  const uint32_t nbatch = (uint32_t)((a.n + BROWS - 1) / BROWS);
   const bool aligned = ((reinterpret_cast<uintptr_t>(a.in_keys) | (VAL ? reinterpret_cast<uintptr_t>(a.in_vals) : 0)) & 15u) == 0;
-  const uint32_t nfull = aligned ? (uint32_t)(a.n / ROUND) : 0u;  // rounds below nfull arrive through the TMA ring
+  const uint32_t nfull = aligned ? (uint32_t)(a.n / BROWS) : 0u;  // batches below nfull arrive through the TMA ring
+  uint64_t* const my_full = s_full + wv * PT_WSLOTS;
   const uint32_t lpo_mask = (1u << a.lpo) - 1u;
   const uint32_t capsec = a.cap >> LOG_EPS;
   const uint32_t pmask = P - 1u;
@@ -111,269 +154,251 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < PT_MAXW; ++i) s_outs[i] = static_cast<unsigned char*>(a.outs[i]);  // static indices: no local copy
-#pragma unroll
-    for (int s = 0; s < PT_STAGES; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < PT_WARPS * PT_WSLOTS; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
-  // reservation -> sector index inside the (partition, source) sub-region; NOPLACE when it does not fit
-  auto to_sector = [&](uint32_t g) -> uint16_t { return g + EPS <= a.cap ? (uint16_t)(g >> LOG_EPS) : (uint16_t)NOPLACE; };
-  // every (CTA, partition) holds one sector reserved in advance
+  // reservation -> sector index inside the (partition, source) sub-region; PT_NOPLACE when it does not fit
+  auto to_sector = [&](uint32_t g) -> uint16_t { return g + EPS <= a.cap ? (uint16_t)(g >> LOG_EPS) : (uint16_t)PT_NOPLACE; };
+  // every slot free, every (CTA, partition) holds one sector reserved in advance
+  for (uint32_t i = tid; i < P * (PT_RINGB / 16); i += PT_THREADS) reinterpret_cast<uint4*>(buf)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
     w[d] = 0;
     nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
   }
   __syncthreads();
 
-  // local ring stage c (c = 0, 1, 2, ... in consumption order) <-> round blockIdx + (c / RS) * G, stage c % RS of it
-  auto issue = [&](uint32_t c) {  // thread 0
-    const uint32_t R = blockIdx.x + (c / PT_RS) * G;
-    if (R >= nfull) return;
-    const int s = c % PT_STAGES;
-    const uint64_t row0 = (uint64_t)R * ROUND + (uint64_t)(c % PT_RS) * SROWS;
-    unsigned char* dst = ring + (size_t)s * PT_STAGE_BYTES;
-    mbar_expect_tx(&s_full[s], PT_STAGE_BYTES);
-    if constexpr (VAL) {
-      bulk_g2s(dst, a.in_keys + row0, SROWS * 8u, &s_full[s]);
-      bulk_g2s(dst + SROWS * 8u, a.in_vals + row0, SROWS * 8u, &s_full[s]);
-    } else {
-      bulk_g2s(dst, a.in_keys + row0, SROWS * 8u, &s_full[s]);
-    }
+  // this warp's batch number kk (batch gw + kk * GW of the input) -> ring slot kk % PT_WSLOTS
+  auto issue = [&](uint32_t kk) {  // one lane
+    const uint32_t B = gw + kk * GW;
+    if (B >= nfull) return;
+    const uint32_t s = kk % PT_WSLOTS;
+    const uint64_t row0 = (uint64_t)B * BROWS;
+    unsigned char* dst = ring + s * PT_SLOT_BYTES;
+    mbar_expect_tx(&my_full[s], PT_SLOT_BYTES);
+    bulk_g2s(dst, a.in_keys + row0, BROWS * 8u, &my_full[s]);
+    if constexpr (VAL) bulk_g2s(dst + BROWS * 8u, a.in_vals + row0, BROWS * 8u, &my_full[s]);
   };
-  if (tid == 0) {
+  if (lane == 0) {
 #pragma unroll
-    for (uint32_t c = 0; c < PT_STAGES; ++c) issue(c);
+    for (uint32_t kk = 0; kk < PT_WSLOTS; ++kk) issue(kk);
   }
 
   unsigned char* const out0 = static_cast<unsigned char*>(a.outs[0]);  // owner 0 (the only one on a single GPU): no table lookup
-  // half h (16 bytes) of one 32-byte sector of partition d: shared memory -> sector gs of its sub-region in the owner's
-  // buffer.  Two lanes share a sector, so a warp moves 16 sectors with ONE 128-bit load and ONE 128-bit store (a lane
-  // per sector took two of each, and every such instruction costs the LSU one pass per sector it touches).
-  auto store_half = [&](uint32_t d, uint32_t sec, uint32_t gs, uint32_t h) {
-    if (gs == NOPLACE) {
-      if (h == 0) atomicOr(&a.ctl->flags, CTL_OVERFLOW);
+  // half hh (16 bytes) of one 32-byte sector of partition d -> sector gs of its sub-region in the owner's buffer.  Two
+  // lanes share a sector, so a warp moves 16 sectors with ONE 128-bit store.
+  auto store_half = [&](uint32_t d, uint32_t gs, uint32_t hh, const uint4& v) {
+    if (gs == PT_NOPLACE) {
+      if (hh == 0) atomicOr(&a.ctl->flags, CTL_OVERFLOW);
       return;
     }
-    const unsigned char* src = buf + d * PT_RINGB + sec * PT_SECTOR;
     const uint32_t region = (d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
     const uint32_t owner = d >> a.lpo;
     unsigned char* dst = (owner ? s_outs[owner] : out0) + (((uint64_t)region * capsec + gs) << 5);
-    if constexpr (TMAST) {
-      if (h == 0) bulk_s2g(dst, src, PT_SECTOR);
-    } else {
-      reinterpret_cast<uint4*>(dst)[h] = reinterpret_cast<const uint4*>(src)[h];
-    }
+    reinterpret_cast<uint4*>(dst)[hh] = v;
   };
 
   struct Rows {
     uint32_t d[IPT];
     uint32_t e[IPT];
-    uint32_t pend;
+    uint32_t pend;  // rows not stored yet
   };
   bool bad = false;
   // digit, element and validity of one row
-  auto decode = [&](uint2 kk, uint2 vv, bool ok, int i, Rows& r) {
-    bool in = (kk.y == 0u) & (kk.x < a.klimit);
-    if constexpr (VAL) in &= (vv.y == 0u) & (vv.x <= 65534u);
+  auto decode = [&](uint32_t klo, uint32_t khi, uint32_t vlo, uint32_t vhi, bool ok, int i, Rows& r) {
+    bool in = (khi == 0u) & (klo < a.klimit);
+    if constexpr (VAL) in &= (vhi == 0u) & (vlo <= 65534u);
     if constexpr (STRICT) bad |= ok & !in;
     ok &= in;
-    r.d[i] = kk.x & pmask;
-    r.e[i] = (kk.x >> a.logp) | (VAL ? vv.x << 16 : 0u);
+    r.d[i] = klo & pmask;
+    r.e[i] = (klo >> a.logp) | (VAL ? vlo << 16 : 0u);
     r.pend |= ok ? (1u << i) : 0u;
   };
-  // the rows of round R (local round k).  Full rounds of 16-byte aligned inputs come out of the TMA ring: stage
-  // j = i / PER of the round, row (i % PER) * 512 + tid of it; the ragged tail / unaligned inputs are loaded directly.
-  auto load_round = [&](uint32_t R, uint32_t k, Rows& r) {
+  // has batch B (this warp's batch number kk) arrived?  (warp-uniform)
+  auto batch_ready = [&](uint32_t B, uint32_t kk) -> bool {
+    if (B >= nfull) return true;
+    return __all_sync(0xffffffffu, mbar_try_wait(&my_full[kk % PT_WSLOTS], (kk / PT_WSLOTS) & 1u));
+  };
+  // the rows of batch B.  Full batches of 16-byte aligned inputs come out of the warp's ring slot (which must be ready):
+  // a lane reads pairs of adjacent rows with 128-bit loads; the slot is refilled as soon as it has been read.  The
+  // ragged tail / unaligned inputs are loaded directly.
+  auto load_rows = [&](uint32_t B, uint32_t kk, Rows& r) {
     r.pend = 0;
-    if (R < nfull) {
+    if (B < nfull) {
+      const uint4* st = reinterpret_cast<const uint4*>(ring + (kk % PT_WSLOTS) * PT_SLOT_BYTES);
+      uint4 k2[IPT / 2], v2[IPT / 2];
 #pragma unroll
-      for (int j = 0; j < PT_RS; ++j) {
-        const uint32_t c = k * PT_RS + j;
-        mbar_wait_bounded(&s_full[c % PT_STAGES], (c / PT_STAGES) & 1u);
-        const uint2* st = reinterpret_cast<const uint2*>(ring + (c % PT_STAGES) * PT_STAGE_BYTES);
-        uint2 kk[PER], vv[PER];
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-          kk[q] = st[q * PT_THREADS + tid];
-          vv[q] = VAL ? st[SROWS + q * PT_THREADS + tid] : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int q = 0; q < PER; ++q) decode(kk[q], vv[q], true, j * PER + q, r);
+      for (int q = 0; q < IPT / 2; ++q) {
+        k2[q] = st[q * 32 + lane];
+        v2[q] = VAL ? st[BROWS / 2 + q * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
       }
+#pragma unroll
+      for (int q = 0; q < IPT / 2; ++q) {
+        decode(k2[q].x, k2[q].y, v2[q].x, v2[q].y, true, 2 * q, r);
+        decode(k2[q].z, k2[q].w, v2[q].z, v2[q].w, true, 2 * q + 1, r);
+      }
+      __syncwarp();  // every lane's loads have returned
+      if (lane == 0) issue(kk + PT_WSLOTS);
     } else {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
-        const uint64_t row = (uint64_t)R * ROUND + (uint64_t)i * PT_THREADS + tid;
+        const uint64_t row = (uint64_t)B * BROWS + (uint64_t)i * 32u + lane;
         const bool ok = row < a.n;
         unsigned long long k64 = ~0ull, v64 = 0;
         if (ok) {
           k64 = ld_stream1(a.in_keys + row);
           if constexpr (VAL) v64 = ld_stream1(a.in_vals + row);
         }
-        decode(make_uint2((uint32_t)k64, (uint32_t)(k64 >> 32)), make_uint2((uint32_t)v64, (uint32_t)(v64 >> 32)), ok, i, r);
+        decode((uint32_t)k64, (uint32_t)(k64 >> 32), (uint32_t)v64, (uint32_t)(v64 >> 32), ok, i, r);
       }
     }
   };
 
-  uint32_t pd[NQ], pg[NQ];  // reservations in flight: partition, reserved element offset
+  uint32_t pd[PT_NQ], pg[PT_NQ];  // reservations in flight: partition, reserved element offset
   uint32_t pvalid = 0;
-  const uint32_t lane = tid & 31u;
+  uint32_t wn = 0;                // entries on this warp's flush list (warp-uniform)
 
-  // ---- place: one shared-memory atomic hands out the slot; a row that finds the ring full stays pending.  The row
-  // that completes a partition's first sector puts the partition on its WARP's flush list (ballot + prefix: no
-  // atomics, no cross-warp list); `ovf` = rows whose partition did not fit the list (flushed by the thread itself).
-  auto place = [&](Rows& r, uint32_t& ovf) -> uint32_t {
+  // ---- place: one shared-memory atomic hands out the ticket
+  auto place = [&](Rows& r, uint32_t (&tk)[IPT]) {
+    const uint32_t valid = r.pend;
     uint32_t old[IPT];
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) old[i] = ((r.pend >> i) & 1u) ? atomicAdd(&w[r.d[i]], 2u) : 0xFFFFFFFEu;
-    uint32_t wn = 0;
-    ovf = 0;
+    for (int i = 0; i < IPT; ++i) old[i] = atomicAdd(&w[r.d[i]], (valid >> i) & 1u);  // a dropped row adds 0: no branch around the ATOMS
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const uint32_t cnt = old[i] >> 1;
-      const bool placed = cnt < SLOTS;  // rows that are not pending carry cnt = 0x7FFFFFFF
-      if (placed) {
-        const uint32_t slot = (cnt + ((old[i] & 1u) << LOG_EPS)) & (SLOTS - 1u);
-        reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + slot] = (ET)r.e[i];
+      const bool v = (valid >> i) & 1u;
+      const uint32_t cnt = old[i] & 0xFFFFu;
+      const uint32_t T = ((old[i] >> 16) + cnt) & 0xFFFFu;
+      tk[i] = T;
+      if (v && cnt < SLOTS) {
+        reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + (T & (SLOTS - 1u))] = (ET)r.e[i];
         r.pend &= ~(1u << i);
       }
-      const bool full = cnt == EPS - 1u;  // first sector complete
-      const unsigned m = __ballot_sync(0xffffffffu, full);
-      if (full) {
-        const uint32_t pos = wn + __popc(m & lanemask_lt());
-        if (pos < (uint32_t)WCAP) wlist[pos] = (uint16_t)r.d[i];
-        else ovf |= 1u << i;
-      }
+      const bool closer = v && (T & (EPS - 1u)) == EPS - 1u;
+      const unsigned m = __ballot_sync(0xffffffffu, closer);
+      if (closer) wl[wn + __popc(m & lanemask_lt())] = r.d[i] | ((T >> LOG_EPS) << 11);
       wn += __popc(m);
     }
-    // the reservations issued in the previous flush phase have returned by now: publish them
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-      if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
-    pvalid = 0;
-    if constexpr (TMAST) fence_proxy_async();  // staged rows become visible to the bulk-copy engine
-    return wn < (uint32_t)WCAP ? wn : (uint32_t)WCAP;
   };
-  // one listed partition: its full sector(s) leave for the place reserved in advance.  Executed by a PAIR of lanes
-  // (h = 0, 1: one half of the sector each; `solo`: one lane does both halves — the rare list-overflow path).  Lane
-  // h == 0 also issues the reservation of the partition's NEXT flush, consumed an iteration later (q >= 0) or
-  // waited for (solo).
-  auto flush_entry = [&](uint32_t d, int q, uint32_t h, bool solo) {
-    const uint32_t ww = w[d];
-    const uint32_t gs = nextg[d];
-    uint32_t cnt = ww >> 1;
-    if (cnt > SLOTS) cnt = SLOTS;  // rows beyond the ring were not staged: they retry
-    const uint32_t tog = ww & 1u;
-    const uint32_t nsec = cnt >> LOG_EPS;  // 1 or 2
-    store_half(d, tog, gs, h);
-    if (solo) store_half(d, tog, gs, 1u);
-    if (nsec == 2) {  // rare: both sectors filled within one iteration
-      uint32_t g1 = 0;
-      if (h == 0) g1 = atomicAdd(a.cursor + d * a.cstride, EPS);
-      if (!solo) g1 = __shfl_sync(3u << (lane & 30u), g1, lane & 30u);  // both lanes of the pair are here (same d, same ww)
-      const uint32_t gs1 = to_sector(g1);
-      store_half(d, tog ^ 1u, gs1, h);
-      if (solo) store_half(d, tog ^ 1u, gs1, 1u);
-    }
-    if (h == 0) {
-      w[d] = ((cnt - (nsec << LOG_EPS)) << 1) | ((tog + nsec) & 1u);
-      if (!solo) {
-        // The reservation's round trip through L2 (1 - 2 us under load) must not be waited for in this phase: the
-        // atomic writes straight into the register that is read an iteration later (a C++ temporary made ptxas
-        // park the warp on a MOV right here: 12 % of all stall samples, profiles/r02d_c3_dense16_ncu_summary.txt)
-        asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[q]) : "l"(a.cursor + d * a.cstride), "r"(EPS) : "memory");
-        pd[q] = d;
-        pvalid |= 1u << q;
-      } else {
-        nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
+  // rows that found their slot occupied: has the tail advanced far enough?
+  auto retry = [&](Rows& r, const uint32_t (&tk)[IPT]) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if ((r.pend >> i) & 1u) {
+        const uint32_t tail = lds_v32(&w[r.d[i]]) >> 16;
+        if (((tk[i] - tail) & 0xFFFFu) < SLOTS) {
+          __threadfence_block();  // the flusher's reset of the slot is ordered before its tail update
+          reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + (tk[i] & (SLOTS - 1u))] = (ET)r.e[i];
+          r.pend &= ~(1u << i);
+        }
       }
     }
   };
-  // ---- flush: every warp flushes the partitions on its own list, sixteen per step
-  auto flush = [&](const Rows& r, uint32_t wn, uint32_t ovf) {
+  // the reservations issued by the previous flush have returned by now: publish them
+  auto publish = [&]() {
+#pragma unroll
+    for (int q = 0; q < PT_NQ; ++q)
+      if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
+    pvalid = 0;
+  };
+  // sixteen list entries, a pair of lanes each (one half of the sector per lane)
+  auto flush_step = [&](const int slot, const uint32_t q, uint32_t& keep) {
+    const uint32_t j = q * 16u + (lane >> 1);
+    const bool act = j < wn;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    const uint32_t ent = act ? wl[j] : 0u;
+    bool ok = false;
+    if (act) {
+      const uint32_t d = ent & (PT_MAXP - 1u), S = ent >> 11;
+      unsigned char* src = buf + d * PT_RINGB + (S & 1u) * PT_SECTOR + h * 16u;
+      const uint32_t ww = lds_v32(&w[d]);
+      const uint32_t gs = lds_v16(&nextg[d]);
+      const uint4 v = lds_v128(src);
+      bool hole = piece_has_hole<VAL>(v);
+      hole |= __shfl_xor_sync(am, (int)hole, 1) != 0;
+      ok = ((ww >> (16 + LOG_EPS)) == S) && !hole && gs != PT_INFLIGHT;
+      if (ok) {
+        store_half(d, gs, h, v);
+        *reinterpret_cast<uint4*>(src) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (h == 0) {
+          nextg[d] = (uint16_t)PT_INFLIGHT;
+          __threadfence_block();  // both halves are free again before the tail moves
+          atomicAdd(&w[d], FLUSH_ADD);
+          // The reservation's round trip through L2 (1 - 2 us under load) is never waited for here: the atomic writes
+          // straight into the register that publish() reads a batch later
+          asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pg[slot]) : "l"(a.cursor + d * a.cstride), "r"(EPS) : "memory");
+          pd[slot] = d;
+          pvalid |= 1u << slot;
+        }
+      }
+    }
+    const bool fail = act && !ok && h == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, fail);
+    if (fail) wl[keep + __popc(m & lanemask_lt())] = ent;  // positions below the entries still to be read
+    keep += __popc(m);
+  };
+  auto flush = [&]() {
     __syncwarp();
+    publish();
+    uint32_t keep = 0;
+    const uint32_t nsteps = (wn + 15u) >> 4;
+    for (uint32_t q0 = 0; q0 < nsteps; q0 += PT_NQ) {
+      if (q0) publish();
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const uint32_t j = (uint32_t)q * 16u + (lane >> 1);
-      if (j < wn) flush_entry(wlist[j], q, lane & 1u, false);
+      for (int s = 0; s < PT_NQ; ++s)
+        if (q0 + s < nsteps) flush_step(s, q0 + s, keep);
     }
-    if (ovf) {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i)
-        if ((ovf >> i) & 1u) flush_entry(r.d[i], 0, 0u, true);
-    }
-    if constexpr (TMAST) {
-      bulk_commit();
-      bulk_wait_read0();  // the sectors have been read: their slots may be overwritten
-    }
+    wn = keep;
   };
 
   Rows cur, nxt;
+  uint32_t tk[IPT];
   uint32_t k = 0;
-  uint32_t R = blockIdx.x;
-  long long tr[6] = {0, 0, 0, 0, 0, 0};
-  auto tick = [&](long long& t0, int seg) {
-    if (a.trace) {
-      const long long t1 = clock64();
-      tr[seg] += t1 - t0;
-      t0 = t1;
+  uint32_t B = gw;
+  if (B < nbatch) {
+    for (uint32_t spin = 0; !batch_ready(B, 0); ++spin)
+      if (spin > (1u << 24)) __trap();
+    load_rows(B, 0, cur);
+  }
+  while (B < nbatch) {
+    place(cur, tk);
+    // the next batch is fetched and decoded before the flush when it has arrived already
+    const uint32_t Bn = B + GW;
+    bool have = false;
+    if (Bn < nbatch && batch_ready(Bn, k + 1)) {
+      load_rows(Bn, k + 1, nxt);
+      have = true;
     }
-  };
-  if (R < rounds) load_round(R, 0, cur);
-  long long t0 = a.trace ? clock64() : 0;
-  while (R < rounds) {
-    uint32_t ovf;
-    uint32_t wn = place(cur, ovf);
-    tick(t0, 0);
-    __syncthreads();  // #1: every row of this iteration is staged
-    tick(t0, 1);
-    if (tid == 0) {
-      // the ring stages of THIS round were read before the previous barrier #2: refill them
-      issue(k * PT_RS + PT_STAGES);
-      issue(k * PT_RS + 1 + PT_STAGES);
+    for (uint32_t spin = 0;; ++spin) {
+      flush();
+      if (!__any_sync(0xffffffffu, cur.pend != 0u) && wn <= (uint32_t)PT_KEEP) break;
+      retry(cur, tk);
+      if (spin > SPIN_LIMIT) __trap();
     }
-    flush(cur, wn, ovf);
-    tick(t0, 2);
-    // the rows of the next round are fetched and decoded before the barrier: warps that finish their flush early go ahead
-    const uint32_t Rn = R + G;
-    if (Rn < rounds) load_round(Rn, k + 1, nxt);
-    tick(t0, 3);
-    int any = __syncthreads_or(cur.pend != 0);  // #2: the flushed rings are consistent again
-    tick(t0, 4);
-    while (any) {  // some ring was full (more than a ring's worth of rows for one partition within a round): retry
-      wn = place(cur, ovf);
-      __syncthreads();
-      flush(cur, wn, ovf);
-      any = __syncthreads_or(cur.pend != 0);
-      tick(t0, 5);
+    if (Bn < nbatch && !have) {
+      for (uint32_t spin = 0; !batch_ready(Bn, k + 1); ++spin) {
+        if (wn) flush();  // never wait for data while other warps may wait for a sector on this list
+        if (spin > SPIN_LIMIT) __trap();
+      }
+      load_rows(Bn, k + 1, nxt);
     }
     cur = nxt;
-    R = Rn;
+    B = Bn;
     ++k;
   }
-  if (a.trace && lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) atomicAdd(a.trace + i, (unsigned long long)tr[i]);
-    atomicAdd(a.trace + 6, (unsigned long long)k);
-    atomicAdd(a.trace + 7, 1ull);
+  for (uint32_t spin = 0; wn; ++spin) {
+    flush();
+    if (spin > SPIN_LIMIT) __trap();
   }
-
-  // ---- drain: pad every partial sector with holes and flush it into the sector held in reserve
-#pragma unroll
-  for (int q = 0; q < NQ; ++q)
-    if ((pvalid >> q) & 1u) nextg[pd[q]] = to_sector(pg[q]);
+  publish();
   __syncthreads();
+
+  // ---- drain: every partition's oldest sector (partially filled, the rest hole markers) goes into the sector held in reserve
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
-    const uint32_t ww = w[d];
-    const uint32_t cnt = ww >> 1, tog = ww & 1u;  // cnt < EPS after the last flush phase
-    ET* sec = reinterpret_cast<ET*>(buf + d * PT_RINGB + tog * PT_SECTOR);
-    for (uint32_t j = cnt; j < EPS; ++j) sec[j] = HOLE;
-    if constexpr (TMAST) fence_proxy_async();
-    store_half(d, tog, nextg[d], 0u);
-    store_half(d, tog, nextg[d], 1u);
-  }
-  if constexpr (TMAST) {
-    bulk_commit();
-    bulk_wait0();
+    const uint32_t sec = (w[d] >> (16 + LOG_EPS)) & 1u;
+    const uint4* src = reinterpret_cast<const uint4*>(buf + d * PT_RINGB + sec * PT_SECTOR);
+    const uint32_t gs = nextg[d];
+    store_half(d, gs, 0u, src[0]);
+    store_half(d, gs, 1u, src[1]);
   }
   if constexpr (STRICT) {
     if (bad) atomicOr(&a.ctl->flags, CTL_NOT_DENSE16);
@@ -381,7 +406,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
 }
 
 size_t part_smem_bytes(int logp) {
-  return ((size_t)1 << logp) * (PT_RINGB + 6) + (PT_THREADS / 32) * 64 * 2 + (size_t)PT_STAGES * PT_STAGE_BYTES;
+  return ((size_t)1 << logp) * (PT_RINGB + 6) + (size_t)PT_WARPS * PT_WCAP * 4 + (size_t)PT_WARPS * PT_WSLOTS * PT_SLOT_BYTES;
 }
 uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
 // One cursor per 256 bytes: 2048 adjacent 4-byte cursors live in 64 cache lines, i.e. on a handful of L2 slices, and the
@@ -389,31 +414,31 @@ uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
 // lts__d_atomic_input_cycles_active max 58 %: profiles/r02e_c3_dense16_ncu_summary.txt)
 uint32_t part_cursor_stride() { return 64u; }
 uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
-  const uint64_t round = val ? 2048 : 4096;
+  const uint64_t round = (uint64_t)PT_WARPS * (val ? 128 : 256);  // one batch per warp
   const uint64_t rounds = (n + round - 1) / round;
   return (uint32_t)(rounds < (uint64_t)di.sms ? (rounds ? rounds : 1) : (uint64_t)di.sms);
 }
 
 bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (x.logp < 4 || (1 << x.logp) > PT_MAXP || x.world > PT_MAXW || x.n == 0) return false;
-  if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= 0xFFFFull) return false;
-  if ((x.n + 2047) / 2048 > 0xFFFFFFF0ull / 8) return false;
+  if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= (uint64_t)PT_INFLIGHT) return false;
+  if ((x.n + 127) / 128 > 0xFFFFFFF0ull) return false;
   PartParams a;
-  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor; a.cstride = x.cursor_stride; a.trace = x.trace;
+  a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor; a.cstride = x.cursor_stride;
   a.ctl = x.ctl;
   for (int i = 0; i < PT_MAXW; ++i) a.outs[i] = i < x.world ? x.outs[i] : nullptr;
   a.logp = x.logp; a.lpo = x.lpo; a.nsub = x.nsub; a.sub = x.sub;
   const size_t smem = part_smem_bytes(x.logp);
   if (smem + 256 > di.smem_optin) return false;
   const uint32_t grid = part_grid(val, x.n, di);
-#define FJ_PART(V, S, T)                                                                            \
-  do {                                                                                              \
-    cudaFuncSetAttribute(k_part<V, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    k_part<V, S, T><<<grid, PT_THREADS, smem, st>>>(a);                                            \
+#define FJ_PART(V, S)                                                                            \
+  do {                                                                                           \
+    cudaFuncSetAttribute(k_part<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_part<V, S><<<grid, PT_THREADS, smem, st>>>(a);                                            \
   } while (0)
-  if (val) { if (x.tma_store) FJ_PART(true, true, true); else FJ_PART(true, true, false); }  // rows with values are a build side
-  else if (x.strict) { if (x.tma_store) FJ_PART(false, true, true); else FJ_PART(false, true, false); }
-  else { if (x.tma_store) FJ_PART(false, false, true); else FJ_PART(false, false, false); }
+  if (val) FJ_PART(true, true);  // rows with values are a build side
+  else if (x.strict) FJ_PART(false, true);
+  else FJ_PART(false, false);
 #undef FJ_PART
   ++*launches;
   return true;

@@ -1375,12 +1375,28 @@ __global__ void __launch_bounds__(256) k_generate_g2(int side, uint64_t ny, uint
                                                      unsigned long long* __restrict__ keys,
                                                      unsigned long long* __restrict__ vals) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  int kbits = 2;
+  while (kbits < 64 && ((ny - 1) >> kbits) != 0) ++kbits;
+  const uint64_t sh_mask = kbits >= 64 ? ~0ull : (1ull << kbits) - 1ull;
+  const uint64_t sh_shift = (uint64_t)((kbits + 1) / 2);
+  const uint64_t sh_add = (seed * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull) & sh_mask;
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count; j += stride) {
     const uint64_t idx = start + j;
     uint64_t id;
     if (side == 0) {
-      id = idx < c ? idx : idx - c + ny;
-      if (vals) vals[j] = mix64(idx + seed * 0x9E3779B97F4A7C15ull) % 100ull;
+      // build row idx holds build id jj = shuffle(idx): a bijective mixer on k bits, cycle-walked into [0, ny)
+      // (datagen.py::_shuffle_index)
+      uint64_t jj = idx;
+      do {
+        jj = (jj + sh_add) & sh_mask;
+        jj ^= jj >> sh_shift;
+        jj = (jj * 0xD6E8FEB86659FD93ull) & sh_mask;
+        jj ^= jj >> sh_shift;
+        jj = (jj * 0xCA5A826395121157ull) & sh_mask;
+        jj ^= jj >> sh_shift;
+      } while (jj >= ny);
+      id = jj < c ? jj : jj - c + ny;
+      if (vals) vals[j] = mix64(jj + seed * 0x9E3779B97F4A7C15ull) % 100ull;
     } else {
       const unsigned long long r = mix64((idx + 1ull) * 0x9E3779B97F4A7C15ull + seed);
       id = r % ny;

@@ -9,7 +9,10 @@ the golden values in tests/golden/ depend on it.
 
 G2 is a counter-based generator with the same shape whose every element is a pure function of
 (seed, index), so shards can be produced independently (per GPU / per rank) and at 1e9 rows
-without a global permutation.
+without a global permutation.  Build rows come in a pseudo-random order (a cycle-walking bijective
+hash of the row index picks the key id), like the shuffled RHS tables of join-datagen.R: an
+arithmetic progression of build keys would make a radix partition pass artificially free of
+shared-memory bank conflicts.
 """
 from __future__ import annotations
 
@@ -74,6 +77,33 @@ def _perm_index(i: np.ndarray, U: int, seed: int) -> np.ndarray:
     return ((i.astype(np.uint64) * np.uint64(a % U)) % np.uint64(U) + np.uint64(b)) % np.uint64(U)
 
 
+def _shuffle_index(j: np.ndarray, n: int, seed: int) -> np.ndarray:
+    """A pseudo-random bijection of [0, n), computed per element: a bijective mixer on k = ceil(log2 n)
+    bits (add, xorshift, odd multiply — each a bijection modulo 2^k), applied again while the
+    result is >= n (cycle walking; fewer than two rounds on average)."""
+    k = max(int(n - 1).bit_length(), 2)
+    mask = np.uint64((1 << k) - 1)
+    sh = np.uint64((k + 1) // 2)
+    add = np.uint64((seed * 0x9E3779B97F4A7C15 + 0x7F4A7C15) & ((1 << k) - 1))
+
+    def f(x):
+        with np.errstate(over="ignore"):
+            x = (x + add) & mask
+            x ^= x >> sh
+            x = (x * np.uint64(0xD6E8FEB86659FD93)) & mask
+            x ^= x >> sh
+            x = (x * np.uint64(0xCA5A826395121157)) & mask
+            x ^= x >> sh
+        return x
+
+    x = f(j.astype(np.uint64, copy=True))
+    todo = np.flatnonzero(x >= np.uint64(n))
+    while todo.size:
+        x[todo] = f(x[todo])
+        todo = todo[x[todo] >= np.uint64(n)]
+    return x
+
+
 def g2_slice(N: int, ny: int, match_pct: int, seed: int, side: str, start: int, stop: int):
     """Elements [start, stop) of one side of the G2 data set.
 
@@ -85,11 +115,12 @@ def g2_slice(N: int, ny: int, match_pct: int, seed: int, side: str, start: int, 
     U = 2 * ny - c
     idx = np.arange(start, stop, dtype=np.uint64)
     if side == "build":
-        # build ids: the c common ids [0, c) and the build-only ids [ny, U)
-        ids = np.where(idx < np.uint64(c), idx, idx - np.uint64(c) + np.uint64(ny))
+        # build row idx holds build id j = shuffle(idx); build ids: the c common ids [0, c) and the build-only ids [ny, U)
+        j = _shuffle_index(idx, ny, seed)
+        ids = np.where(j < np.uint64(c), j, j - np.uint64(c) + np.uint64(ny))
         keys = _perm_index(ids, U, seed) + np.uint64(1)
         with np.errstate(over="ignore"):
-            vals = _mix64(idx + np.uint64(seed) * _GOLD) % np.uint64(100)
+            vals = _mix64(j + np.uint64(seed) * _GOLD) % np.uint64(100)
         return keys, vals
     if side == "probe":
         with np.errstate(over="ignore"):

@@ -512,19 +512,18 @@ def test_dense_radix_edges(dense_small):
 # ------------------------------------------------------------------------------------------------ dense key domain, round 2
 @pytest.fixture()
 def dense16_small(fj):
-    fj.configure(dense_min_rows=1024, dense16=1, dense16_logp=0, part_tma_store=0)
+    fj.configure(dense_min_rows=1024, dense16=1, dense16_logp=0)
     yield fj
-    fj.configure(dense_min_rows=1 << 20, dense16=1, dense16_logp=0, part_tma_store=0, dense=1)
+    fj.configure(dense_min_rows=1 << 20, dense16=1, dense16_logp=0, dense=1)
 
 
-@pytest.mark.parametrize("logp,tma_store", [(0, 0), (8, 0), (11, 0), (0, 1), (11, 1)])
-def test_dense16_partition_join(dense16_small, logp, tma_store):
+@pytest.mark.parametrize("logp", [0, 8, 10, 11])
+def test_dense16_partition_join(dense16_small, logp):
     """Radix entry points on a dense key domain, round 2: ONE partition pass by the low key bits with per-SM
     write-combining sector buffers (k_part; rows shrink to idx16 | value16 and idx16) + the direct-address join in
-    shared memory (k_sjoin).  The partition count and the way sectors leave shared memory (LDS + STG or TMA bulk
-    store) must not change the result."""
+    shared memory (k_sjoin).  The partition count must not change the result."""
     fj = dense16_small
-    fj.configure(dense16_logp=logp, part_tma_store=tma_store)
+    fj.configure(dense16_logp=logp)
     for N, ny, pct in ((400_000, 300_000, 90), (3_000_000, 2_000_000, 90), (1_000_000, 70_000, 10), (5_001, 2_049, 50)):
         bk, bv, pk = g1(N, ny, pct)
         expect = O.np_join(bk, bv, pk)

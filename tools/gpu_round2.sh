@@ -19,8 +19,6 @@ if has sanity; then
       echo "sanity $cfg $mode exit $?" >> "$OUT/sanity.log"
     done
   done
-  timeout 120 python tools/prof_case.py S radix mat --check --reps 2 --set dense_min_rows=1024 --set part_tma_store=1 >> "$OUT/sanity.log" 2>&1
-  echo "sanity S mat tma_store exit $?" >> "$OUT/sanity.log"
   tail -n 30 "$OUT/sanity.log"
 fi
 if has sanitize; then
@@ -28,9 +26,7 @@ if has sanitize; then
   echo "exit $?" >> "$OUT/memcheck_dense16.log"
   timeout 300 compute-sanitizer --tool racecheck python tools/prof_case.py T radix mat --reps 1 --set dense_min_rows=1024 > "$OUT/racecheck_dense16.log" 2>&1
   echo "exit $?" >> "$OUT/racecheck_dense16.log"
-  timeout 300 compute-sanitizer --tool memcheck python tools/prof_case.py T radix mat --reps 1 --set dense_min_rows=1024 --set part_tma_store=1 > "$OUT/memcheck_dense16_tma.log" 2>&1
-  echo "exit $?" >> "$OUT/memcheck_dense16_tma.log"
-  tail -n 6 "$OUT/memcheck_dense16.log" "$OUT/racecheck_dense16.log" "$OUT/memcheck_dense16_tma.log"
+  tail -n 6 "$OUT/memcheck_dense16.log" "$OUT/racecheck_dense16.log"
 fi
 if has sanitize_general; then  # the general-path kernels under memcheck + racecheck
   timeout 600 compute-sanitizer --tool memcheck python tools/prof_case.py S radix mat --reps 1 --set dense=0 > "$OUT/memcheck_radix_general.log" 2>&1

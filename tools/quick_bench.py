@@ -66,9 +66,6 @@ def main():
         else:
             run(f"{c} radix mat (dense16: k_part + k_sjoin)", R, M, d, a.reps, N)
             run(f"{c} radix count (dense16)", R, 0, d, a.reps, N)
-            run(f"{c} radix mat (dense16, TMA bulk stores)", R, M, d, a.reps, N, {"part_tma_store": 1})
-            run(f"{c} radix count (dense16, TMA bulk stores)", R, 0, d, a.reps, N)
-            capi.config_set(part_tma_store=0)
             run(f"{c} adaptive mat (dense16)", A, M, d, a.reps, N)
             if a.full:
                 run(f"{c} radix mat (dense, L2 direct-address k_djoin)", R, M, d, a.reps, N, {"dense16": 0})
