@@ -116,7 +116,8 @@ __device__ __forceinline__ bool piece_has_hole(const uint4& v) {
 //     reservation of the partition's next global sector, whose answer is published a batch later.
 //   * Entries that cannot leave yet stay on the list; a warp never blocks (on input data, on a pending row) without
 //     servicing its list, so the oldest sector of every partition can always make progress.
-template <bool VAL, bool STRICT>
+// MULTI: partitions have owners (several GPUs) and sub-regions per source; else one plain region per partition
+template <bool VAL, bool STRICT, bool MULTI>
 __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   using ET = std::conditional_t<VAL, uint32_t, uint16_t>;
   constexpr uint32_t ES = sizeof(ET);
@@ -191,16 +192,23 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
       if (hh == 0) atomicOr(&a.ctl->flags, CTL_OVERFLOW);
       return;
     }
-    const uint32_t region = (d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
-    const uint32_t owner = d >> a.lpo;
-    unsigned char* dst = (owner ? s_outs[owner] : out0) + (((uint64_t)region * capsec + gs) << 5);
+    unsigned char* dst;
+    if constexpr (MULTI) {
+      const uint32_t region = (d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
+      const uint32_t owner = d >> a.lpo;
+      dst = (owner ? s_outs[owner] : out0) + (((uint64_t)region * capsec + gs) << 5);
+    } else {
+      dst = out0 + (((uint64_t)d * capsec + gs) << 5);
+    }
     reinterpret_cast<uint4*>(dst)[hh] = v;
   };
 
+  constexpr uint32_t NOROW = 0xFFFFFFFFu;  // element of a row that is dropped (no valid element equals it)
   struct Rows {
     uint32_t d[IPT];
     uint32_t e[IPT];
-    uint32_t pend;  // rows not stored yet
+    uint32_t pend;  // rows that hold a ticket and are not stored yet
+    bool inv;       // some row of the batch is dropped (outside the domain, or beyond the end of the input)
   };
   bool bad = false;
   // digit, element and validity of one row
@@ -210,8 +218,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     if constexpr (STRICT) bad |= ok & !in;
     ok &= in;
     r.d[i] = klo & pmask;
-    r.e[i] = (klo >> a.logp) | (VAL ? vlo << 16 : 0u);
-    r.pend |= ok ? (1u << i) : 0u;
+    r.e[i] = ok ? ((klo >> a.logp) | (VAL ? vlo << 16 : 0u)) : NOROW;
+    r.inv |= !ok;
   };
   // has batch B (this warp's batch number kk) arrived?  (warp-uniform)
   auto batch_ready = [&](uint32_t B, uint32_t kk) -> bool {
@@ -223,6 +231,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   // ragged tail / unaligned inputs are loaded directly.
   auto load_rows = [&](uint32_t B, uint32_t kk, Rows& r) {
     r.pend = 0;
+    r.inv = false;
     if (B < nfull) {
       const uint4* st = reinterpret_cast<const uint4*>(ring + (kk % PT_WSLOTS) * PT_SLOT_BYTES);
       uint4 k2[IPT / 2], v2[IPT / 2];
@@ -258,20 +267,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   uint32_t wn = 0;                // entries on this warp's flush list (warp-uniform)
 
   // ---- place: one shared-memory atomic hands out the ticket
-  auto place = [&](Rows& r, uint32_t (&tk)[IPT]) {
-    const uint32_t valid = r.pend;
+  // ALLV (a literal at both call sites): no row of the warp's batch is dropped, no per-row predicate
+  auto place = [&](const bool ALLV, Rows& r, uint32_t (&tk)[IPT]) {
     uint32_t old[IPT];
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) old[i] = atomicAdd(&w[r.d[i]], (valid >> i) & 1u);  // a dropped row adds 0: no branch around the ATOMS
+    for (int i = 0; i < IPT; ++i)  // a dropped row adds 0 (a branch around every ATOMS otherwise)
+      old[i] = atomicAdd(&w[r.d[i]], ALLV ? 1u : (r.e[i] != NOROW ? 1u : 0u));
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const bool v = (valid >> i) & 1u;
+      const bool v = ALLV || r.e[i] != NOROW;
       const uint32_t cnt = old[i] & 0xFFFFu;
       const uint32_t T = ((old[i] >> 16) + cnt) & 0xFFFFu;
       tk[i] = T;
-      if (v && cnt < SLOTS) {
-        reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + (T & (SLOTS - 1u))] = (ET)r.e[i];
-        r.pend &= ~(1u << i);
+      if (v) {
+        if (cnt < SLOTS) reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + (T & (SLOTS - 1u))] = (ET)r.e[i];
+        else r.pend |= 1u << i;
       }
       const bool closer = v && (T & (EPS - 1u)) == EPS - 1u;
       const unsigned m = __ballot_sync(0xffffffffu, closer);
@@ -301,9 +311,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     pvalid = 0;
   };
   // sixteen list entries, a pair of lanes each (one half of the sector per lane)
-  auto flush_step = [&](const int slot, const uint32_t q, uint32_t& keep) {
+  auto flush_step = [&](const int slot, const uint32_t q, uint32_t& keep, const uint32_t nvis) {
     const uint32_t j = q * 16u + (lane >> 1);
-    const bool act = j < wn;
+    const bool act = j < nvis;
     const unsigned am = __ballot_sync(0xffffffffu, act);
     const uint32_t ent = act ? wl[j] : 0u;
     bool ok = false;
@@ -336,16 +346,27 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     if (fail) wl[keep + __popc(m & lanemask_lt())] = ent;  // positions below the entries still to be read
     keep += __popc(m);
   };
-  auto flush = [&]() {
+  // all == false: only whole steps of sixteen entries (the last few entries of the list wait for the next batch: a
+  // step costs the same for one entry as for sixteen)
+  auto flush = [&](bool all) {
     __syncwarp();
     publish();
     uint32_t keep = 0;
-    const uint32_t nsteps = (wn + 15u) >> 4;
+    const uint32_t nsteps = all ? (wn + 15u) >> 4 : wn >> 4;
+    const uint32_t done = nsteps << 4 < wn ? nsteps << 4 : wn;  // entries visited
     for (uint32_t q0 = 0; q0 < nsteps; q0 += PT_NQ) {
       if (q0) publish();
 #pragma unroll
       for (int s = 0; s < PT_NQ; ++s)
-        if (q0 + s < nsteps) flush_step(s, q0 + s, keep);
+        if (q0 + s < nsteps) flush_step(s, q0 + s, keep, done);
+    }
+    // the entries not visited move down behind the ones that stay
+    if (done < wn) {
+      if (keep < done) {
+        for (uint32_t j = done + lane; j < wn; j += 32u) wl[keep + (j - done)] = wl[j];  // fewer than 16: one pass, reads before writes
+        __syncwarp();
+      }
+      keep += wn - done;
     }
     wn = keep;
   };
@@ -360,7 +381,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     load_rows(B, 0, cur);
   }
   while (B < nbatch) {
-    place(cur, tk);
+    if (__any_sync(0xffffffffu, cur.inv)) place(false, cur, tk);
+    else place(true, cur, tk);
     // the next batch is fetched and decoded before the flush when it has arrived already
     const uint32_t Bn = B + GW;
     bool have = false;
@@ -368,15 +390,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
       load_rows(Bn, k + 1, nxt);
       have = true;
     }
-    for (uint32_t spin = 0;; ++spin) {
-      flush();
-      if (!__any_sync(0xffffffffu, cur.pend != 0u) && wn <= (uint32_t)PT_KEEP) break;
+    bool anyp = __any_sync(0xffffffffu, cur.pend != 0u);
+    flush(anyp);
+    for (uint32_t spin = 0; anyp || wn > (uint32_t)PT_KEEP; ++spin) {  // rare: a ring was full, or many sectors cannot leave yet
       retry(cur, tk);
+      flush(true);
+      anyp = __any_sync(0xffffffffu, cur.pend != 0u);
       if (spin > SPIN_LIMIT) __trap();
     }
     if (Bn < nbatch && !have) {
       for (uint32_t spin = 0; !batch_ready(Bn, k + 1); ++spin) {
-        if (wn) flush();  // never wait for data while other warps may wait for a sector on this list
+        if (wn) flush(true);  // never wait for data while other warps may wait for a sector on this list
         if (spin > SPIN_LIMIT) __trap();
       }
       load_rows(Bn, k + 1, nxt);
@@ -386,7 +410,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
     ++k;
   }
   for (uint32_t spin = 0; wn; ++spin) {
-    flush();
+    flush(true);
     if (spin > SPIN_LIMIT) __trap();
   }
   publish();
@@ -431,14 +455,15 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   const size_t smem = part_smem_bytes(x.logp);
   if (smem + 256 > di.smem_optin) return false;
   const uint32_t grid = part_grid(val, x.n, di);
-#define FJ_PART(V, S)                                                                            \
-  do {                                                                                           \
-    cudaFuncSetAttribute(k_part<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    k_part<V, S><<<grid, PT_THREADS, smem, st>>>(a);                                            \
+  const bool multi = x.world > 1 || x.nsub > 1 || x.lpo != x.logp;
+#define FJ_PART(V, S, M)                                                                            \
+  do {                                                                                              \
+    cudaFuncSetAttribute(k_part<V, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_part<V, S, M><<<grid, PT_THREADS, smem, st>>>(a);                                            \
   } while (0)
-  if (val) FJ_PART(true, true);  // rows with values are a build side
-  else if (x.strict) FJ_PART(false, true);
-  else FJ_PART(false, false);
+  if (val) { if (multi) FJ_PART(true, true, true); else FJ_PART(true, true, false); }  // rows with values are a build side
+  else if (x.strict) { if (multi) FJ_PART(false, true, true); else FJ_PART(false, true, false); }
+  else { if (multi) FJ_PART(false, false, true); else FJ_PART(false, false, false); }
 #undef FJ_PART
   ++*launches;
   return true;
