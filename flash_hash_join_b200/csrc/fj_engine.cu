@@ -127,7 +127,7 @@ struct Engine {
   fj_status h2d(void* dst, const void* src, size_t bytes);
   void stager_release();
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
-  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush;
+  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush, sj_tails;
   uint64_t pairs_n = 0;
   bool pairs_valid = false, pairs_idx = false;
   std::map<std::string, int64_t> cfg;
@@ -278,7 +278,7 @@ void Engine::shutdown() {
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
                     &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &direct, &dist_scratch, &send_b, &send_p, &recv_b,
-                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv})
+                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv, &sj_tails})
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
@@ -843,6 +843,12 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   FJ_TRY(cursors.ensure(2 * (size_t)P * cs * 4));
   uint32_t* cur_b = cursors.as<uint32_t>();
   uint32_t* cur_p = cur_b + (size_t)P * cs;
+  if (mat) {  // k_sjoin reserves output in blocks: room for every CTA's unused block tails
+    const size_t ob = (size_t)(np + sjoin_out_slack_pairs(di)) * 8;
+    FJ_TRY(out_keys.ensure(ob));
+    FJ_TRY(out_vals.ensure(ob));
+    FJ_TRY(sj_tails.ensure(sjoin_tail_bytes(di)));
+  }
   Ctl* d_ctl = ctl.as<Ctl>();
   int launches = 0;
   FJ_CUDA(cudaEventRecord(ev[0], st));
@@ -866,6 +872,7 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
     j.ctl = d_ctl;
     j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
     j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
+    j.tails = mat ? sj_tails.as<unsigned long long>() : nullptr;
     launched = launch_sjoin(mat, j, di, st, &launches);
   }
   FJ_CUDA(cudaEventRecord(ev[3], st));
@@ -874,6 +881,13 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   FJ_CUDA(cudaStreamSynchronize(st));
   FJ_CUDA(cudaGetLastError());
   if (!launched) h_ctl->flags |= CTL_NOT_DENSE16;  // no launch configuration: the next layout answers
+  if (mat && launched && !(h_ctl->flags & (CTL_NOT_DENSE16 | CTL_OVERFLOW))) {
+    // out_cursor counts whole reserved blocks; k_pairs_compact has made [0, match_count) dense
+    if (h_ctl->out_cursor < h_ctl->match_count || h_ctl->out_cursor - h_ctl->match_count > sjoin_out_slack_pairs(di))
+      return set_err(FJ_ERR_STATE, "internal: %llu pairs reserved for %llu matches", (unsigned long long)h_ctl->out_cursor,
+                     (unsigned long long)h_ctl->match_count);
+    h_ctl->out_cursor = h_ctl->match_count;
+  }
   s->clear_s += ms(0, 1) * 1e-3;
   s->partition_s += ms(1, 2) * 1e-3;
   s->probe_s += ms(2, 3) * 1e-3;

@@ -201,9 +201,14 @@ struct SjoinArgs {
   Ctl* ctl = nullptr;
   unsigned long long* out_keys = nullptr;
   unsigned long long* out_vals = nullptr;
+  unsigned long long* tails = nullptr;  // mat: sjoin_tail_bytes() of scratch (per-CTA output tails for the pair compaction)
 };
 size_t sjoin_smem_bytes(uint32_t slots_alloc);
 uint32_t sjoin_max_slots(const DeviceInfo& di);
+size_t sjoin_tail_bytes(const DeviceInfo& di);
+// a materializing k_sjoin reserves output in blocks: out_keys / out_vals need room for this many pairs beyond np; after
+// launch_sjoin the pairs are the dense range [0, Ctl::match_count) (Ctl::out_cursor counts the blocks reserved)
+uint64_t sjoin_out_slack_pairs(const DeviceInfo& di);
 bool launch_sjoin(bool mat, const SjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,

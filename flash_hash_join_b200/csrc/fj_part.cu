@@ -477,6 +477,10 @@ constexpr int SJ_NPC = 2;                 // 16-byte pieces per consumer thread 
 constexpr int SJ_CH = SJ_CONS * 16 * SJ_NPC;  // bytes per ring stage
 constexpr int SJ_STAGES = 3;
 constexpr uint32_t SJ_SLOTS = 65536;      // direct-address slots: every 16-bit index has one (0xFFFF = hole: never set)
+constexpr int SJ_LOG_BLK = 12;            // pairs per output block
+constexpr uint32_t SJ_BLK = 1u << SJ_LOG_BLK;
+constexpr int SJ_NBLK = 8;                // output-block table entries (blocks b - 6 .. b + 1 around the newest one)
+constexpr int SJ_TAIL_WORDS = 4;          // per-CTA record for k_pairs_compact: partial block base, pairs in it, unused block base, -
 
 struct SjoinParams {
   const unsigned char* build;  // regions of cap_b elements (MAT: 4 bytes idx | value << 16; count: 2 bytes idx)
@@ -488,34 +492,57 @@ struct SjoinParams {
   uint32_t cnt_stride, cstride;  // cursor of (sub, p) = cnt[(sub * cnt_stride + p) * cstride]
   uint32_t p_first, p_count;   // partitions joined here: global ids p_first .. p_first + p_count - 1
   int logp, nsub;
-  uint32_t slots;              // slots a build row can address (multiple of 8): only these are zeroed
+  uint32_t slots;              // slots a build row can address (multiple of 8): only these are cleared between partitions
   Ctl* ctl;
   unsigned long long* out_keys;
   unsigned long long* out_vals;
+  unsigned long long* tails;   // MAT: [gridDim.x * SJ_TAIL_WORDS]
 };
 
 __device__ __forceinline__ void sj_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"r"(SJ_CONS) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_v64(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v64(void* p, unsigned long long v) {
+  asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+// sum of the two 16-bit halves of x, added to acc (one IDP.2A)
+__device__ __forceinline__ uint32_t add_halves(uint32_t x, uint32_t acc) {
+  uint32_t r;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x0101u), "r"(acc));
+  return r;
+}
 
-// MAT: the probe rows of a partition stream through TWICE.  Pass 1 only counts the matches, so that the
-// partition's output range is reserved with ONE global atomic (a per-warp reservation on the single output
-// cursor serialises in L2: 41 % of all stall samples of the first version, profiles/r02a_c3_dense16_ncu_summary.txt);
-// pass 2 (an L2 hit) looks the rows up again and writes the pairs, warps sub-allocating from the reserved range
-// with a shared-memory atomic.  The region has a slot for EVERY 16-bit index, so a lookup needs no bounds check:
-// slot 0xFFFF (the hole marker) and the slots beyond the build side's domain are zero.
+// One partition at a time per CTA: fill the direct-address region (plain 16-bit stores: region[idx] = value + 1), stream
+// the probe rows ONCE, then clear the region again.
+//   * Duplicate build keys are found without atomics: every row contributes value + 1 >= 1 to a row sum, every slot its
+//     content to a slot sum when the region is cleared; a key stored twice loses one contribution (CTL_DUP).
+//   * MAT: pairs go to output blocks of SJ_BLK pairs.  A CTA numbers its pairs with a shared-memory cursor; the warp
+//     that is first to enter block b reserves block b + 1 with ONE global atomic (2.2e4 for 9e7 pairs; a reservation
+//     per warp serialised in L2, a reservation per partition needed a second pass over the probe rows:
+//     profiles/r02a / r02i _c3_dense16_ncu_summary.txt).  The unused tail of every CTA's last block (and its block
+//     reserved ahead) is a hole that k_pairs_compact fills with the pairs beyond the final count.
+//   * The region has a slot for EVERY 16-bit index, so a lookup needs no bounds check: slot 0xFFFF (the hole marker of
+//     the partition buffers) and the slots beyond the build side's domain stay zero.
 template <bool MAT>
 __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   constexpr uint32_t EB = MAT ? 4u : 2u;  // bytes per build element
   extern __shared__ __align__(128) unsigned char smem[];
   uint16_t* region16 = reinterpret_cast<uint16_t*>(smem);
-  uint32_t* region32 = reinterpret_cast<uint32_t*>(smem);
   unsigned char* ring = smem + (size_t)SJ_SLOTS * 2;
   __shared__ __align__(8) uint64_t s_full[SJ_STAGES], s_empty[SJ_STAGES];
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_total, s_cur;
+  __shared__ __align__(8) unsigned long long s_blk[SJ_NBLK];  // block b: first pair index | (b + 1) << 40
+  __shared__ unsigned long long s_rowsum[2], s_slotsum[2];
+  __shared__ uint32_t s_vcur;                                  // pairs emitted by this CTA
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // an earlier kernel of this attempt gave up: nothing to do (uniform; before any copy is in flight)
-  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_NOT_DENSE16 | CTL_OVERFLOW)) return;
+  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_NOT_DENSE16 | CTL_OVERFLOW)) {
+    if (MAT && tid == 0) a.tails[blockIdx.x * SJ_TAIL_WORDS] = ~0ull;
+    return;
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -524,11 +551,12 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
       mbar_init(&s_empty[s], SJ_CWARPS);
     }
     mbar_fence_init();
-    s_total = 0;
-    s_cur = 0;
+#pragma unroll
+    for (int i = 0; i < SJ_NBLK; ++i) s_blk[i] = 0;
+    s_rowsum[0] = s_rowsum[1] = s_slotsum[0] = s_slotsum[1] = 0;
+    s_vcur = 0;
   }
-  // the slots no build row can address stay zero for the whole kernel
-  for (uint32_t i = a.slots / 8u + (uint32_t)tid; i < SJ_SLOTS / 8u; i += SJ_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = (uint32_t)tid; i < SJ_SLOTS / 8u; i += SJ_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
   // elements of one side of partition l (local index), summed over the sub-regions
@@ -540,7 +568,6 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     }
     return t;
   };
-  constexpr int NPASS = MAT ? 3 : 2;  // build, probe (count), probe (emit)
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
@@ -548,8 +575,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     uint32_t it = 0;
     for (uint32_t l = blockIdx.x; l < a.p_count; l += gridDim.x) {
       if (side_total(a.bcnt, a.cap_b, l) == 0 || side_total(a.pcnt, a.cap_p, l) == 0) continue;
-      for (int pass = 0; pass < NPASS; ++pass) {
-        const int side = pass ? 1 : 0;
+      for (int side = 0; side < 2; ++side) {
         const uint32_t* cnt = side ? a.pcnt : a.bcnt;
         const uint64_t cap = side ? a.cap_p : a.cap_b;
         const uint32_t eb = side ? 2u : EB;
@@ -576,34 +602,37 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
   // ------------------------------------------------------------------ consumers
   const uint32_t ct = (uint32_t)tid - 32u;
   unsigned long long local_count = 0;
-  bool dup = false;
-  uint32_t it = 0;
+  uint32_t it = 0, par = 0;
+  const uint4 HOLES = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   // the eight 16-bit indices of one 16-byte piece of a probe chunk -> direct-address values (0 = no match)
-  auto lookup8 = [&](const uint4& v, uint32_t (&idx)[8], uint32_t (&val)[8]) -> uint32_t {
+  auto lookup8 = [&](const uint4& v, uint32_t (&idx)[8], uint32_t (&val)[8]) {
     const uint32_t e[4] = {v.x, v.y, v.z, v.w};
-    uint32_t hitmask = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       idx[r] = (r & 1) ? (e[r >> 1] >> 16) : (e[r >> 1] & 0xffffu);
       val[r] = region16[idx[r]];
     }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) hitmask |= val[r] ? (1u << r) : 0u;
-    return hitmask;
   };
-  const uint4 HOLES = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  // reserve output block b (one lane): SJ_BLK pairs from the global cursor, published as base | (b + 1) << 40
+  auto reserve_block = [&](uint32_t b) {
+    const unsigned long long g = atomicAdd(&a.ctl->out_cursor, (unsigned long long)SJ_BLK);
+    sts_v64(&s_blk[b % SJ_NBLK], g | ((unsigned long long)(b + 1u) << 40));
+  };
+  // first pair index of block b (waits for the reservation, which was issued a whole block earlier)
+  auto block_base = [&](uint32_t b) -> unsigned long long {
+    unsigned long long e = lds_v64(&s_blk[b % SJ_NBLK]);
+    for (uint32_t spin = 0; (uint32_t)(e >> 40) != b + 1u; ++spin) {
+      if (spin > (1u << 24)) __trap();
+      e = lds_v64(&s_blk[b % SJ_NBLK]);
+    }
+    return e & ((1ull << 40) - 1ull);
+  };
 
   for (uint32_t l = blockIdx.x; l < a.p_count; l += gridDim.x) {
     if (side_total(a.bcnt, a.cap_b, l) == 0 || side_total(a.pcnt, a.cap_p, l) == 0) continue;
     const uint32_t plow = a.p_first + l;  // the key bits the partition implies
-    // ---- zero the addressable part of the region
-    {
-      uint4* r4 = reinterpret_cast<uint4*>(smem);
-      const uint32_t n4 = a.slots / 8u;
-      for (uint32_t i = ct; i < n4; i += SJ_CONS) r4[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    sj_bar_consumers();
-    // ---- fill: region[idx] = value + 1
+    // ---- fill: region[idx] = value + 1 (count: 1)
+    unsigned long long rowsum = 0;
     for (int sub = 0; sub < a.nsub; ++sub) {
       uint64_t c = a.bcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
       if (c > a.cap_b) c = a.cap_b;
@@ -619,17 +648,17 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
           const uint32_t piece = (uint32_t)q * SJ_CONS + ct;
           v[q] = piece * 16u < bytes ? st[piece] : HOLES;
         }
+        uint32_t part = 0;
 #pragma unroll
         for (int q = 0; q < SJ_NPC; ++q) {
           const uint32_t e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
           if constexpr (MAT) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              const uint32_t idx = e[r] & 0xffffu;
-              const uint32_t sh = (idx & 1u) * 16u;
-              // a hole (idx 0xFFFF, value field 0xFFFF) ORs a zero into slot 0xFFFF
-              const uint32_t old = atomicOr(&region32[idx >> 1], (((e[r] >> 16) + 1u) & 0xffffu) << sh);
-              dup |= ((old >> sh) & 0xffffu) != 0u;  // the slot was taken: duplicate build key
+              // a hole (idx 0xFFFF, value field 0xFFFF) stores 0 into slot 0xFFFF and adds 0 to the row sum
+              const uint32_t val1 = ((e[r] >> 16) + 1u) & 0xffffu;
+              region16[e[r] & 0xffffu] = (uint16_t)val1;
+              part += val1;
             }
           } else {
 #pragma unroll
@@ -640,13 +669,19 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
             }
           }
         }
+        rowsum += part;
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);
         ++it;
       }
     }
+    if constexpr (MAT) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) rowsum += __shfl_xor_sync(0xffffffffu, rowsum, d);
+      if (lane == 0 && rowsum) atomicAdd(&s_rowsum[par], rowsum);
+    }
     sj_bar_consumers();
-    // ---- probe, pass 1: count
+    // ---- probe: one pass
     uint32_t mine = 0;
     for (int sub = 0; sub < a.nsub; ++sub) {
       uint64_t c = a.pcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
@@ -657,93 +692,220 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
         const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
         const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
+        uint4 v[SJ_NPC];
 #pragma unroll
         for (int q = 0; q < SJ_NPC; ++q) {
           const uint32_t piece = (uint32_t)q * SJ_CONS + ct;
-          const uint4 v = piece * 16u < bytes ? st[piece] : HOLES;
-          uint32_t idx[8], val[8];
-          mine += __popc(lookup8(v, idx, val));  // the lookups depend on v: the stage has been read before it is released
+          v[q] = piece * 16u < bytes ? st[piece] : HOLES;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[s]);
-        ++it;
-      }
-    }
-    if constexpr (!MAT) {
-      local_count += mine;
-    } else {
-      // one reservation of the partition's output range
-      mine = __reduce_add_sync(0xffffffffu, mine);
-      if (lane == 0 && mine) atomicAdd(&s_total, mine);
-      sj_bar_consumers();
-      if (ct == 0) {
-        const uint32_t t = s_total;
-        s_base = t ? atomicAdd(&a.ctl->out_cursor, (unsigned long long)t) : 0ull;
-        local_count += t;
-        s_total = 0;
-        s_cur = 0;
-      }
-      sj_bar_consumers();
-      unsigned long long* const okp = a.out_keys + s_base;
-      unsigned long long* const ovp = a.out_vals + s_base;
-      // ---- probe, pass 2: emit
-      for (int sub = 0; sub < a.nsub; ++sub) {
-        uint64_t c = a.pcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
-        if (c > a.cap_p) c = a.cap_p;
-        const uint32_t bytes_total = (uint32_t)(c * 2u);
-        for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
-          const int s = it % SJ_STAGES;
-          mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
-          const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
-          const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
-          uint4 v[SJ_NPC];
 #pragma unroll
-          for (int q = 0; q < SJ_NPC; ++q) {
-            const uint32_t piece = (uint32_t)q * SJ_CONS + ct;
-            v[q] = piece * 16u < bytes ? st[piece] : HOLES;
+        for (int q = 0; q < SJ_NPC; ++q) {
+          uint32_t idx[8], val[8];
+          lookup8(v[q], idx, val);
+          if (q == SJ_NPC - 1) {  // every piece of the stage is in registers (the lookups depend on them)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
           }
+          if constexpr (!MAT) {
 #pragma unroll
-          for (int q = 0; q < SJ_NPC; ++q) {
-            uint32_t idx[8], val[8];
-            const uint32_t hitmask = lookup8(v[q], idx, val);
-            if (q == SJ_NPC - 1) {  // every piece of the stage is in registers and looked up
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&s_empty[s]);
-            }
+            for (int r = 0; r < 8; ++r) mine += val[r] != 0u;
+          } else {
             uint32_t offs[8];
             uint32_t wtot = 0;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              const unsigned bal = __ballot_sync(0xffffffffu, (hitmask >> r) & 1u);
+              const unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0u);
               offs[r] = wtot + __popc(bal & lanemask_lt());
               wtot += __popc(bal);
             }
-            uint32_t wbase = 0;
-            if (lane == 0 && wtot) wbase = atomicAdd(&s_cur, wtot);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (wtot) {  // warp-uniform
+              uint32_t v0 = 0;
+              if (lane == 0) {
+                v0 = atomicAdd(&s_vcur, wtot);
+                const uint32_t bl = (v0 + wtot - 1u) >> SJ_LOG_BLK;
+                if (v0 == 0u) {  // the CTA's first pairs
+                  reserve_block(0u);
+                  reserve_block(1u);
+                } else if (bl != ((v0 - 1u) >> SJ_LOG_BLK)) {  // first to enter block bl
+                  reserve_block(bl + 1u);
+                }
+              }
+              v0 = __shfl_sync(0xffffffffu, v0, 0);
+              const uint32_t b0 = v0 >> SJ_LOG_BLK;
+              // pair number pv of block b lies at base(b) + (pv - b * BLK): fold the block start into the pointers
+              const unsigned long long base0 = block_base(b0) - ((unsigned long long)b0 << SJ_LOG_BLK);
+              unsigned long long* const kp0 = a.out_keys + base0;
+              unsigned long long* const vp0 = a.out_vals + base0;
+              if (((v0 + wtot - 1u) >> SJ_LOG_BLK) == b0) {  // warp-uniform, 15 cases of 16: one block
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              if ((hitmask >> r) & 1u) {
-                const uint32_t o = wbase + offs[r];
-                st_stream(okp + o, (unsigned long long)((idx[r] << a.logp) | plow));  // keys of this path are < 2^32
-                st_stream(ovp + o, (unsigned long long)(val[r] - 1u));
+                for (int r = 0; r < 8; ++r) {
+                  if (val[r] != 0u) {
+                    const uint32_t pv = v0 + offs[r];
+                    st_stream(kp0 + pv, (unsigned long long)((idx[r] << a.logp) | plow));  // keys of this path are < 2^32
+                    st_stream(vp0 + pv, (unsigned long long)(val[r] - 1u));
+                  }
+                }
+              } else {
+                const unsigned long long base1 = block_base(b0 + 1u) - ((unsigned long long)(b0 + 1u) << SJ_LOG_BLK);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                  if (val[r] != 0u) {
+                    const uint32_t pv = v0 + offs[r];
+                    const unsigned long long o = ((pv >> SJ_LOG_BLK) == b0 ? base0 : base1) + pv;
+                    st_stream(a.out_keys + o, (unsigned long long)((idx[r] << a.logp) | plow));
+                    st_stream(a.out_vals + o, (unsigned long long)(val[r] - 1u));
+                  }
+                }
               }
             }
           }
-          ++it;
         }
+        ++it;
       }
     }
-    sj_bar_consumers();  // every probe of this partition is done before the region is zeroed again
-  }
+    local_count += mine;
+    sj_bar_consumers();  // every lookup of this partition is done
+    // ---- clear the addressable part of the region (MAT: and sum its contents)
+    {
+      uint4* r4 = reinterpret_cast<uint4*>(smem);
+      const uint32_t n4 = a.slots / 8u;
+      uint32_t part = 0;
+      for (uint32_t i = ct; i < n4; i += SJ_CONS) {
+        if constexpr (MAT) {
+          const uint4 x = r4[i];
+          part = add_halves(x.x, add_halves(x.y, add_halves(x.z, add_halves(x.w, part))));
+        }
+        r4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if constexpr (MAT) {
+        unsigned long long slotsum = part;  // <= 67 slots x 65535 per thread
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
-  if (lane == 0 && local_count) atomicAdd(&a.ctl->match_count, local_count);
-  if (dup) atomicOr(&a.ctl->flags, CTL_DUP);
+        for (int d = 16; d > 0; d >>= 1) slotsum += __shfl_xor_sync(0xffffffffu, slotsum, d);
+        if (lane == 0 && slotsum) atomicAdd(&s_slotsum[par], slotsum);
+      }
+    }
+    sj_bar_consumers();
+    if constexpr (MAT) {
+      if (ct == 0) {  // the sums of this parity are next touched two partitions (four barriers) from now
+        if (s_rowsum[par] != s_slotsum[par]) atomicOr(&a.ctl->flags, CTL_DUP);
+        s_rowsum[par] = 0;
+        s_slotsum[par] = 0;
+      }
+      par ^= 1u;
+    }
+  }
+  if constexpr (MAT) {
+    sj_bar_consumers();
+    if (ct == 0) {
+      const uint32_t total = s_vcur;
+      unsigned long long* t = a.tails + (size_t)blockIdx.x * SJ_TAIL_WORDS;
+      if (total == 0u) {
+        t[0] = ~0ull;
+      } else {
+        const uint32_t bl = (total - 1u) >> SJ_LOG_BLK;
+        t[0] = block_base(bl);
+        t[1] = total - (bl << SJ_LOG_BLK);
+        t[2] = block_base(bl + 1u);
+        atomicAdd(&a.ctl->match_count, (unsigned long long)total);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
+    if (lane == 0 && local_count) atomicAdd(&a.ctl->match_count, local_count);
+  }
+}
+
+// The pairs k_sjoin<true> wrote occupy [0, R) (R = Ctl::out_cursor, whole blocks) with one or two holes per CTA: the
+// unused tail of its last block and the block it reserved ahead.  Move the pairs at positions >= M (M = Ctl::match_count)
+// into the holes below M, so that the pairs are the dense range [0, M) the C ABI hands out.  Every CTA derives the same
+// (small) tables — holes sorted by position, prefix sums of the hole positions below M (destinations) and of the filled
+// positions at or above M (sources; as many as destinations) — then fills its share of the holes.
+constexpr int PC_MAXH = 512;  // holes: two per k_sjoin CTA
+constexpr int PC_THREADS = 512;
+__device__ __forceinline__ void pc_scan(unsigned long long* x, unsigned long long* tmp, uint32_t n) {  // inclusive, in place; n <= PC_THREADS + 1
+  for (uint32_t d = 1; d < n; d <<= 1) {
+    for (uint32_t i = threadIdx.x; i < n; i += PC_THREADS) tmp[i] = x[i] + (i >= d ? x[i - d] : 0ull);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += PC_THREADS) x[i] = tmp[i];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(PC_THREADS) k_pairs_compact(const Ctl* ctl, const unsigned long long* tails, uint32_t ncta,
+                                                               unsigned long long* out_keys, unsigned long long* out_vals) {
+  __shared__ unsigned long long us[PC_MAXH], ue[PC_MAXH];  // holes as recorded
+  __shared__ unsigned long long hs[PC_MAXH], he[PC_MAXH];  // holes sorted by start, clipped to [0, R]
+  __shared__ unsigned long long dsum[PC_MAXH + 1];         // inclusive prefix sums: hole positions below M
+  __shared__ unsigned long long fs[PC_MAXH + 1], fsum[PC_MAXH + 1];  // filled segments at or above M: start, inclusive prefix sums of lengths
+  __shared__ unsigned long long tmp[PC_MAXH + 1];
+  const unsigned long long R = ctl->out_cursor, M = ctl->match_count;
+  const uint32_t nh = 2u * ncta;
+  for (uint32_t i = threadIdx.x; i < nh; i += PC_THREADS) {
+    const unsigned long long* t = tails + (size_t)(i >> 1) * SJ_TAIL_WORDS;
+    unsigned long long s = R, e = R;
+    if (t[0] != ~0ull) {
+      if (i & 1u) { s = t[2]; e = t[2] + SJ_BLK; }
+      else { s = t[0] + t[1]; e = t[0] + SJ_BLK; }
+      if (s >= e) s = e = R;
+    }
+    us[i] = s;
+    ue[i] = e;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nh; i += PC_THREADS) {  // rank sort (starts are distinct unless the hole is empty)
+    const unsigned long long s = us[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nh; ++j) rank += (us[j] < s) || (us[j] == s && j < i);
+    hs[rank] = s;
+    he[rank] = ue[i];
+  }
+  __syncthreads();
+  // holes are disjoint and sorted: the filled segment in front of hole k starts where hole k - 1 ends (not below M)
+  for (uint32_t k = threadIdx.x; k <= nh; k += PC_THREADS) {
+    const unsigned long long prev_end = k ? (he[k - 1] > M ? he[k - 1] : M) : M;
+    const unsigned long long s = k < nh ? hs[k] : R, e = k < nh ? he[k] : R;
+    const unsigned long long s_hi = s > M ? s : M;
+    fs[k] = prev_end;
+    fsum[k] = s_hi > prev_end ? s_hi - prev_end : 0ull;
+    dsum[k] = k < nh ? (e < M ? e : M) - (s < M ? s : M) : 0ull;
+  }
+  __syncthreads();
+  pc_scan(dsum, tmp, nh + 1);
+  pc_scan(fsum, tmp, nh + 1);
+  // hole k receives the source positions number [dsum[k - 1], dsum[k]) in the order of the filled segments
+  for (uint32_t k = blockIdx.x; k < nh; k += gridDim.x) {
+    unsigned long long t = k ? dsum[k - 1] : 0ull;
+    const unsigned long long t_end = dsum[k];
+    if (t == t_end) continue;
+    unsigned long long dst = hs[k];
+    uint32_t lo = 0, hi = nh + 1;  // smallest j with fsum[j] > t
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (fsum[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    uint32_t j = lo;
+    while (t < t_end) {
+      const unsigned long long seg_before = j ? fsum[j - 1] : 0ull;
+      const unsigned long long src = fs[j] + (t - seg_before);
+      unsigned long long n = fsum[j] - t;
+      if (n > t_end - t) n = t_end - t;
+      for (unsigned long long i = threadIdx.x; i < n; i += PC_THREADS) {
+        out_keys[dst + i] = out_keys[src + i];
+        out_vals[dst + i] = out_vals[src + i];
+      }
+      t += n;
+      dst += n;
+      ++j;
+      while (j <= nh && t < t_end && fsum[j] == (j ? fsum[j - 1] : 0ull)) ++j;  // empty segments
+    }
+  }
 }
 
 size_t sjoin_smem_bytes(uint32_t) { return (size_t)SJ_SLOTS * 2 + (size_t)SJ_STAGES * SJ_CH; }
 uint32_t sjoin_max_slots(const DeviceInfo&) { return 65528; }  // idx 0xFFFF is the hole marker
+uint32_t sjoin_grid(uint32_t p_count, const DeviceInfo& di) { return p_count < (uint32_t)di.sms ? p_count : (uint32_t)di.sms; }
+size_t sjoin_tail_bytes(const DeviceInfo& di) { return (size_t)di.sms * SJ_TAIL_WORDS * 8; }
+uint64_t sjoin_out_slack_pairs(const DeviceInfo& di) { return (uint64_t)di.sms * 2 * SJ_BLK; }
 
 bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (x.p_count == 0) return false;
@@ -751,14 +913,17 @@ bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream
   a.build = static_cast<const unsigned char*>(x.build); a.bcnt = x.bcnt; a.cap_b = x.cap_b;
   a.probe = static_cast<const unsigned char*>(x.probe); a.pcnt = x.pcnt; a.cap_p = x.cap_p;
   a.cnt_stride = x.cnt_stride; a.cstride = x.cursor_stride; a.p_first = x.p_first; a.p_count = x.p_count; a.logp = x.logp; a.nsub = x.nsub;
-  a.slots = x.slots_alloc; a.ctl = x.ctl; a.out_keys = x.out_keys; a.out_vals = x.out_vals;
+  a.slots = x.slots_alloc; a.ctl = x.ctl; a.out_keys = x.out_keys; a.out_vals = x.out_vals; a.tails = x.tails;
   const size_t smem = sjoin_smem_bytes(x.slots_alloc);
   if (smem + 256 > di.smem_optin || (x.slots_alloc & 7u) || x.slots_alloc > 65528u) return false;
   if (x.cap_b * 4 > 0xFFFFFFF0ull || x.cap_p * 2 > 0xFFFFFFF0ull) return false;
-  const uint32_t grid = x.p_count < (uint32_t)di.sms ? x.p_count : (uint32_t)di.sms;
+  const uint32_t grid = sjoin_grid(x.p_count, di);
   if (mat) {
+    if (!x.tails || 2u * grid > (uint32_t)PC_MAXH) return false;
     cudaFuncSetAttribute(k_sjoin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_sjoin<true><<<grid, SJ_THREADS, smem, st>>>(a);
+    k_pairs_compact<<<di.sms, PC_THREADS, 0, st>>>(x.ctl, x.tails, grid, x.out_keys, x.out_vals);
+    ++*launches;
   } else {
     cudaFuncSetAttribute(k_sjoin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_sjoin<false><<<grid, SJ_THREADS, smem, st>>>(a);
