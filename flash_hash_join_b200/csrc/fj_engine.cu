@@ -104,7 +104,7 @@ struct Engine {
   bool inited = false;
   DeviceInfo di;
   cudaStream_t st = nullptr;
-  cudaEvent_t ev[13] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases, 12 build | probe partition pass
+  cudaEvent_t ev[16] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases, 12 build | probe partition pass, 13 end of the result exchange
   Ctl* h_ctl = nullptr;  // pinned
   // multi-GPU count: the ncclAllReduce of the control block is enqueued right behind the first attempt's kernels
   // (before the host has seen the flags), so a step has ONE host synchronisation instead of two.  The summed
@@ -143,6 +143,21 @@ struct Engine {
   } peer;
   fj_status peer_setup();
   void peer_teardown();
+  // peer-memory shuffle (dense key domain): every rank's partition buffers + exchange area, mapped by every rank
+  struct XPart {
+    void* local = nullptr;
+    size_t bytes = 0;
+    std::vector<void*> mapped;           // [world], mapped[rank] == local
+    unsigned long long step = 0;         // advances in lockstep on every rank
+    bool meta_valid = false;             // meta[] = (nb, np) of every rank's slice, as of the last size exchange
+    unsigned long long meta[16] = {};
+    bool broken = false;                 // IPC mapping failed once: the NCCL shuffle answers from now on
+  } xp;
+  fj_status xpart_ensure(size_t bytes);
+  void xpart_teardown();
+  // returns FJ_OK with *handled == false when the data / configuration need the general NCCL shuffle
+  fj_status join_shuffle_peer(unsigned jflags, const unsigned long long* d_bk, const unsigned long long* d_bv, uint64_t nb,
+                              const unsigned long long* d_pk, uint64_t np, fj_stats* s, uint64_t* total, bool* handled);
   fj_status attempt_count_peer(uint64_t dbits, int root, const unsigned long long* bk_root, bool bk_on_device, uint64_t nb,
                                const unsigned long long* pk, uint64_t np, fj_stats* s);
 
@@ -167,6 +182,9 @@ struct Engine {
     cfg["dense_delay_p"] = 3;       // k_djoin: steps between filling a group and probing it (sweep: profiles/r01f_sweep_djoin.jsonl)
     cfg["stage_threads"] = 8;       // host threads staging large pageable inputs through pinned buffers (0: plain cudaMemcpyAsync)
     cfg["stage_min_mb"] = 64;       // smallest pageable input column that is staged
+    cfg["part_warps_kv"] = 16;      // k_part warps per CTA, rows with values (16 | 32)
+    cfg["part_warps_k"] = 16;       // k_part warps per CTA, keys only (16 | 32)
+    cfg["dist_peer_shuffle"] = 1;   // SHUFFLE on a dense key domain: one partition pass storing straight into the owners' buffers
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
     cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
     cfg["dense_fused"] = 1;         // bitmap count as one persistent launch (grid barriers) instead of three kernels
@@ -273,6 +291,7 @@ fj_status Engine::init(int device) {
 
 void Engine::shutdown() {
   if (!inited) return;
+  xpart_teardown();
   peer_teardown();
   dist_destroy(dist);
   cudaStreamSynchronize(st);
@@ -859,9 +878,11 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = a.lpo = dp.logp; a.world = 1; a.nsub = 1; a.sub = 0;
   a.cursor_stride = cs;
   a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.outs[0] = part_a_b.p; a.strict = true;
+  a.warps = (int)(mat ? cfg["part_warps_kv"] : cfg["part_warps_k"]);
   bool launched = launch_part(mat, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[12], st));
   a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.outs[0] = part_a_p.p; a.strict = false;
+  a.warps = (int)cfg["part_warps_k"];
   launched = launched && launch_part(false, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[2], st));
   if (launched) {
@@ -1288,6 +1309,225 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
   return set_err(FJ_ERR_STATE, "internal: shuffle join did not converge");
 }
 
+// ---- SHUFFLE over peer memory (dense key domain; BASELINE.json configs[2] at G > 1) --------------------------
+// ONE partition pass per side (k_part<MULTI>): partition d = low key bits, owner GPU = top log2(world) bits of d; every
+// source stores its sectors straight into the owner's IPC-mapped partition buffer (own sub-region per source, so no
+// cursor is shared between GPUs: rows cross NVLink once, 4 bytes per build row and 2 per probe row), then every GPU joins
+// its P / world partitions in shared memory (k_sjoin).  Three small k_xsync launches replace the collectives: entry
+// barrier + slice-size check, count push + barrier, result exchange.  One host synchronisation per step; no NCCL call
+// in the steady state (the slice sizes are exchanged with ncclAllGather only when some rank's sizes changed).
+fj_status Engine::xpart_ensure(size_t bytes) {
+  if (xp.local && xp.bytes >= bytes) return FJ_OK;
+  const int W = dist.world, R = dist.rank;
+  xpart_teardown();
+  const size_t want = bytes + bytes / 8 + (1 << 20);
+  bool ok = cudaMalloc(&xp.local, want) == cudaSuccess;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) ok = cudaMemset(xp.local, 0, want) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine, xp.local) == cudaSuccess;
+  cudaGetLastError();
+  FJ_TRY(dist_scratch.ensure((size_t)(W + 1) * 64 + 64));
+  unsigned long long* d_h = dist_scratch.as<unsigned long long>();
+  std::vector<cudaIpcMemHandle_t> all((size_t)W);
+  FJ_CUDA(cudaMemcpyAsync(d_h, &mine, 64, cudaMemcpyHostToDevice, st));
+  FJ_TRY(dist_allgather_u64(dist, d_h, d_h + 8, 8, st));
+  FJ_CUDA(cudaMemcpyAsync(all.data(), d_h + 8, (size_t)W * 64, cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  xp.mapped.assign((size_t)W, nullptr);
+  xp.mapped[(size_t)R] = xp.local;
+  for (int r = 0; r < W && ok; ++r) {
+    if (r == R) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+    xp.mapped[(size_t)r] = p;
+  }
+  // everybody or nobody
+  unsigned long long flag = ok ? 1ull : 0ull, sum = 0;
+  FJ_CUDA(cudaMemcpyAsync(d_h, &flag, 8, cudaMemcpyHostToDevice, st));
+  FJ_TRY(dist_allreduce_sum_u64(dist, d_h, d_h + 1, 1, st));
+  FJ_CUDA(cudaMemcpyAsync(&sum, d_h + 1, 8, cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  if (sum != (unsigned long long)W) {
+    xpart_teardown();
+    xp.broken = true;
+    return FJ_OK;
+  }
+  xp.bytes = want;
+  xp.step = 0;  // fresh (zeroed) barrier words on every rank
+  return FJ_OK;
+}
+
+void Engine::xpart_teardown() {
+  if (st) cudaStreamSynchronize(st);
+  for (size_t r = 0; r < xp.mapped.size(); ++r)
+    if (xp.mapped[r] && xp.mapped[r] != xp.local) cudaIpcCloseMemHandle(xp.mapped[r]);
+  xp.mapped.clear();
+  if (xp.local) cudaFree(xp.local);
+  xp.local = nullptr;
+  xp.bytes = 0;
+  cudaGetLastError();
+}
+
+fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d_bk, const unsigned long long* d_bv, uint64_t nb,
+                                    const unsigned long long* d_pk, uint64_t np, fj_stats* s, uint64_t* total, bool* handled) {
+  *handled = false;
+  const int W = dist.world, R = dist.rank;
+  // decided from what every rank knows identically
+  if (!cfg["dist_peer_shuffle"] || !cfg["dense"] || !cfg["dense16"] || !cfg["narrow"] || xp.broken) return FJ_OK;
+  if (jflags & (FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX)) return FJ_OK;
+  if (W < 2 || W > 8 || (W & (W - 1))) return FJ_OK;
+  const bool mat = jflags & FJ_FLAG_MATERIALIZE;
+  int lw = 0;
+  while ((1 << lw) < W) ++lw;
+  Ctl* d_ctl = ctl.as<Ctl>();
+  FJ_TRY(dist_scratch.ensure(4096));
+  pairs_valid = false;
+
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    // ---- slice sizes of every rank (exchanged only when the device-side check of the previous step said so)
+    if (!xp.meta_valid) {
+      unsigned long long mine[2] = {nb, np};
+      unsigned long long* d_m = dist_scratch.as<unsigned long long>();
+      FJ_CUDA(cudaMemcpyAsync(d_m, mine, 16, cudaMemcpyHostToDevice, st));
+      FJ_TRY(dist_allgather_u64(dist, d_m, d_m + 2, 2, st));
+      FJ_CUDA(cudaMemcpyAsync(xp.meta, d_m + 2, 16 * (size_t)W, cudaMemcpyDeviceToHost, st));
+      FJ_CUDA(cudaStreamSynchronize(st));
+      xp.meta_valid = true;
+    }
+    uint64_t nb_tot = 0, np_tot = 0, nb_max = 0, np_max = 0;
+    for (int r = 0; r < W; ++r) {
+      nb_tot += xp.meta[2 * r]; np_tot += xp.meta[2 * r + 1];
+      nb_max = std::max<uint64_t>(nb_max, xp.meta[2 * r]); np_max = std::max<uint64_t>(np_max, xp.meta[2 * r + 1]);
+    }
+    if (nb_tot == 0 || np_tot == 0) return FJ_OK;  // the general path knows how to answer (0, t)
+    // ---- plan (identical on every rank): partitions from the global build side, capacities from the largest slice
+    const Dense16Plan gp = plan_dense16(jflags, nb_tot, np_tot);
+    if (!gp.ok || gp.logp < lw + 4) return FJ_OK;
+    const uint32_t P = 1u << gp.logp, lpo = (uint32_t)(gp.logp - lw), ppo = 1u << lpo;
+    const size_t eb = mat ? 4 : 2;
+    const uint64_t cap_b = round16(cap_build(std::max<uint64_t>(nb_max, 1), P) + ((uint64_t)part_grid(mat, nb_max, di) + 2) * part_sector_elems(mat));
+    const uint64_t cap_p = round16(cap_probe(std::max<uint64_t>(np_max, 1), P) + ((uint64_t)part_grid(false, np_max, di) + 2) * part_sector_elems(false));
+    const size_t ctrl_bytes = (xsync_ctrl_bytes(P) + 255) & ~size_t(255);
+    const size_t b_bytes = ((size_t)P * cap_b * eb + 255) & ~size_t(255);   // ppo partitions x W sources
+    const size_t p_bytes = ((size_t)P * cap_p * 2 + 255) & ~size_t(255);
+    FJ_TRY(xpart_ensure(ctrl_bytes + b_bytes + p_bytes));
+    if (xp.broken) return FJ_OK;
+    const uint32_t cs = part_cursor_stride();
+    FJ_TRY(cursors.ensure(2 * (size_t)P * cs * 4));
+    uint32_t* cur_b = cursors.as<uint32_t>();
+    uint32_t* cur_p = cur_b + (size_t)P * cs;
+    // pairs of my partitions: at most every probe row of the job (skew), expected np_tot / W: allocate for the expected
+    // share with slack and let k_sjoin's block reservation fail loudly beyond it
+    const uint64_t out_rows = np_tot / (uint64_t)W + np_tot / (uint64_t)(4 * W) + (1u << 20);
+    if (mat) {
+      const size_t ob = (size_t)(out_rows + sjoin_out_slack_pairs(di)) * 8;
+      FJ_TRY(out_keys.ensure(ob));
+      FJ_TRY(out_vals.ensure(ob));
+      FJ_TRY(sj_tails.ensure(sjoin_tail_bytes(di)));
+    }
+    unsigned long long* d_res = dist_scratch.as<unsigned long long>() + 64;
+    unsigned long long* h_res = reinterpret_cast<unsigned long long*>(h_spec);  // pinned scratch (8 words)
+
+    int launches = 0;
+    const unsigned long long step = xp.step++;
+    XsyncArgs xa;
+    for (int r = 0; r < W; ++r) xa.ctrl[r] = xp.mapped[(size_t)r];
+    xa.rank = R; xa.world = W; xa.ctl = d_ctl; xa.nb = nb; xa.np = np;
+    for (int i = 0; i < 2 * W; ++i) xa.meta[i] = xp.meta[i];
+    xa.cur_b = cur_b; xa.cur_p = cur_p; xa.cursor_stride = cs; xa.P = P; xa.lpo = lpo; xa.result = d_res;
+
+    FJ_CUDA(cudaEventRecord(ev[0], st));
+    launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st);
+    ++launches;
+    xa.phase = 0; xa.seq = 3 * step + 1;
+    launch_xsync(xa, st, &launches);
+    FJ_CUDA(cudaEventRecord(ev[1], st));
+    PartArgs a;
+    a.ctl = d_ctl; a.klimit = gp.klimit; a.logp = gp.logp; a.lpo = (int)lpo; a.world = W; a.nsub = W; a.sub = R;
+    a.cursor_stride = cs;
+    bool launched = true;
+    if (nb) {
+      for (int r = 0; r < W; ++r) a.outs[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes;
+      a.in_keys = d_bk; a.in_vals = mat ? d_bv : nullptr; a.n = nb; a.cap = cap_b; a.cursor = cur_b; a.strict = true;
+      a.warps = (int)(mat ? cfg["part_warps_kv"] : cfg["part_warps_k"]);
+      launched = launch_part(mat, a, di, st, &launches);
+    }
+    FJ_CUDA(cudaEventRecord(ev[12], st));
+    if (np && launched) {
+      for (int r = 0; r < W; ++r) a.outs[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes + b_bytes;
+      a.in_keys = d_pk; a.in_vals = nullptr; a.n = np; a.cap = cap_p; a.cursor = cur_p; a.strict = false;
+      a.warps = (int)cfg["part_warps_k"];
+      launched = launch_part(false, a, di, st, &launches);
+    }
+    xa.phase = 1; xa.seq = 3 * step + 2;
+    launch_xsync(xa, st, &launches);
+    FJ_CUDA(cudaEventRecord(ev[2], st));
+    if (launched) {
+      const uint32_t* cnt = reinterpret_cast<const uint32_t*>(static_cast<char*>(xp.local) + xsync_count_offset_bytes());
+      SjoinArgs j;
+      j.build = static_cast<char*>(xp.local) + ctrl_bytes; j.cap_b = cap_b;
+      j.probe = static_cast<char*>(xp.local) + ctrl_bytes + b_bytes; j.cap_p = cap_p;
+      j.p_first = (uint32_t)R * ppo; j.p_count = ppo; j.logp = gp.logp; j.nsub = W; j.slots_alloc = gp.slots;
+      // count arrays [source][local partition]; k_sjoin indexes them with the GLOBAL partition id
+      j.cnt_stride = ppo; j.cursor_stride = 1;
+      j.bcnt = cnt - j.p_first; j.pcnt = cnt + (size_t)W * ppo - j.p_first;
+      j.ctl = d_ctl;
+      j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
+      j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
+      j.tails = mat ? sj_tails.as<unsigned long long>() : nullptr;
+      launched = launch_sjoin(mat, j, di, st, &launches);
+    }
+    FJ_CUDA(cudaEventRecord(ev[3], st));
+    xa.phase = 2; xa.seq = 3 * step + 3;
+    launch_xsync(xa, st, &launches);
+    FJ_CUDA(cudaMemcpyAsync(h_res, d_res, 32, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaEventRecord(ev[13], st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    FJ_CUDA(cudaGetLastError());
+    s->kernel_launches += launches;
+    if (!launched) return set_err(FJ_ERR_STATE, "internal: no launch configuration for the peer-memory shuffle");
+    if (h_ctl->flags & CTL_PEER_TIMEOUT) return set_err(FJ_ERR_NCCL, "peer-memory shuffle timed out (a rank did not join the step)");
+    const unsigned gflags = (unsigned)h_res[1];
+    if (gflags & CTL_PEER_TIMEOUT) return set_err(FJ_ERR_NCCL, "peer-memory shuffle timed out on a peer");
+    if (gflags & CTL_META_CHANGED) {  // same verdict on every rank: exchange the sizes and plan again
+      xp.meta_valid = false;
+      continue;
+    }
+    if (gflags & (CTL_NOT_DENSE16 | CTL_OVERFLOW | CTL_DUP)) return FJ_OK;  // same verdict on every rank: the general shuffle answers
+    if (mat) {
+      if (h_ctl->out_cursor < h_ctl->match_count || h_ctl->out_cursor - h_ctl->match_count > sjoin_out_slack_pairs(di))
+        return set_err(FJ_ERR_STATE, "internal: %llu pairs reserved for %llu matches", (unsigned long long)h_ctl->out_cursor,
+                       (unsigned long long)h_ctl->match_count);
+      if (h_ctl->out_cursor > out_rows + sjoin_out_slack_pairs(di))
+        return set_err(FJ_ERR_STATE, "peer-memory shuffle: %llu pairs on this rank exceed the output arena (skewed partitions)",
+                       (unsigned long long)h_ctl->out_cursor);
+      h_ctl->out_cursor = h_ctl->match_count;
+    }
+    s->attempts = attempt + 1;
+    s->clear_s += ms(0, 1) * 1e-3;
+    s->partition_s += ms(1, 2) * 1e-3;
+    s->probe_s += ms(2, 3) * 1e-3;
+    s->comm_s += ms(3, 13) * 1e-3;
+    s->table_bytes = (uint64_t)b_bytes + p_bytes;
+    s->path = FJ_ALGO_RADIX;
+    s->narrow = 1;
+    s->bloom_kind = 0;
+    s->dedup_exact = 0;
+    s->radix_bits1 = gp.logp;
+    s->radix_bits2 = 0;
+    s->dense = 2;
+    s->part_build_us = (int32_t)(ms(1, 12) * 1e3f);
+    s->part_probe_us = (int32_t)(ms(12, 2) * 1e3f);
+    FJ_TRY(finish_attempt(jflags, s));
+    *total = h_res[0];
+    *handled = true;
+    return FJ_OK;
+  }
+  return set_err(FJ_ERR_STATE, "internal: peer-memory shuffle did not settle on the slice sizes");
+}
+
 // ---- peer-memory exchange (CUDA IPC) ------------------------------------------------------------
 // Every rank allocates one exchange buffer, publishes its IPC handle with an ncclAllGather and maps everybody
 // else's buffer.  All ranks must agree on whether the peer path exists, so the per-rank outcome is summed.
@@ -1549,7 +1789,9 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
     }
     FJ_CUDA(cudaEventRecord(ev[4], st));
     uint64_t tot = 0;
-    FJ_TRY(join_shuffle(algo, jflags, d_bk, d_bv, nb, d_pk, np, &s, &tot));
+    bool handled = false;
+    if (algo != FJ_ALGO_SCALAR) FJ_TRY(join_shuffle_peer(jflags, d_bk, d_bv, nb, d_pk, np, &s, &tot, &handled));
+    if (!handled) FJ_TRY(join_shuffle(algo, jflags, d_bk, d_bv, nb, d_pk, np, &s, &tot));
     FJ_CUDA(cudaEventRecord(ev[5], st));
     FJ_CUDA(cudaEventSynchronize(ev[5]));
     s.device_s = ms(4, 5) * 1e-3;  // whole distributed join on this rank, exchange included

@@ -180,6 +180,7 @@ struct PartArgs {
   int logp = 11, lpo = 11;  // log2(partitions), log2(partitions per owner)
   int nsub = 1, sub = 0;    // sub-regions per partition (= sources), this source's index
   bool strict = false;
+  int warps = 16;           // warps per CTA: 16 (2 KB batches per warp) or 32 (1 KB batches)
 };
 size_t part_smem_bytes(int logp);
 uint32_t part_sector_elems(bool val);
@@ -210,6 +211,25 @@ size_t sjoin_tail_bytes(const DeviceInfo& di);
 // launch_sjoin the pairs are the dense range [0, Ctl::match_count) (Ctl::out_cursor counts the blocks reserved)
 uint64_t sjoin_out_slack_pairs(const DeviceInfo& di);
 bool launch_sjoin(bool mat, const SjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
+
+// cross-GPU steps of the peer-memory shuffle (k_xsync, fj_part.cu): phase 0 entry barrier + slice-size check,
+// phase 1 count push + barrier, phase 2 result exchange.  ctrl[r] = rank r's exchange area (peer mapped), whose count
+// arrays (uint32 [2 sides][world][P / world]) start at xsync_count_offset_bytes()
+struct XsyncArgs {
+  void* ctrl[8] = {};
+  int rank = 0, world = 1, phase = 0;
+  unsigned long long seq = 0;
+  Ctl* ctl = nullptr;
+  unsigned long long nb = 0, np = 0;
+  unsigned long long meta[16] = {};
+  const uint32_t* cur_b = nullptr;
+  const uint32_t* cur_p = nullptr;
+  uint32_t cursor_stride = 1, P = 0, lpo = 0;
+  unsigned long long* result = nullptr;
+};
+size_t xsync_ctrl_bytes(uint32_t P);
+size_t xsync_count_offset_bytes();
+void launch_xsync(const XsyncArgs& a, cudaStream_t st, int* launches);
 
 void launch_emit_sentinel(Ctl* ctl, const unsigned long long* bv, unsigned long long* out_keys,
                           unsigned long long* out_vals, bool mat, cudaStream_t st, int* launches);

@@ -45,16 +45,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // ================================================================================= k_part
-constexpr int PT_THREADS = 512;
-constexpr int PT_WARPS = PT_THREADS / 32;
-constexpr int PT_SLOT_BYTES = 2048;           // one batch of one warp: 256 keys, or 128 keys + 128 values
+constexpr int PT_RING_BYTES = 65536;          // input rings of a CTA: 16 warps x 2 slots x 2 KB, or 32 warps x 2 slots x 1 KB
 constexpr int PT_WSLOTS = 2;                  // input ring slots per warp
 constexpr int PT_SECTOR = 32;                 // bytes per flush
 constexpr int PT_RINGB = 2 * PT_SECTOR;       // bytes of staging per partition
 constexpr int PT_MAXP = 2048;                 // flush-list entries keep the partition in 11 bits
 constexpr int PT_MAXW = 8;                    // owners (GPUs) a pass can store to
 constexpr int PT_KEEP = 32;                   // flush-list entries a warp may carry into its next batch
-constexpr int PT_WCAP = 32 * 8 + PT_KEEP;     // flush-list entries per warp: every row of a batch may complete a sector
+constexpr int PT_LIST_BYTES = 20480;          // flush lists of a CTA: warps x (32 x rows per lane and batch + PT_KEEP) x 4 bytes
 constexpr int PT_NQ = 4;                      // sector reservations in flight per lane pair
 constexpr uint32_t PT_NOPLACE = 0xFFFFu;      // nextg: the reservation lies beyond the region
 constexpr uint32_t PT_INFLIGHT = 0xFFFEu;     // nextg: the reservation has been issued, its answer is not published yet
@@ -117,8 +115,14 @@ __device__ __forceinline__ bool piece_has_hole(const uint4& v) {
 //   * Entries that cannot leave yet stay on the list; a warp never blocks (on input data, on a pending row) without
 //     servicing its list, so the oldest sector of every partition can always make progress.
 // MULTI: partitions have owners (several GPUs) and sub-regions per source; else one plain region per partition
-template <bool VAL, bool STRICT, bool MULTI>
-__global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
+// NW: warps per CTA (16: batches of 2 KB per warp; 32: batches of 1 KB)
+template <bool VAL, bool STRICT, bool MULTI, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
+  constexpr int PT_THREADS = NW * 32;
+  constexpr int PT_WARPS = NW;
+  constexpr int PT_SLOT_BYTES = PT_RING_BYTES / (NW * PT_WSLOTS);  // one batch of one warp
+  constexpr int PT_WCAP = 32 * (PT_SLOT_BYTES / (VAL ? 16 : 8) / 32) + PT_KEEP;  // every row of a batch may complete a sector
+  static_assert(NW * PT_WCAP * 4 <= PT_LIST_BYTES, "flush lists do not fit");
   using ET = std::conditional_t<VAL, uint32_t, uint16_t>;
   constexpr uint32_t ES = sizeof(ET);
   constexpr uint32_t EPS = PT_SECTOR / ES;            // elements per sector: 8 | 16
@@ -128,7 +132,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   constexpr int IPT = BROWS / 32;                     // rows per thread and batch: 4 | 8
   constexpr uint32_t FLUSH_ADD = (EPS << 16) - EPS;   // tail += EPS, count -= EPS (count >= EPS: no borrow)
   constexpr uint32_t SPIN_LIMIT = 1u << 22;           // a protocol error must trap, not hang the GPU
-  static_assert(32 * IPT + PT_KEEP <= PT_WCAP, "flush list too small");
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = 1u << a.logp;
   unsigned char* buf = smem;                                               // P x 64 B: two sectors per partition
@@ -137,11 +140,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
   uint32_t* wl = reinterpret_cast<uint32_t*>(nextg + P) + (threadIdx.x >> 5) * PT_WCAP;  // this warp's flush list: d | sector number << 11
   // every warp streams its own batches through its own PT_WSLOTS x 2 KB input ring (a ring shared by the CTA is refilled
   // only when the slowest warp has read a stage: the warps starved, profiles/r02h_c3_dense16_ncu_summary.txt)
-  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 6) + (size_t)PT_WARPS * PT_WCAP * 4 + (size_t)(threadIdx.x >> 5) * PT_WSLOTS * PT_SLOT_BYTES;
+  unsigned char* ring = smem + (size_t)P * (PT_RINGB + 6) + PT_LIST_BYTES + (size_t)(threadIdx.x >> 5) * PT_WSLOTS * PT_SLOT_BYTES;
   __shared__ __align__(8) uint64_t s_full[PT_WARPS * PT_WSLOTS];
   __shared__ unsigned char* s_outs[PT_MAXW];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, wv = tid >> 5, h = tid & 1u;
+  if constexpr (MULTI) {  // the cross-GPU entry barrier gave up (a peer is missing / joins with other sizes): touch nothing
+    if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_PEER_TIMEOUT | CTL_META_CHANGED)) return;
+  }
   const uint32_t GW = gridDim.x * PT_WARPS;          // warps of the grid
   const uint32_t gw = blockIdx.x * PT_WARPS + wv;    // this warp: batches gw, gw + GW, gw + 2 GW, ...
   const uint32_t nbatch = (uint32_t)((a.n + BROWS - 1) / BROWS);
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part(const PartParams a) {
 }
 
 size_t part_smem_bytes(int logp) {
-  return ((size_t)1 << logp) * (PT_RINGB + 6) + (size_t)PT_WARPS * PT_WCAP * 4 + (size_t)PT_WARPS * PT_WSLOTS * PT_SLOT_BYTES;
+  return ((size_t)1 << logp) * (PT_RINGB + 6) + PT_LIST_BYTES + PT_RING_BYTES;
 }
 uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
 // One cursor per 256 bytes: 2048 adjacent 4-byte cursors live in 64 cache lines, i.e. on a handful of L2 slices, and the
@@ -438,7 +444,7 @@ uint32_t part_sector_elems(bool val) { return val ? 8u : 16u; }
 // lts__d_atomic_input_cycles_active max 58 %: profiles/r02e_c3_dense16_ncu_summary.txt)
 uint32_t part_cursor_stride() { return 64u; }
 uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
-  const uint64_t round = (uint64_t)PT_WARPS * (val ? 128 : 256);  // one batch per warp
+  const uint64_t round = val ? 2048 : 4096;  // one batch per warp
   const uint64_t rounds = (n + round - 1) / round;
   return (uint32_t)(rounds < (uint64_t)di.sms ? (rounds ? rounds : 1) : (uint64_t)di.sms);
 }
@@ -456,17 +462,147 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   if (smem + 256 > di.smem_optin) return false;
   const uint32_t grid = part_grid(val, x.n, di);
   const bool multi = x.world > 1 || x.nsub > 1 || x.lpo != x.logp;
-#define FJ_PART(V, S, M)                                                                            \
-  do {                                                                                              \
-    cudaFuncSetAttribute(k_part<V, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    k_part<V, S, M><<<grid, PT_THREADS, smem, st>>>(a);                                            \
+#define FJ_PART4(V, S, M, W)                                                                           \
+  do {                                                                                                 \
+    cudaFuncSetAttribute(k_part<V, S, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_part<V, S, M, W><<<grid, W * 32, smem, st>>>(a);                                                \
   } while (0)
+#define FJ_PART(V, S, M) do { if (x.warps == 32) FJ_PART4(V, S, M, 32); else FJ_PART4(V, S, M, 16); } while (0)
   if (val) { if (multi) FJ_PART(true, true, true); else FJ_PART(true, true, false); }  // rows with values are a build side
   else if (x.strict) { if (multi) FJ_PART(false, true, true); else FJ_PART(false, true, false); }
   else { if (multi) FJ_PART(false, false, true); else FJ_PART(false, false, false); }
 #undef FJ_PART
+#undef FJ_PART4
   ++*launches;
   return true;
+}
+
+// ================================================================================= k_xsync
+// Multi-GPU shuffle over peer memory (one process per GPU, every rank's exchange area mapped by every other rank through
+// CUDA IPC): the cross-GPU steps around k_part<MULTI> and k_sjoin, each ONE small launch on the rank's own stream.
+//   phase 0  entry barrier + size check: every rank posts (nb, np) of its slice into every peer's area and waits for
+//            all of them; afterwards nobody is still reading the partition buffers of the previous step, and every rank
+//            has compared the sizes with the ones the plan (capacities, partition count) was made for
+//            (CTL_META_CHANGED: every rank sees the same vector, so every rank re-plans)
+//   phase 1  count push + barrier: my reservation cursors of the partitions a peer owns go into that peer's count
+//            array (k_sjoin's bcnt / pcnt, indexed [source][local partition]); the barrier that follows makes the
+//            partition rows every rank stored into my buffers, and their counts, visible to my k_sjoin
+//   phase 2  result exchange: (matches, flags, nb, np) of every rank -> sum / or on every rank (replaces ncclAllReduce)
+// Barrier words carry a sequence number (3 * step + phase + 1) and are never reset.  Spins give up after 10 s.
+constexpr int XS_BAR = 0;          // + rank: barrier sequence number posted by `rank`
+constexpr int XS_META = 16;        // + 2 * rank: nb, np of `rank` (phase 0)
+constexpr int XS_RED = 64;         // + 4 * rank: matches, flags, nb, np of `rank` (phase 2)
+constexpr int XS_CNT = 128;        // 64-bit word offset of the count arrays: uint32 [2 sides][world][P / world]
+__device__ __forceinline__ unsigned long long xs_ld_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long xs_ld_relaxed(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void xs_st_release(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void xs_st_relaxed(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool xs_wait_ge(const unsigned long long* p, unsigned long long want) {
+  if (xs_ld_acquire(p) >= want) return true;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    if (xs_ld_acquire(p) >= want) return true;
+    __nanosleep(100);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) return false;
+  }
+}
+struct XsyncParams {
+  unsigned long long* ctrl[PT_MAXW];  // every rank's exchange area (ctrl[rank] is the local one)
+  int rank, world, phase;
+  unsigned long long seq;
+  Ctl* ctl;
+  unsigned long long nb, np;              // this rank's slice
+  unsigned long long meta[2 * PT_MAXW];   // phase 0: the sizes the plan was made for
+  const uint32_t* cur_b;                  // phase 1: this rank's reservation cursors
+  const uint32_t* cur_p;
+  uint32_t cstride, P, lpo;
+  unsigned long long* result;             // phase 2: [4] matches, flags, nb, np over all ranks (local memory)
+};
+__global__ void __launch_bounds__(1024) k_xsync(const XsyncParams a) {
+  const int tid = threadIdx.x;
+  const int W = a.world;
+  unsigned long long* const mine = a.ctrl[a.rank];
+  if (a.phase == 0) {
+    if (tid < W) {
+      xs_st_relaxed(a.ctrl[tid] + XS_META + 2 * a.rank, a.nb);
+      xs_st_relaxed(a.ctrl[tid] + XS_META + 2 * a.rank + 1, a.np);
+    }
+  } else if (a.phase == 1) {
+    const uint32_t ppo = 1u << a.lpo;  // partitions per owner
+    for (uint32_t d = tid; d < a.P; d += blockDim.x) {
+      uint32_t* cnt = reinterpret_cast<uint32_t*>(a.ctrl[d >> a.lpo] + XS_CNT);
+      const uint32_t at = (uint32_t)a.rank * ppo + (d & (ppo - 1u));
+      cnt[at] = a.cur_b[(size_t)d * a.cstride];
+      cnt[(uint32_t)W * ppo + at] = a.cur_p[(size_t)d * a.cstride];
+    }
+  } else {
+    if (tid < W) {
+      unsigned long long* slot = a.ctrl[tid] + XS_RED + 4 * a.rank;
+      xs_st_relaxed(slot, a.ctl->match_count);
+      xs_st_relaxed(slot + 1, (unsigned long long)a.ctl->flags);
+      xs_st_relaxed(slot + 2, a.nb);
+      xs_st_relaxed(slot + 3, a.np);
+    }
+  }
+  __threadfence_system();  // my stores (and the partition rows of the kernels before this one) before the signal
+  __syncthreads();
+  __shared__ int s_ok;
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  if (tid < W) {
+    xs_st_release(a.ctrl[tid] + XS_BAR + a.rank, a.seq);
+    if (!xs_wait_ge(mine + XS_BAR + tid, a.seq)) s_ok = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (!s_ok) {
+      atomicOr(&a.ctl->flags, CTL_PEER_TIMEOUT);
+    } else if (a.phase == 0) {
+      bool same = true;
+      for (int r = 0; r < W; ++r)
+        same &= xs_ld_relaxed(mine + XS_META + 2 * r) == a.meta[2 * r] && xs_ld_relaxed(mine + XS_META + 2 * r + 1) == a.meta[2 * r + 1];
+      if (!same) atomicOr(&a.ctl->flags, CTL_META_CHANGED);
+    } else if (a.phase == 2) {
+      unsigned long long m = 0, f = 0, nb = 0, np = 0;
+      for (int r = 0; r < W; ++r) {
+        const unsigned long long* slot = mine + XS_RED + 4 * r;
+        m += xs_ld_relaxed(slot);
+        f |= xs_ld_relaxed(slot + 1);
+        nb += xs_ld_relaxed(slot + 2);
+        np += xs_ld_relaxed(slot + 3);
+      }
+      a.result[0] = m;
+      a.result[1] = f;
+      a.result[2] = nb;
+      a.result[3] = np;
+    }
+  }
+}
+size_t xsync_ctrl_bytes(uint32_t P) { return (size_t)XS_CNT * 8 + (size_t)2 * P * 4 + 256; }
+size_t xsync_count_offset_bytes() { return (size_t)XS_CNT * 8; }
+void launch_xsync(const XsyncArgs& x, cudaStream_t st, int* launches) {
+  XsyncParams a;
+  for (int i = 0; i < PT_MAXW; ++i) a.ctrl[i] = i < x.world ? static_cast<unsigned long long*>(x.ctrl[i]) : nullptr;
+  a.rank = x.rank; a.world = x.world; a.phase = x.phase; a.seq = x.seq; a.ctl = x.ctl; a.nb = x.nb; a.np = x.np;
+  for (int i = 0; i < 2 * PT_MAXW; ++i) a.meta[i] = x.meta[i];
+  a.cur_b = x.cur_b; a.cur_p = x.cur_p; a.cstride = x.cursor_stride; a.P = x.P; a.lpo = x.lpo; a.result = x.result;
+  k_xsync<<<1, x.phase == 1 ? 1024 : 32, 0, st>>>(a);
+  ++*launches;
 }
 
 // ================================================================================= k_sjoin
@@ -872,31 +1008,37 @@ __global__ void __launch_bounds__(PC_THREADS) k_pairs_compact(const Ctl* ctl, co
   __syncthreads();
   pc_scan(dsum, tmp, nh + 1);
   pc_scan(fsum, tmp, nh + 1);
-  // hole k receives the source positions number [dsum[k - 1], dsum[k]) in the order of the filled segments
+  // hole k receives the sources number [dsum[k - 1], dsum[k]) (numbered along the filled segments); every thread
+  // has all its loads in flight before the first store
   for (uint32_t k = blockIdx.x; k < nh; k += gridDim.x) {
-    unsigned long long t = k ? dsum[k - 1] : 0ull;
-    const unsigned long long t_end = dsum[k];
-    if (t == t_end) continue;
-    unsigned long long dst = hs[k];
-    uint32_t lo = 0, hi = nh + 1;  // smallest j with fsum[j] > t
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (fsum[mid] > t) hi = mid; else lo = mid + 1;
-    }
-    uint32_t j = lo;
-    while (t < t_end) {
-      const unsigned long long seg_before = j ? fsum[j - 1] : 0ull;
-      const unsigned long long src = fs[j] + (t - seg_before);
-      unsigned long long n = fsum[j] - t;
-      if (n > t_end - t) n = t_end - t;
-      for (unsigned long long i = threadIdx.x; i < n; i += PC_THREADS) {
-        out_keys[dst + i] = out_keys[src + i];
-        out_vals[dst + i] = out_vals[src + i];
+    const unsigned long long t0 = k ? dsum[k - 1] : 0ull;
+    const unsigned long long len = dsum[k] - t0;
+    const unsigned long long dst0 = hs[k];
+    for (unsigned long long base = 0; base < len; base += 8ull * PC_THREADS) {
+      unsigned long long kk[8], vv[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const unsigned long long e = base + (unsigned long long)m * PC_THREADS + threadIdx.x;
+        if (e < len) {
+          const unsigned long long t = t0 + e;
+          uint32_t lo = 0, hi = nh + 1;  // smallest j with fsum[j] > t: the segment that holds source t
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (fsum[mid] > t) hi = mid; else lo = mid + 1;
+          }
+          const unsigned long long src = fs[lo] + (t - (lo ? fsum[lo - 1] : 0ull));
+          kk[m] = out_keys[src];
+          vv[m] = out_vals[src];
+        }
       }
-      t += n;
-      dst += n;
-      ++j;
-      while (j <= nh && t < t_end && fsum[j] == (j ? fsum[j - 1] : 0ull)) ++j;  // empty segments
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const unsigned long long e = base + (unsigned long long)m * PC_THREADS + threadIdx.x;
+        if (e < len) {
+          out_keys[dst0 + e] = kk[m];
+          out_vals[dst0 + e] = vv[m];
+        }
+      }
     }
   }
 }

@@ -60,7 +60,7 @@ def main():
                 g, l, sec, st = capi.join_dist(mode, capi.ALGO_ADAPTIVE, flags, 0, bk, bv, pk)
             k, v = capi.pairs() if flags & capi.FLAG_MATERIALIZE else (np.empty(0, np.uint64), np.empty(0, np.uint64))
             gathered = [None] * world
-            dist.all_gather_object(gathered, (l, k, v, sec, st["comm_s"], st["path"]))
+            dist.all_gather_object(gathered, (l, k, v, sec, st["comm_s"], st["path"] + ("/dense%d" % st["dense"] if st["dense"] else "")))
             if rank == 0:
                 fbk, fbv = g2_slice(N, ny, 90, 108, "build", 0, ny)
                 fpk = g2_slice(N, ny, 90, 108, "probe", 0, N)
