@@ -62,17 +62,19 @@ assert n == 3, f"expected 3 materialize returns, patched {n}"
 open(p, 'w').write('\n'.join(out))
 PYEOF
 g++ $CXXFLAGS $INC -I"$TMP/stub" -I"$(dirname "$REF")" "$TMP/hash_join_pairs.cpp" -o "$OUT/pairs/flash_join_pairs$EXT"
-# timing variant: the reference linked against its own vendored allocator with the malloc override on, as its
-# CMakeLists.txt configures it (MI_OVERRIDE / MI_MALLOC_OVERRIDE, :9-16, :23-28) — mimalloc's single-file build
-# (src/static.c) compiled where it lies; the reference's CMake itself is not run.  This module interposes
-# malloc/operator new: it is only ever loaded FIRST in a numpy-only subprocess (bench.py's CPU worker), as the
-# reference's benchmark.py:13 demands; next to torch/pandas it crashes, so parity uses "plain".
+# timing variant: the reference's vendored allocator (mimalloc, /root/reference/mimalloc) as a malloc-overriding shared
+# library, built from its single-file source (src/static.c) where it lies; the reference's CMake itself is not run.
+# bench.py's CPU worker — a numpy-only subprocess — runs the plain module above under LD_PRELOAD of this library, so
+# every allocation of the process (std::vector / make_unique of the hot path included) goes through mimalloc, which is
+# what the reference's CMakeLists.txt (MI_OVERRIDE / MI_MALLOC_OVERRIDE, :9-16, :23-28) arranges.  (Linking mimalloc
+# into the module with hidden symbols crashed: libstdc++ freed the module's blocks with glibc's free.)  Never
+# preloaded next to torch/pandas; parity always uses the plain build.
 MI="$(dirname "$REF")/mimalloc"
 if [ -f "$MI/src/static.c" ]; then
   mkdir -p "$OUT/mimalloc"
-  gcc -O3 -DNDEBUG -DMI_MALLOC_OVERRIDE -DMI_STATIC_LIB -fPIC -fvisibility=hidden -std=gnu11 -fno-builtin-malloc \
-      -ftls-model=initial-exec -I"$MI/include" -c "$MI/src/static.c" -o "$TMP/mimalloc_static.o"
-  g++ $CXXFLAGS $INC -I"$MI/include" "$REF" "$TMP/mimalloc_static.o" -o "$OUT/mimalloc/flash_join$EXT"
-  echo "built: $OUT/mimalloc/flash_join$EXT"
+  rm -f "$OUT/mimalloc/flash_join$EXT"
+  gcc -O3 -DNDEBUG -DMI_MALLOC_OVERRIDE -fPIC -shared -std=gnu11 -fno-builtin-malloc -ftls-model=initial-exec \
+      -I"$MI/include" "$MI/src/static.c" -o "$OUT/mimalloc/libmimalloc_override.so" -lpthread
+  echo "built: $OUT/mimalloc/libmimalloc_override.so"
 fi
 echo "built: $OUT/plain/flash_join$EXT $OUT/pairs/flash_join_pairs$EXT"

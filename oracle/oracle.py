@@ -178,7 +178,7 @@ def checksums(keys, values) -> dict:
 # the compiled reference (oracle/_ref, built by oracle/build_ref.sh from /root/reference)
 # ------------------------------------------------------------------------------------------------
 _ref_cache: dict = {}
-_REF_MODNAME = {"plain": "flash_join", "pairs": "flash_join_pairs", "mimalloc": "flash_join"}
+_REF_MODNAME = {"plain": "flash_join", "pairs": "flash_join_pairs"}
 
 
 def _ref_path(kind: str) -> Path:
@@ -191,9 +191,8 @@ def reference_available(kind: str = "plain") -> bool:
 
 
 def load_reference(kind: str = "plain"):
-    """Import the compiled reference module (kind 'plain', 'pairs', or 'mimalloc' — the latter overrides malloc and
-    must only be loaded first in a numpy-only process, see build_ref.sh) without putting it on
-    sys.path / sys.modules, so it can never shadow the engine's own ``flash_join`` module."""
+    """Import the compiled reference module (kind 'plain' or 'pairs') without putting it on sys.path / sys.modules,
+    so it can never shadow the engine's own ``flash_join`` module."""
     if kind not in _ref_cache:
         p = _ref_path(kind)
         if not p.exists():
@@ -203,6 +202,13 @@ def load_reference(kind: str = "plain"):
         spec.loader.exec_module(mod)
         _ref_cache[kind] = mod
     return _ref_cache[kind]
+
+
+def mimalloc_preload_path():
+    """The reference's vendored allocator as an LD_PRELOAD library (oracle/build_ref.sh), or None.  Only for timing
+    the reference in a numpy-only subprocess (bench.py's CPU worker)."""
+    p = _HERE / "_ref" / "mimalloc" / "libmimalloc_override.so"
+    return p if p.exists() else None
 
 
 def build_reference() -> None:

@@ -56,7 +56,8 @@ capi.generate_g2 = lambda side, *a: (FakeDev(), FakeDev()) if side == "build" el
 capi.config_set = lambda **kw: None
 fj = types.ModuleType("flash_hash_join_b200.flash_join")
 fj.pinned_empty = lambda n: np.zeros(min(n, 1000), dtype=np.uint64)
-for nm in ("hash_join_count_bloom", "hash_join_radix", "adaptive_join_count"):
+fj.last_pairs = lambda: (np.zeros(12345, dtype=np.uint64), np.zeros(12345, dtype=np.uint64))
+for nm in ("hash_join_count_bloom", "hash_join_radix", "adaptive_join_count", "adaptive_join"):
     setattr(fj, nm, lambda bk, bv, pk: (12345, 0.001))
 sys.modules["flash_hash_join_b200.flash_join"] = fj
 pkg.flash_join = fj
