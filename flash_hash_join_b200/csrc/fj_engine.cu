@@ -871,7 +871,7 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   Ctl* d_ctl = ctl.as<Ctl>();
   int launches = 0;
   FJ_CUDA(cudaEventRecord(ev[0], st));
-  launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st);
+  launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st, cs, P, part_cursor_start(mat, nb, di), part_cursor_start(false, np, di));
   ++launches;
   FJ_CUDA(cudaEventRecord(ev[1], st));
   PartArgs a;
@@ -1438,7 +1438,7 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
     xa.cur_b = cur_b; xa.cur_p = cur_p; xa.cursor_stride = cs; xa.P = P; xa.lpo = lpo; xa.result = d_res;
 
     FJ_CUDA(cudaEventRecord(ev[0], st));
-    launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st);
+    launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st, cs, P, part_cursor_start(mat, nb, di), part_cursor_start(false, np, di));
     ++launches;
     xa.phase = 0; xa.seq = 3 * step + 1;
     launch_xsync(xa, st, &launches);

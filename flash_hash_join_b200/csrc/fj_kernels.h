@@ -35,8 +35,10 @@ struct ProbeOut {
 void launch_init_ctl(Ctl* ctl, cudaStream_t st);
 // control block reset + `ones` filled with 0xFF (empty table) + `zeros` cleared, in one launch; sizes are
 // rounded up to 16 bytes (either region may be empty)
+// counter_stride != 0: the zeros region is an array of 32-bit counters, one every counter_stride words (a multiple of
+// 4); counters [0, counters_half) start at value_a, the others at value_b
 void launch_prepare(Ctl* ctl, void* ones, size_t ones_bytes, void* zeros, size_t zeros_bytes, const DeviceInfo& di,
-                    cudaStream_t st);
+                    cudaStream_t st, uint32_t counter_stride = 0, uint32_t counters_half = 0, uint32_t value_a = 0, uint32_t value_b = 0);
 // build kernels: mode 0 = fast (CAS on key, plain value store, raises CTL_DUP on duplicates),
 //                mode 1 = exact keep-first (wide only: value word holds min row index, then fix-up)
 void launch_build(const TableView& t, const unsigned long long* bk, const unsigned long long* bv, uint64_t nb,
@@ -186,6 +188,9 @@ size_t part_smem_bytes(int logp);
 uint32_t part_sector_elems(bool val);
 uint32_t part_cursor_stride();
 uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di);
+// every CTA of a pass starts with sector number blockIdx.x of every partition: the cursors must start at this value
+// (0 when the pass is not launched at all, n == 0)
+uint32_t part_cursor_start(bool val, uint64_t n, const DeviceInfo& di);
 bool launch_part(bool val, const PartArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 struct SjoinArgs {
   const void* build = nullptr;     // regions [(l * nsub + sub) * cap_b, +bcnt): mat: 4-byte idx | value << 16; count: 2-byte idx

@@ -166,11 +166,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   }
   // reservation -> sector index inside the (partition, source) sub-region; PT_NOPLACE when it does not fit
   auto to_sector = [&](uint32_t g) -> uint16_t { return g + EPS <= a.cap ? (uint16_t)(g >> LOG_EPS) : (uint16_t)PT_NOPLACE; };
-  // every slot free, every (CTA, partition) holds one sector reserved in advance
+  // every slot free; every (CTA, partition) holds one sector reserved in advance: sector blockIdx.x to begin with (the
+  // cursors start at gridDim.x sectors, part_cursor_start: no reservation round trips in the prologue)
   for (uint32_t i = tid; i < P * (PT_RINGB / 16); i += PT_THREADS) reinterpret_cast<uint4*>(buf)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   for (uint32_t d = tid; d < P; d += PT_THREADS) {
     w[d] = 0;
-    nextg[d] = to_sector(atomicAdd(a.cursor + d * a.cstride, EPS));
+    nextg[d] = to_sector(blockIdx.x * EPS);
   }
   __syncthreads();
 
@@ -449,6 +450,8 @@ uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
   return (uint32_t)(rounds < (uint64_t)di.sms ? (rounds ? rounds : 1) : (uint64_t)di.sms);
 }
 
+uint32_t part_cursor_start(bool val, uint64_t n, const DeviceInfo& di) { return n ? part_grid(val, n, di) * part_sector_elems(val) : 0u; }
+
 bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (x.logp < 4 || (1 << x.logp) > PT_MAXP || x.world > PT_MAXW || x.n == 0) return false;
   if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= (uint64_t)PT_INFLIGHT) return false;
@@ -462,10 +465,14 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   if (smem + 256 > di.smem_optin) return false;
   const uint32_t grid = part_grid(val, x.n, di);
   const bool multi = x.world > 1 || x.nsub > 1 || x.lpo != x.logp;
-#define FJ_PART4(V, S, M, W)                                                                           \
-  do {                                                                                                 \
-    cudaFuncSetAttribute(k_part<V, S, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    k_part<V, S, M, W><<<grid, W * 32, smem, st>>>(a);                                                \
+#define FJ_PART4(V, S, M, W)                                                                             \
+  do {                                                                                                   \
+    static size_t smem_set = 0; /* the attribute call costs microseconds: once per size */               \
+    if (smem_set != smem) {                                                                              \
+      cudaFuncSetAttribute(k_part<V, S, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      smem_set = smem;                                                                                   \
+    }                                                                                                    \
+    k_part<V, S, M, W><<<grid, W * 32, smem, st>>>(a);                                                  \
   } while (0)
 #define FJ_PART(V, S, M) do { if (x.warps == 32) FJ_PART4(V, S, M, 32); else FJ_PART4(V, S, M, 16); } while (0)
   if (val) { if (multi) FJ_PART(true, true, true); else FJ_PART(true, true, false); }  // rows with values are a build side
@@ -613,7 +620,7 @@ constexpr int SJ_NPC = 2;                 // 16-byte pieces per consumer thread 
 constexpr int SJ_CH = SJ_CONS * 16 * SJ_NPC;  // bytes per ring stage
 constexpr int SJ_STAGES = 3;
 constexpr uint32_t SJ_SLOTS = 65536;      // direct-address slots: every 16-bit index has one (0xFFFF = hole: never set)
-constexpr int SJ_LOG_BLK = 12;            // pairs per output block
+constexpr int SJ_LOG_BLK = 11;            // pairs per output block
 constexpr uint32_t SJ_BLK = 1u << SJ_LOG_BLK;
 constexpr int SJ_NBLK = 8;                // output-block table entries (blocks b - 6 .. b + 1 around the newest one)
 constexpr int SJ_TAIL_WORDS = 4;          // per-CTA record for k_pairs_compact: partial block base, pairs in it, unused block base, -
@@ -1062,12 +1069,14 @@ bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream
   const uint32_t grid = sjoin_grid(x.p_count, di);
   if (mat) {
     if (!x.tails || 2u * grid > (uint32_t)PC_MAXH) return false;
-    cudaFuncSetAttribute(k_sjoin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_mat = false;
+    if (!attr_mat) { cudaFuncSetAttribute(k_sjoin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_mat = true; }
     k_sjoin<true><<<grid, SJ_THREADS, smem, st>>>(a);
     k_pairs_compact<<<di.sms, PC_THREADS, 0, st>>>(x.ctl, x.tails, grid, x.out_keys, x.out_vals);
     ++*launches;
   } else {
-    cudaFuncSetAttribute(k_sjoin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_cnt = false;
+    if (!attr_cnt) { cudaFuncSetAttribute(k_sjoin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_cnt = true; }
     k_sjoin<false><<<grid, SJ_THREADS, smem, st>>>(a);
   }
   ++*launches;

@@ -39,8 +39,11 @@ void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ct
 // One launch instead of {k_init_ctl, cudaMemsetAsync(table), cudaMemsetAsync(bloom | cursors)}: the control
 // block, a 16-byte-granular region filled with all-ones (the empty table, FlashHashTable ctor :98-110) and a
 // 16-byte-granular region of zeros (the Bloom filter, or the partition cursors of the radix path).
+// Optionally the zeros region is an array of strided 32-bit counters (k_part's reservation cursors, one every `cs` words,
+// cs a multiple of 4): counter d starts at va (d < half) or vb instead of 0.
 __global__ void __launch_bounds__(512) k_prepare(Ctl* __restrict__ ctl, uint4* __restrict__ ones, uint64_t n_ones,
-                                                 uint4* __restrict__ zeros, uint64_t n_zeros) {
+                                                 uint4* __restrict__ zeros, uint64_t n_zeros, uint32_t cs, uint32_t half, uint32_t va,
+                                                 uint32_t vb) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t == 0) {
@@ -57,17 +60,26 @@ __global__ void __launch_bounds__(512) k_prepare(Ctl* __restrict__ ctl, uint4* _
   }
   const uint4 f = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0u, 0u, 0u, 0u);
   for (uint64_t i = t; i < n_ones; i += stride) ones[i] = f;
-  for (uint64_t i = t; i < n_zeros; i += stride) zeros[i] = z;
+  if (cs == 0) {
+    for (uint64_t i = t; i < n_zeros; i += stride) zeros[i] = z;
+  } else {
+    const uint32_t q = cs / 4;  // 16-byte pieces per counter
+    for (uint64_t i = t; i < n_zeros; i += stride) {
+      const uint64_t d = i / q;
+      zeros[i] = (i % q == 0) ? make_uint4(d < half ? va : vb, 0u, 0u, 0u) : z;
+    }
+  }
 }
 // ones_bytes / zeros_bytes are rounded UP to 16 bytes: the buffers behind them come from the engine's arena,
 // whose allocations are 256-byte granular
 void launch_prepare(Ctl* ctl, void* ones, size_t ones_bytes, void* zeros, size_t zeros_bytes, const DeviceInfo& di,
-                    cudaStream_t st) {
+                    cudaStream_t st, uint32_t counter_stride, uint32_t counters_half, uint32_t value_a, uint32_t value_b) {
   const uint64_t n1 = (ones_bytes + 15) / 16, n0 = (zeros_bytes + 15) / 16;
   const uint64_t want = (std::max(n1, n0) + 511) / 512;
   const uint64_t cap = (uint64_t)di.sms * 8;
   const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
-  k_prepare<<<grid, 512, 0, st>>>(ctl, static_cast<uint4*>(ones), n1, static_cast<uint4*>(zeros), n0);
+  k_prepare<<<grid, 512, 0, st>>>(ctl, static_cast<uint4*>(ones), n1, static_cast<uint4*>(zeros), n0, counter_stride & ~3u, counters_half, value_a,
+                                  value_b);
 }
 
 // =================================================================================== build
