@@ -875,20 +875,20 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   ++launches;
   FJ_CUDA(cudaEventRecord(ev[1], st));
   PartArgs a;
-  a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = a.lpo = dp.logp; a.world = 1; a.nsub = 1; a.sub = 0;
+  a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = dp.logp;
   a.cursor_stride = cs;
-  a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.outs[0] = part_a_b.p; a.strict = true;
+  a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.out = part_a_b.p; a.strict = true;
   a.warps = (int)(mat ? cfg["part_warps_kv"] : cfg["part_warps_k"]);
   bool launched = launch_part(mat, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[12], st));
-  a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.outs[0] = part_a_p.p; a.strict = false;
+  a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.out = part_a_p.p; a.strict = false;
   a.warps = (int)cfg["part_warps_k"];
   launched = launched && launch_part(false, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[2], st));
   if (launched) {
     SjoinArgs j;
-    j.build = part_a_b.p; j.bcnt = cur_b; j.cap_b = dp.cap_b;
-    j.probe = part_a_p.p; j.pcnt = cur_p; j.cap_p = dp.cap_p;
+    j.build[0] = part_a_b.p; j.bcnt = cur_b; j.cap_b = dp.cap_b;
+    j.probe[0] = part_a_p.p; j.pcnt = cur_p; j.cap_p = dp.cap_p;
     j.cnt_stride = 0; j.cursor_stride = cs; j.p_first = 0; j.p_count = P; j.logp = dp.logp; j.nsub = 1; j.slots_alloc = dp.slots;
     j.ctl = d_ctl;
     j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
@@ -1310,12 +1310,15 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
 }
 
 // ---- SHUFFLE over peer memory (dense key domain; BASELINE.json configs[2] at G > 1) --------------------------
-// ONE partition pass per side (k_part<MULTI>): partition d = low key bits, owner GPU = top log2(world) bits of d; every
-// source stores its sectors straight into the owner's IPC-mapped partition buffer (own sub-region per source, so no
-// cursor is shared between GPUs: rows cross NVLink once, 4 bytes per build row and 2 per probe row), then every GPU joins
-// its P / world partitions in shared memory (k_sjoin).  Three small k_xsync launches replace the collectives: entry
-// barrier + slice-size check, count push + barrier, result exchange.  One host synchronisation per step; no NCCL call
-// in the steady state (the slice sizes are exchanged with ncclAllGather only when some rank's sizes changed).
+// ONE partition pass per side (k_part): partition d = low key bits, owner GPU = top log2(world) bits of d.  Every GPU
+// partitions its slice into its OWN IPC-mapped partition buffer at local speed; the owner of a partition then PULLS its
+// rows from every source's buffer with the bulk copies (TMA, chunks of up to 31 KB) that feed k_sjoin's input ring, so
+// rows cross NVLink once (4 bytes per build row, 2 per probe row), in large transfers, overlapped with the join.
+// (Storing the 32-byte sectors straight into the owner's buffer from k_part was measured first: NVLink moved only
+// ~200 GB/s per GPU in 32-byte writes and the partition pass did not scale — profiles/r02q_bench_n4_peer_store.json.)
+// Three small k_xsync launches replace the collectives: entry barrier + slice-size check, count push + barrier, result
+// exchange.  One host synchronisation per step; no NCCL call in the steady state (the slice sizes are exchanged with
+// ncclAllGather only when some rank's sizes changed).
 fj_status Engine::xpart_ensure(size_t bytes) {
   if (xp.local && xp.bytes >= bytes) return FJ_OK;
   const int W = dist.world, R = dist.rank;
@@ -1444,18 +1447,18 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
     launch_xsync(xa, st, &launches);
     FJ_CUDA(cudaEventRecord(ev[1], st));
     PartArgs a;
-    a.ctl = d_ctl; a.klimit = gp.klimit; a.logp = gp.logp; a.lpo = (int)lpo; a.world = W; a.nsub = W; a.sub = R;
+    a.ctl = d_ctl; a.klimit = gp.klimit; a.logp = gp.logp;
     a.cursor_stride = cs;
     bool launched = true;
     if (nb) {
-      for (int r = 0; r < W; ++r) a.outs[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes;
+      a.out = static_cast<char*>(xp.local) + ctrl_bytes;
       a.in_keys = d_bk; a.in_vals = mat ? d_bv : nullptr; a.n = nb; a.cap = cap_b; a.cursor = cur_b; a.strict = true;
       a.warps = (int)(mat ? cfg["part_warps_kv"] : cfg["part_warps_k"]);
       launched = launch_part(mat, a, di, st, &launches);
     }
     FJ_CUDA(cudaEventRecord(ev[12], st));
     if (np && launched) {
-      for (int r = 0; r < W; ++r) a.outs[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes + b_bytes;
+      a.out = static_cast<char*>(xp.local) + ctrl_bytes + b_bytes;
       a.in_keys = d_pk; a.in_vals = nullptr; a.n = np; a.cap = cap_p; a.cursor = cur_p; a.strict = false;
       a.warps = (int)cfg["part_warps_k"];
       launched = launch_part(false, a, di, st, &launches);
@@ -1466,8 +1469,11 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
     if (launched) {
       const uint32_t* cnt = reinterpret_cast<const uint32_t*>(static_cast<char*>(xp.local) + xsync_count_offset_bytes());
       SjoinArgs j;
-      j.build = static_cast<char*>(xp.local) + ctrl_bytes; j.cap_b = cap_b;
-      j.probe = static_cast<char*>(xp.local) + ctrl_bytes + b_bytes; j.cap_p = cap_p;
+      for (int r = 0; r < W; ++r) {  // source r keeps its rows of my partitions in ITS buffer: pulled over NVLink by k_sjoin's bulk copies
+        j.build[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes;
+        j.probe[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes + b_bytes;
+      }
+      j.cap_b = cap_b; j.cap_p = cap_p;
       j.p_first = (uint32_t)R * ppo; j.p_count = ppo; j.logp = gp.logp; j.nsub = W; j.slots_alloc = gp.slots;
       // count arrays [source][local partition]; k_sjoin indexes them with the GLOBAL partition id
       j.cnt_stride = ppo; j.cursor_stride = 1;

@@ -166,21 +166,19 @@ bool launch_djoin(bool mat, const DjoinArgs& a, const DeviceInfo& di, cudaStream
 // dense key domain, round 2 (fj_part.cu): ONE partition pass by the low `logp` key bits with per-SM write-combining
 // sector buffers (k_part), rows reduced to idx = key >> logp (build: idx | value << 16, 4 bytes; probe: idx, 2 bytes),
 // then a direct-address join whose region lives in shared memory (k_sjoin).  The same kernels serve the multi-GPU
-// shuffle: a partition's owner GPU is d >> lpo, `outs[owner]` its (peer-mapped) partition buffer, and every source
-// writes its own sub-region, so no cursor is shared between GPUs.
+// shuffle: every GPU partitions its slice into its OWN (IPC-mapped) partition buffer, and the owner of a partition
+// pulls its rows from every source's buffer with the bulk copies that feed k_sjoin's input ring.
 struct PartArgs {
   const unsigned long long* in_keys = nullptr;
   const unsigned long long* in_vals = nullptr;  // val == true only
   uint64_t n = 0;
   uint64_t klimit = 0;   // keys >= klimit are outside the domain (strict: CTL_NOT_DENSE16; else the row is dropped)
-  uint64_t cap = 0;      // elements per (partition, sub-region), multiple of 16
-  uint32_t* cursor = nullptr;  // [2^logp * cursor_stride], zeroed: elements reserved per partition by THIS source
+  uint64_t cap = 0;      // elements per partition, multiple of 16
+  uint32_t* cursor = nullptr;  // [2^logp * cursor_stride], starting at part_cursor_start(): elements reserved per partition
   uint32_t cursor_stride = 1;  // 32-bit words between two cursors
   Ctl* ctl = nullptr;
-  void* outs[8] = {};    // [world] base of every owner's partition buffer
-  int world = 1;
-  int logp = 11, lpo = 11;  // log2(partitions), log2(partitions per owner)
-  int nsub = 1, sub = 0;    // sub-regions per partition (= sources), this source's index
+  void* out = nullptr;   // partition buffer: partition d at elements [d * cap, d * cap + cursor[d])
+  int logp = 11;         // log2(partitions)
   bool strict = false;
   int warps = 16;           // warps per CTA: 16 (2 KB batches per warp) or 32 (1 KB batches)
 };
@@ -193,10 +191,11 @@ uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di);
 uint32_t part_cursor_start(bool val, uint64_t n, const DeviceInfo& di);
 bool launch_part(bool val, const PartArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 struct SjoinArgs {
-  const void* build = nullptr;     // regions [(l * nsub + sub) * cap_b, +bcnt): mat: 4-byte idx | value << 16; count: 2-byte idx
+  const void* build[8] = {};       // [nsub] every source's partition buffer (peer mapped for remote sources): partition p at
+                                   // elements [p * cap_b, +bcnt); mat: 4-byte idx | value << 16; count: 2-byte idx
   const uint32_t* bcnt = nullptr;  // bcnt[sub * cnt_stride + p]
   uint64_t cap_b = 0;
-  const void* probe = nullptr;     // 2-byte idx
+  const void* probe[8] = {};       // 2-byte idx
   const uint32_t* pcnt = nullptr;
   uint64_t cap_p = 0;
   uint32_t cnt_stride = 0;

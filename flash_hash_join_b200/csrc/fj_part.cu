@@ -50,7 +50,7 @@ constexpr int PT_WSLOTS = 2;                  // input ring slots per warp
 constexpr int PT_SECTOR = 32;                 // bytes per flush
 constexpr int PT_RINGB = 2 * PT_SECTOR;       // bytes of staging per partition
 constexpr int PT_MAXP = 2048;                 // flush-list entries keep the partition in 11 bits
-constexpr int PT_MAXW = 8;                    // owners (GPUs) a pass can store to
+constexpr int PT_MAXW = 8;                    // GPUs of a peer-memory shuffle (sources a partition is pulled from)
 constexpr int PT_KEEP = 32;                   // flush-list entries a warp may carry into its next batch
 constexpr int PT_LIST_BYTES = 20480;          // flush lists of a CTA: warps x (32 x rows per lane and batch + PT_KEEP) x 4 bytes
 constexpr int PT_NQ = 4;                      // sector reservations in flight per lane pair
@@ -66,10 +66,8 @@ struct PartParams {
   uint32_t* cursor;    // [P * cstride] elements reserved per partition (this source)
   uint32_t cstride;    // 32-bit words between two cursors (see fj_kernels.h: part_cursor_stride)
   Ctl* ctl;
-  void* outs[PT_MAXW]; // base of every owner's partition buffer (peer-mapped for remote owners)
+  void* out;           // partition buffer: partition d occupies elements [d * cap, d * cap + cursor[d])
   int logp;            // log2(partitions)
-  int lpo;             // log2(partitions per owner)
-  int nsub, sub;       // sub-regions per partition on the owner (= sources) and this source's index
 };
 
 __device__ __forceinline__ uint32_t lds_v32(const void* p) {
@@ -114,9 +112,8 @@ __device__ __forceinline__ bool piece_has_hole(const uint4& v) {
 //     reservation of the partition's next global sector, whose answer is published a batch later.
 //   * Entries that cannot leave yet stay on the list; a warp never blocks (on input data, on a pending row) without
 //     servicing its list, so the oldest sector of every partition can always make progress.
-// MULTI: partitions have owners (several GPUs) and sub-regions per source; else one plain region per partition
 // NW: warps per CTA (16: batches of 2 KB per warp; 32: batches of 1 KB)
-template <bool VAL, bool STRICT, bool MULTI, int NW>
+template <bool VAL, bool STRICT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   constexpr int PT_THREADS = NW * 32;
   constexpr int PT_WARPS = NW;
@@ -142,25 +139,21 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   // only when the slowest warp has read a stage: the warps starved, profiles/r02h_c3_dense16_ncu_summary.txt)
   unsigned char* ring = smem + (size_t)P * (PT_RINGB + 6) + PT_LIST_BYTES + (size_t)(threadIdx.x >> 5) * PT_WSLOTS * PT_SLOT_BYTES;
   __shared__ __align__(8) uint64_t s_full[PT_WARPS * PT_WSLOTS];
-  __shared__ unsigned char* s_outs[PT_MAXW];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, wv = tid >> 5, h = tid & 1u;
-  if constexpr (MULTI) {  // the cross-GPU entry barrier gave up (a peer is missing / joins with other sizes): touch nothing
-    if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_PEER_TIMEOUT | CTL_META_CHANGED)) return;
-  }
+  // multi-GPU shuffle: the cross-GPU entry barrier gave up (a peer is missing / joins with other sizes) — peers may
+  // still be reading the partition buffers of the previous step: touch nothing
+  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_PEER_TIMEOUT | CTL_META_CHANGED)) return;
   const uint32_t GW = gridDim.x * PT_WARPS;          // warps of the grid
   const uint32_t gw = blockIdx.x * PT_WARPS + wv;    // this warp: batches gw, gw + GW, gw + 2 GW, ...
   const uint32_t nbatch = (uint32_t)((a.n + BROWS - 1) / BROWS);
   const bool aligned = ((reinterpret_cast<uintptr_t>(a.in_keys) | (VAL ? reinterpret_cast<uintptr_t>(a.in_vals) : 0)) & 15u) == 0;
   const uint32_t nfull = aligned ? (uint32_t)(a.n / BROWS) : 0u;  // batches below nfull arrive through the TMA ring
   uint64_t* const my_full = s_full + wv * PT_WSLOTS;
-  const uint32_t lpo_mask = (1u << a.lpo) - 1u;
   const uint32_t capsec = a.cap >> LOG_EPS;
   const uint32_t pmask = P - 1u;
 
   if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < PT_MAXW; ++i) s_outs[i] = static_cast<unsigned char*>(a.outs[i]);  // static indices: no local copy
     for (int s = 0; s < PT_WARPS * PT_WSLOTS; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
@@ -191,7 +184,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
     for (uint32_t kk = 0; kk < PT_WSLOTS; ++kk) issue(kk);
   }
 
-  unsigned char* const out0 = static_cast<unsigned char*>(a.outs[0]);  // owner 0 (the only one on a single GPU): no table lookup
+  unsigned char* const out0 = static_cast<unsigned char*>(a.out);
   // half hh (16 bytes) of one 32-byte sector of partition d -> sector gs of its sub-region in the owner's buffer.  Two
   // lanes share a sector, so a warp moves 16 sectors with ONE 128-bit store.
   auto store_half = [&](uint32_t d, uint32_t gs, uint32_t hh, const uint4& v) {
@@ -199,14 +192,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
       if (hh == 0) atomicOr(&a.ctl->flags, CTL_OVERFLOW);
       return;
     }
-    unsigned char* dst;
-    if constexpr (MULTI) {
-      const uint32_t region = (d & lpo_mask) * (uint32_t)a.nsub + (uint32_t)a.sub;
-      const uint32_t owner = d >> a.lpo;
-      dst = (owner ? s_outs[owner] : out0) + (((uint64_t)region * capsec + gs) << 5);
-    } else {
-      dst = out0 + (((uint64_t)d * capsec + gs) << 5);
-    }
+    unsigned char* dst = out0 + (((uint64_t)d * capsec + gs) << 5);
     reinterpret_cast<uint4*>(dst)[hh] = v;
   };
 
@@ -453,31 +439,28 @@ uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di) {
 uint32_t part_cursor_start(bool val, uint64_t n, const DeviceInfo& di) { return n ? part_grid(val, n, di) * part_sector_elems(val) : 0u; }
 
 bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
-  if (x.logp < 4 || (1 << x.logp) > PT_MAXP || x.world > PT_MAXW || x.n == 0) return false;
+  if (x.logp < 4 || (1 << x.logp) > PT_MAXP || x.n == 0) return false;
   if (x.klimit > 0xFFFFFFFFull || x.cap > 0xFFFFFFF0ull || (x.cap & 15u) || (x.cap >> (val ? 3 : 4)) >= (uint64_t)PT_INFLIGHT) return false;
   if ((x.n + 127) / 128 > 0xFFFFFFF0ull) return false;
   PartParams a;
   a.in_keys = x.in_keys; a.in_vals = x.in_vals; a.n = x.n; a.klimit = (uint32_t)x.klimit; a.cap = (uint32_t)x.cap; a.cursor = x.cursor; a.cstride = x.cursor_stride;
-  a.ctl = x.ctl;
-  for (int i = 0; i < PT_MAXW; ++i) a.outs[i] = i < x.world ? x.outs[i] : nullptr;
-  a.logp = x.logp; a.lpo = x.lpo; a.nsub = x.nsub; a.sub = x.sub;
+  a.ctl = x.ctl; a.out = x.out; a.logp = x.logp;
   const size_t smem = part_smem_bytes(x.logp);
   if (smem + 256 > di.smem_optin) return false;
   const uint32_t grid = part_grid(val, x.n, di);
-  const bool multi = x.world > 1 || x.nsub > 1 || x.lpo != x.logp;
-#define FJ_PART4(V, S, M, W)                                                                             \
-  do {                                                                                                   \
-    static size_t smem_set = 0; /* the attribute call costs microseconds: once per size */               \
-    if (smem_set != smem) {                                                                              \
-      cudaFuncSetAttribute(k_part<V, S, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      smem_set = smem;                                                                                   \
-    }                                                                                                    \
-    k_part<V, S, M, W><<<grid, W * 32, smem, st>>>(a);                                                  \
+#define FJ_PART4(V, S, W)                                                                             \
+  do {                                                                                                \
+    static size_t smem_set = 0; /* the attribute call costs microseconds: once per size */            \
+    if (smem_set != smem) {                                                                           \
+      cudaFuncSetAttribute(k_part<V, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      smem_set = smem;                                                                                \
+    }                                                                                                 \
+    k_part<V, S, W><<<grid, W * 32, smem, st>>>(a);                                                  \
   } while (0)
-#define FJ_PART(V, S, M) do { if (x.warps == 32) FJ_PART4(V, S, M, 32); else FJ_PART4(V, S, M, 16); } while (0)
-  if (val) { if (multi) FJ_PART(true, true, true); else FJ_PART(true, true, false); }  // rows with values are a build side
-  else if (x.strict) { if (multi) FJ_PART(false, true, true); else FJ_PART(false, true, false); }
-  else { if (multi) FJ_PART(false, false, true); else FJ_PART(false, false, false); }
+#define FJ_PART(V, S) do { if (x.warps == 32) FJ_PART4(V, S, 32); else FJ_PART4(V, S, 16); } while (0)
+  if (val) FJ_PART(true, true);  // rows with values are a build side
+  else if (x.strict) FJ_PART(false, true);
+  else FJ_PART(false, false);
 #undef FJ_PART
 #undef FJ_PART4
   ++*launches;
@@ -486,14 +469,14 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
 
 // ================================================================================= k_xsync
 // Multi-GPU shuffle over peer memory (one process per GPU, every rank's exchange area mapped by every other rank through
-// CUDA IPC): the cross-GPU steps around k_part<MULTI> and k_sjoin, each ONE small launch on the rank's own stream.
+// CUDA IPC): the cross-GPU steps around k_part and k_sjoin, each ONE small launch on the rank's own stream.
 //   phase 0  entry barrier + size check: every rank posts (nb, np) of its slice into every peer's area and waits for
 //            all of them; afterwards nobody is still reading the partition buffers of the previous step, and every rank
 //            has compared the sizes with the ones the plan (capacities, partition count) was made for
 //            (CTL_META_CHANGED: every rank sees the same vector, so every rank re-plans)
 //   phase 1  count push + barrier: my reservation cursors of the partitions a peer owns go into that peer's count
-//            array (k_sjoin's bcnt / pcnt, indexed [source][local partition]); the barrier that follows makes the
-//            partition rows every rank stored into my buffers, and their counts, visible to my k_sjoin
+//            array (k_sjoin's bcnt / pcnt, indexed [source][local partition]); after the barrier that follows every
+//            rank's partition pass is complete and visible, so k_sjoin may pull partition rows from every peer
 //   phase 2  result exchange: (matches, flags, nb, np) of every rank -> sum / or on every rank (replaces ncclAllReduce)
 // Barrier words carry a sequence number (3 * step + phase + 1) and are never reset.  Spins give up after 10 s.
 constexpr int XS_BAR = 0;          // + rank: barrier sequence number posted by `rank`
@@ -626,10 +609,10 @@ constexpr int SJ_NBLK = 8;                // output-block table entries (blocks 
 constexpr int SJ_TAIL_WORDS = 4;          // per-CTA record for k_pairs_compact: partial block base, pairs in it, unused block base, -
 
 struct SjoinParams {
-  const unsigned char* build;  // regions of cap_b elements (MAT: 4 bytes idx | value << 16; count: 2 bytes idx)
+  const unsigned char* build[PT_MAXW];  // per source: partition p at elements [p * cap_b, +count) (MAT: 4 bytes idx | value << 16; count: 2 bytes idx)
   const uint32_t* bcnt;        // elements written: bcnt[sub * cnt_stride + p]
   uint64_t cap_b;
-  const unsigned char* probe;  // regions of cap_p 2-byte elements
+  const unsigned char* probe[PT_MAXW];  // per source: partition p at 2-byte elements [p * cap_p, +count)
   const uint32_t* pcnt;
   uint64_t cap_p;
   uint32_t cnt_stride, cstride;  // cursor of (sub, p) = cnt[(sub * cnt_stride + p) * cstride]
@@ -722,12 +705,13 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         const uint32_t* cnt = side ? a.pcnt : a.bcnt;
         const uint64_t cap = side ? a.cap_p : a.cap_b;
         const uint32_t eb = side ? 2u : EB;
-        const unsigned char* base = side ? a.probe : a.build;
         for (int sub = 0; sub < a.nsub; ++sub) {
           uint64_t c = cnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
           if (c > cap) c = cap;
           const uint64_t bytes_total = c * eb;  // multiple of 32 (sectors)
-          const unsigned char* src = base + ((uint64_t)l * (uint32_t)a.nsub + (uint32_t)sub) * cap * eb;
+          // source `sub` keeps the rows of partition p in ITS partition buffer (local, or a peer's over NVLink: the bulk
+          // copies below pull them in chunks of up to 31 KB)
+          const unsigned char* src = (side ? a.probe[sub] : a.build[sub]) + (uint64_t)(a.p_first + l) * cap * eb;
           for (uint64_t off = 0; off < bytes_total; off += SJ_CH) {
             const int s = it % SJ_STAGES;
             mbar_wait_bounded(&s_empty[s], ((it / SJ_STAGES) & 1u) ^ 1u);
@@ -1059,8 +1043,12 @@ uint64_t sjoin_out_slack_pairs(const DeviceInfo& di) { return (uint64_t)di.sms *
 bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (x.p_count == 0) return false;
   SjoinParams a;
-  a.build = static_cast<const unsigned char*>(x.build); a.bcnt = x.bcnt; a.cap_b = x.cap_b;
-  a.probe = static_cast<const unsigned char*>(x.probe); a.pcnt = x.pcnt; a.cap_p = x.cap_p;
+  if (x.nsub < 1 || x.nsub > PT_MAXW) return false;
+  for (int i = 0; i < PT_MAXW; ++i) {
+    a.build[i] = static_cast<const unsigned char*>(i < x.nsub ? x.build[i] : nullptr);
+    a.probe[i] = static_cast<const unsigned char*>(i < x.nsub ? x.probe[i] : nullptr);
+  }
+  a.bcnt = x.bcnt; a.cap_b = x.cap_b; a.pcnt = x.pcnt; a.cap_p = x.cap_p;
   a.cnt_stride = x.cnt_stride; a.cstride = x.cursor_stride; a.p_first = x.p_first; a.p_count = x.p_count; a.logp = x.logp; a.nsub = x.nsub;
   a.slots = x.slots_alloc; a.ctl = x.ctl; a.out_keys = x.out_keys; a.out_vals = x.out_vals; a.tails = x.tails;
   const size_t smem = sjoin_smem_bytes(x.slots_alloc);

@@ -17,6 +17,10 @@ if has check; then
   echo "dist_check exit $?" >> "$OUT/dist_check.log"
   tail -n 4 "$OUT/dist_check.log" | cut -c1-3000
 fi
+if has bench; then  # the contract line at N GPUs: C3 strong scaling + C4 / C2 under other_configs
+  timeout 900 $TR --master-port 29517 bench.py --gpus $N --steps 20 --warmup 3 > "$OUT/bench_n$N.json" 2> "$OUT/bench_n$N.err"
+  echo "bench exit $?"; cut -c1-1500 "$OUT/bench_n$N.json"; tail -3 "$OUT/bench_n$N.err"
+fi
 if has bench_c3; then
   timeout 400 $TR --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --config C3 > "$OUT/bench_c3_n$N.json" 2> "$OUT/bench_c3_n$N.err"
   echo "bench c3 exit $?"; cat "$OUT/bench_c3_n$N.json"; tail -3 "$OUT/bench_c3_n$N.err"
