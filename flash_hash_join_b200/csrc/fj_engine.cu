@@ -143,6 +143,9 @@ struct Engine {
   } peer;
   fj_status peer_setup();
   void peer_teardown();
+  // every rank passes the status of its rank-local work; every rank gets FJ_OK only if all did (one 8-byte
+  // ncclAllReduce): no rank may walk into a data collective its peers will never enter
+  fj_status agree(fj_status local);
   // peer-memory shuffle (dense key domain): every rank's partition buffers + exchange area, mapped by every rank
   struct XPart {
     void* local = nullptr;
@@ -254,7 +257,11 @@ static Engine& E() {
 }
 
 fj_status Engine::init(int device) {
-  if (inited) return FJ_OK;
+  if (inited) {
+    if (device >= 0 && device != di.device)
+      return set_err(FJ_ERR_STATE, "the engine is already initialised on device %d (fj_shutdown first to move to device %d)", di.device, device);
+    return FJ_OK;
+  }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -262,9 +269,10 @@ fj_status Engine::init(int device) {
     return set_err(FJ_ERR_NO_DEVICE, "no CUDA device available (%s); flashjoin_b200 has no CPU fallback",
                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   }
-  if (device < 0) {
+  if (device < 0) {  // LOCAL_RANK (one process per GPU), else the calling thread's current device
     const char* lr = getenv("LOCAL_RANK");
-    device = lr ? atoi(lr) % n : 0;
+    if (lr) device = atoi(lr) % n;
+    else if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
   }
   if (device >= n) return set_err(FJ_ERR_BAD_ARG, "device %d out of range (%d devices)", device, n);
   FJ_CUDA(cudaSetDevice(device));
@@ -1052,7 +1060,9 @@ fj_status Engine::join(int algo, unsigned flags, const uint64_t* bk, const uint6
   s.wall_s = now_s() - t0;
   s.algorithmic_bytes = (flags & FJ_FLAG_MATERIALIZE) ? 16ull * nb + 8ull * np + 16ull * s.matches : 8ull * (nb + np);
   *out_matches = s.matches;
-  if (out_seconds) *out_seconds = s.device_s;
+  // host inputs: the copy into HBM is part of the join the caller timed (the reference's seconds cover the whole join
+  // from the arrays it was given, hash_join.cpp:319-379); fj_stats keeps device_s and h2d_s apart
+  if (out_seconds) *out_seconds = s.device_s + s.h2d_s;
   if (stats) *stats = s;
   return FJ_OK;
 }
@@ -1081,44 +1091,59 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
   uint64_t* d_meta = shuf_meta.as<uint64_t>();
   double comm_ms = 0.0, part_ms = 0.0;
 
-  for (int attempt = 1; attempt <= 3; ++attempt) {
-    // ---- 1. scatter the local rows by destination
+  bool conservative = false;  // send regions sized for ALL local rows (after an overflow of the expected-size regions)
+  for (int attempt = 1; attempt <= 4; ++attempt) {
+    // ---- 1. scatter the local rows by destination.  A rank-local failure here (allocation, launch) must not leave the
+    // peers alone in the collective of step 2: the status travels with the metadata and every rank returns an error.
     const size_t tb = radix_elem_bytes(true, narrow), tp = radix_elem_bytes(false, narrow);
-    const uint64_t cap_sb = round4(nb + (uint64_t)scatter_pad_rows(true, narrow) * (nb / scatter_tile_rows(true, narrow) + 1) + 16);
-    const uint64_t cap_sp = round4(np + (uint64_t)scatter_pad_rows(false, narrow) * (np / scatter_tile_rows(false, narrow) + 1) + 16);
-    FJ_TRY(send_b.ensure((size_t)F * cap_sb * tb));
-    FJ_TRY(send_p.ensure((size_t)F * cap_sp * tp));
-    FJ_TRY(shuf_cur.ensure(2 * (size_t)F * 4));
-    uint32_t* cur_sb = shuf_cur.as<uint32_t>();
-    uint32_t* cur_sp = cur_sb + F;
-    int launches = 0;
-    FJ_CUDA(cudaEventRecord(ev[8], st));
-    launch_init_ctl(d_ctl, st);
-    ++launches;
-    FJ_CUDA(cudaMemsetAsync(shuf_cur.p, 0, 2 * (size_t)F * 4, st));
-    ScatterArgs a;
-    a.ctl = d_ctl; a.shift = -1; a.fan = F;
-    if (nb) {
-      a.in_keys = d_bk; a.in_vals = d_bv; a.n = nb; a.out = send_b.p; a.out_cursor = cur_sb; a.out_cap = cap_sb;
-      launch_scatter(true, narrow, 1, a, di, st, &launches);
+    // destination regions like the local radix pass: expected size + 6 sigma + the per-tile padding; CTL_OVERFLOW on any
+    // rank re-runs with regions that hold every local row (heavy skew towards one destination)
+    const uint64_t pad_b = (uint64_t)scatter_pad_rows(true, narrow) * (nb / scatter_tile_rows(true, narrow) + 1) + 16;
+    const uint64_t pad_p = (uint64_t)scatter_pad_rows(false, narrow) * (np / scatter_tile_rows(false, narrow) + 1) + 16;
+    const uint64_t cap_sb = round4((conservative || F == 1 ? nb : std::min<uint64_t>(nb, cap_build(nb, F))) + pad_b);
+    const uint64_t cap_sp = round4((conservative || F == 1 ? np : std::min<uint64_t>(np, cap_probe(np, F))) + pad_p);
+    std::vector<uint32_t> h_cur(2 * (size_t)F, 0u);
+    unsigned long long srow = EMPTY64, sval = 0, my_sent_probes = 0;
+    const fj_status st1 = [&]() -> fj_status {
+      FJ_TRY(send_b.ensure((size_t)F * cap_sb * tb));
+      FJ_TRY(send_p.ensure((size_t)F * cap_sp * tp));
+      FJ_TRY(shuf_cur.ensure(2 * (size_t)F * 4));
+      uint32_t* cur_sb = shuf_cur.as<uint32_t>();
+      uint32_t* cur_sp = cur_sb + F;
+      int launches = 0;
+      FJ_CUDA(cudaEventRecord(ev[8], st));
+      launch_init_ctl(d_ctl, st);
+      ++launches;
+      FJ_CUDA(cudaMemsetAsync(shuf_cur.p, 0, 2 * (size_t)F * 4, st));
+      ScatterArgs a;
+      a.ctl = d_ctl; a.shift = -1; a.fan = F;
+      if (nb) {
+        a.in_keys = d_bk; a.in_vals = d_bv; a.n = nb; a.out = send_b.p; a.out_cursor = cur_sb; a.out_cap = cap_sb;
+        launch_scatter(true, narrow, 1, a, di, st, &launches);
+      }
+      if (np) {
+        a.in_keys = d_pk; a.in_vals = nullptr; a.n = np; a.out = send_p.p; a.out_cursor = cur_sp; a.out_cap = cap_sp;
+        launch_scatter(false, narrow, 1, a, di, st, &launches);
+      }
+      FJ_CUDA(cudaEventRecord(ev[9], st));
+      FJ_CUDA(cudaMemcpyAsync(h_cur.data(), shuf_cur.p, 2 * (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+      FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+      FJ_CUDA(cudaStreamSynchronize(st));
+      FJ_CUDA(cudaGetLastError());
+      part_ms += ms(8, 9);
+      s->kernel_launches += launches;
+      // the out-of-band key (wide rows only): first build row that carries it, and its value
+      srow = h_ctl->sentinel_row;
+      if (!narrow && srow != EMPTY64) FJ_CUDA(cudaMemcpy(&sval, d_bv + srow, 8, cudaMemcpyDeviceToHost));
+      my_sent_probes = narrow ? 0ull : h_ctl->sentinel_probes;
+      return FJ_OK;
+    }();
+    const std::string err1 = st1 == FJ_OK ? std::string() : g_err;
+    if (st1 != FJ_OK) {
+      cudaGetLastError();
+      std::fill(h_cur.begin(), h_cur.end(), 0u);
+      h_ctl->flags = 0;
     }
-    if (np) {
-      a.in_keys = d_pk; a.in_vals = nullptr; a.n = np; a.out = send_p.p; a.out_cursor = cur_sp; a.out_cap = cap_sp;
-      launch_scatter(false, narrow, 1, a, di, st, &launches);
-    }
-    FJ_CUDA(cudaEventRecord(ev[9], st));
-    std::vector<uint32_t> h_cur(2 * (size_t)F);
-    FJ_CUDA(cudaMemcpyAsync(h_cur.data(), shuf_cur.p, 2 * (size_t)F * 4, cudaMemcpyDeviceToHost, st));
-    FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-    FJ_CUDA(cudaStreamSynchronize(st));
-    FJ_CUDA(cudaGetLastError());
-    part_ms += ms(8, 9);
-    s->kernel_launches += launches;
-    // the out-of-band key (wide rows only): first build row that carries it, and its value
-    const unsigned long long srow = h_ctl->sentinel_row;
-    unsigned long long sval = 0;
-    if (!narrow && srow != EMPTY64) FJ_CUDA(cudaMemcpy(&sval, d_bv + srow, 8, cudaMemcpyDeviceToHost));
-    const unsigned long long my_sent_probes = narrow ? 0ull : h_ctl->sentinel_probes;
 
     // ---- 2. everybody learns everybody's flags and send counts
     meta[0] = h_ctl->flags;
@@ -1127,7 +1152,8 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
     meta[3] = my_sent_probes;
     meta[4] = nb;
     meta[5] = np;
-    meta[6] = meta[7] = 0;
+    meta[6] = st1 == FJ_OK ? 0 : 1;  // rank-local failure before the exchange
+    meta[7] = 0;
     for (uint32_t d = 0; d < F; ++d) { meta[8 + d] = h_cur[d]; meta[8 + F + d] = h_cur[F + d]; }
     FJ_CUDA(cudaEventRecord(ev[10], st));
     FJ_CUDA(cudaMemcpyAsync(d_meta, meta.data(), M * 8, cudaMemcpyHostToDevice, st));
@@ -1135,7 +1161,22 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
     FJ_CUDA(cudaMemcpyAsync(all.data(), d_meta + M, M * W * 8, cudaMemcpyDeviceToHost, st));
     FJ_CUDA(cudaStreamSynchronize(st));
     unsigned any = 0;
-    for (int r = 0; r < W; ++r) any |= (unsigned)all[(size_t)r * M];
+    bool any_failed = false;
+    for (int r = 0; r < W; ++r) {
+      any |= (unsigned)all[(size_t)r * M];
+      any_failed |= all[(size_t)r * M + 6] != 0;
+    }
+    if (any_failed) {  // every rank leaves here, with the same verdict
+      if (st1 != FJ_OK) { g_err = err1; return st1; }
+      return set_err(FJ_ERR_STATE, "shuffle: a peer rank failed before the exchange (see its fj_last_error)");
+    }
+    if ((any & CTL_OVERFLOW) && !conservative) {  // a destination received far more than its share: regions for every local row
+      FJ_CUDA(cudaEventRecord(ev[11], st));
+      FJ_CUDA(cudaEventSynchronize(ev[11]));
+      comm_ms += ms(10, 11);
+      conservative = true;
+      continue;
+    }
     if ((any & CTL_NEED_WIDE) && narrow) {  // some rank holds a row that does not fit 32|32: everybody re-runs wide
       FJ_CUDA(cudaEventRecord(ev[11], st));
       FJ_CUDA(cudaEventSynchronize(ev[11]));
@@ -1534,6 +1575,21 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
   return set_err(FJ_ERR_STATE, "internal: peer-memory shuffle did not settle on the slice sizes");
 }
 
+fj_status Engine::agree(fj_status local) {
+  const std::string err = local == FJ_OK ? std::string() : g_err;
+  if (local != FJ_OK) cudaGetLastError();
+  if (dist_scratch.ensure(4096) != FJ_OK) return local != FJ_OK ? local : FJ_ERR_OOM;  // nothing collective has been started yet
+  unsigned long long* d_w = dist_scratch.as<unsigned long long>() + 128;
+  unsigned long long mine = local == FJ_OK ? 0ull : 1ull, sum = 0;
+  FJ_CUDA(cudaMemcpyAsync(d_w, &mine, 8, cudaMemcpyHostToDevice, st));
+  FJ_TRY(dist_allreduce_sum_u64(dist, d_w, d_w + 1, 1, st));
+  FJ_CUDA(cudaMemcpyAsync(&sum, d_w + 1, 8, cudaMemcpyDeviceToHost, st));
+  FJ_CUDA(cudaStreamSynchronize(st));
+  if (local != FJ_OK) { g_err = err; return local; }
+  if (sum) return set_err(FJ_ERR_STATE, "a peer rank failed before the collective (see its fj_last_error)");
+  return FJ_OK;
+}
+
 // ---- peer-memory exchange (CUDA IPC) ------------------------------------------------------------
 // Every rank allocates one exchange buffer, publishes its IPC handle with an ncclAllGather and maps everybody
 // else's buffer.  All ranks must agree on whether the peer path exists, so the per-rank outcome is summed.
@@ -1658,7 +1714,6 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
 
   if (mode == FJ_DIST_BROADCAST) {
     const bool is_root = dist.rank == root;
-    if (is_root && nb && (!bk || !bv)) return set_err(FJ_ERR_BAD_ARG, "root rank must supply the build side");
     // count on a dense key domain with the global-table path: one kernel per GPU over peer memory, no NCCL call.
     // The decision uses only what every rank knows identically (flags, nb, configuration).
     {
@@ -1689,7 +1744,7 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
           if (out_local) *out_local = s.matches;
           s.wall_s = now_s() - t0;
           s.algorithmic_bytes = 8ull * (nb + np);
-          if (out_seconds) *out_seconds = s.device_s;
+          if (out_seconds) *out_seconds = s.device_s + s.h2d_s;
           if (stats) *stats = s;
           return FJ_OK;
         }
@@ -1697,30 +1752,37 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
         s.attempts = 0;
       }
     }
-    // stage inputs in HBM
-    const unsigned long long* d_pk;
-    FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
-    FJ_TRY(in_bv.ensure(std::max<size_t>(nb, 1) * 8));
+    // stage inputs in HBM.  Rank-local failures (the root's missing build side, an allocation, a host->device copy) are
+    // agreed on before the broadcast: every rank returns an error, nobody waits in a collective
+    const bool mat = jflags & FJ_FLAG_MATERIALIZE;
+    const unsigned long long* d_pk = nullptr;
+    const void *src_bk = nullptr, *src_bv = nullptr;  // what root broadcasts from
     const double th = now_s();
-    const void *src_bk = in_bk.p, *src_bv = in_bv.p;  // what root broadcasts from
-    if (dev_in) {
-      d_pk = reinterpret_cast<const unsigned long long*>(pk);
-      if (is_root) { src_bk = bk; src_bv = bv; }  // straight out of the caller's HBM arrays
-    } else {
-      FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
-      if (is_root && nb) {
-        FJ_TRY(h2d(in_bk.p, bk, nb * 8));
-        FJ_TRY(h2d(in_bv.p, bv, nb * 8));
+    FJ_TRY(agree([&]() -> fj_status {
+      if (is_root && nb && (!bk || (mat && !bv))) return set_err(FJ_ERR_BAD_ARG, "root rank must supply the build side");
+      FJ_TRY(in_bk.ensure(std::max<size_t>(nb, 1) * 8));
+      FJ_TRY(in_bv.ensure(std::max<size_t>(nb, 1) * 8));
+      src_bk = in_bk.p;
+      src_bv = in_bv.p;
+      if (dev_in) {
+        d_pk = reinterpret_cast<const unsigned long long*>(pk);
+        if (is_root) { src_bk = bk; src_bv = bv; }  // straight out of the caller's HBM arrays
+      } else {
+        FJ_TRY(in_pk.ensure(std::max<size_t>(np, 1) * 8));
+        if (is_root && nb) {
+          FJ_TRY(h2d(in_bk.p, bk, nb * 8));
+          if (mat) FJ_TRY(h2d(in_bv.p, bv, nb * 8));
+        }
+        if (np) FJ_TRY(h2d(in_pk.p, pk, np * 8));
+        FJ_CUDA(cudaStreamSynchronize(st));
+        s.h2d_s = now_s() - th;
+        s.h2d_bytes = (uint64_t)((is_root ? (mat ? 2 : 1) * nb : 0) + np) * 8;
+        d_pk = in_pk.as<unsigned long long>();
       }
-      if (np) FJ_TRY(h2d(in_pk.p, pk, np * 8));
-      FJ_CUDA(cudaStreamSynchronize(st));
-      s.h2d_s = now_s() - th;
-      s.h2d_bytes = (uint64_t)((is_root ? 2 * nb : 0) + np) * 8;
-      d_pk = in_pk.as<unsigned long long>();
-    }
+      return FJ_OK;
+    }()));
     // broadcast the raw build rows (keys and values in one NCCL group; a count never reads the values, so only
     // the keys travel then)
-    const bool mat = jflags & FJ_FLAG_MATERIALIZE;
     FJ_CUDA(cudaEventRecord(ev[4], st));
     if (nb) {
       if (mat) FJ_TRY(dist_broadcast2_u64(dist, src_bk, in_bk.p, src_bv, in_bv.p, nb, root, st));
@@ -1806,7 +1868,7 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
   if (out_local) *out_local = s.matches;
   s.wall_s = now_s() - t0;
   s.algorithmic_bytes = (jflags & FJ_FLAG_MATERIALIZE) ? 16ull * nb + 8ull * np + 16ull * s.matches : 8ull * (nb + np);
-  if (out_seconds) *out_seconds = s.device_s;
+  if (out_seconds) *out_seconds = s.device_s + s.h2d_s;
   if (stats) *stats = s;
   return FJ_OK;
 }
@@ -1904,21 +1966,28 @@ FJ_API fj_status fj_dev_alloc(void** ptr, size_t bytes) {
   FJ_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
   return FJ_OK;
 }
+static void select_engine_device() {
+  std::lock_guard<std::mutex> lk(E().mu);
+  if (E().inited) cudaSetDevice(E().di.device);
+}
 FJ_API fj_status fj_dev_free(void* ptr) {
+  select_engine_device();
   if (ptr) FJ_CUDA(cudaFree(ptr));
   return FJ_OK;
 }
 FJ_API fj_status fj_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes) {
+  select_engine_device();
   if (bytes) FJ_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
   return FJ_OK;
 }
 FJ_API fj_status fj_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
+  select_engine_device();
   if (bytes) FJ_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
   return FJ_OK;
 }
 FJ_API fj_status fj_host_alloc_pinned(void** ptr, size_t bytes) {
   if (!ptr) return set_err(FJ_ERR_BAD_ARG, "ptr is NULL");
-  { std::lock_guard<std::mutex> lk(E().mu); FJ_TRY(E().init(-1)); }
+  { std::lock_guard<std::mutex> lk(E().mu); FJ_TRY(E().init(-1)); FJ_CUDA(cudaSetDevice(E().di.device)); }
   FJ_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
   return FJ_OK;
 }
@@ -1927,6 +1996,7 @@ FJ_API fj_status fj_host_free_pinned(void* ptr) {
   return FJ_OK;
 }
 FJ_API fj_status fj_device_synchronize(void) {
+  select_engine_device();
   FJ_CUDA(cudaDeviceSynchronize());
   return FJ_OK;
 }

@@ -6,7 +6,32 @@
 
 #include "fj_common.cuh"
 
+#ifdef __CUDACC__
+#include <tuple>
+#include <utility>
+#endif
+
 namespace fj {
+
+#ifdef __CUDACC__
+// Launch a kernel whose CTAs synchronise with each other by spinning (grid barriers, producer / consumer tickets) as a
+// COOPERATIVE launch: the driver then refuses the launch (an error return, and the caller takes its multi-kernel
+// fallback) when the grid cannot be fully co-resident — MPS limits, green contexts, a persistent kernel of another
+// stream — instead of starting a grid that would spin forever.
+template <class... KArgs, size_t... I>
+inline cudaError_t launch_coop_impl(void (*kern)(KArgs...), unsigned grid, unsigned threads, size_t smem, cudaStream_t st,
+                                    std::tuple<KArgs...>& t, std::index_sequence<I...>) {
+  void* p[] = {static_cast<void*>(&std::get<I>(t))...};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(threads), p, smem, st);
+}
+template <class... KArgs, class... Args>
+inline bool launch_coop(void (*kern)(KArgs...), unsigned grid, unsigned threads, size_t smem, cudaStream_t st, Args... args) {
+  std::tuple<KArgs...> t(static_cast<KArgs>(args)...);
+  if (launch_coop_impl(kern, grid, threads, smem, st, t, std::index_sequence_for<KArgs...>{}) == cudaSuccess) return true;
+  cudaGetLastError();  // not sticky: the caller falls back
+  return false;
+}
+#endif
 
 struct DeviceInfo {
   int device = -1;

@@ -1497,14 +1497,14 @@ bool launch_djoin(bool mat, const DjoinArgs& a, const DeviceInfo& di, cudaStream
   if (db > (uint32_t)DJ_DELAY_MAX - 1) db = DJ_DELAY_MAX - 1;
   if (db + dp > (uint32_t)DJ_DELAY_MAX) dp = DJ_DELAY_MAX - db;
   const uint32_t tune = ring | (batch << 8) | (db << 16) | (dp << 24);
-  if (mat)
-    k_djoin<true><<<grid, DJ_THREADS, 0, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
-                                               reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride,
-                                               a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals, tune);
-  else
-    k_djoin<false><<<grid, DJ_THREADS, 0, st>>>(reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
-                                                reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride,
-                                                a.group_bytes, a.ctl, a.sync, a.out_keys, a.out_vals, tune);
+  // cooperative: the work items synchronise by spinning on each other, every CTA must be resident
+  const bool ok = mat ? launch_coop(k_djoin<true>, grid, DJ_THREADS, 0, st, reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
+                                    reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride, a.group_bytes, a.ctl,
+                                    a.sync, a.out_keys, a.out_vals, tune)
+                      : launch_coop(k_djoin<false>, grid, DJ_THREADS, 0, st, reinterpret_cast<const unsigned long long*>(a.build), a.bcnt, a.cap_b,
+                                    reinterpret_cast<const uint32_t*>(a.probe), a.pcnt, a.cap_p, a.direct, a.rstride, a.group_bytes, a.ctl,
+                                    a.sync, a.out_keys, a.out_vals, tune);
+  if (!ok) return false;
   ++*launches;
   return true;
 }

@@ -822,8 +822,7 @@ static bool launch_count_dense_fused_inst(const unsigned long long* bk, uint64_t
   const uint64_t ntiles = (np + tile - 1) / tile;
   if (grid > ntiles) grid = ntiles ? ntiles : 1;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(bk, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok);
-  return true;
+  return launch_coop(kern, (unsigned)grid, THREADS, smem, st, bk, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok);
 }
 bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const unsigned long long* pk, uint64_t np,
                               uint32_t* bitmap, uint32_t dwords, Ctl* ctl, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st,
@@ -1046,8 +1045,7 @@ static bool launch_count_dense_peer_inst(uint64_t nb, const unsigned long long* 
   const uint64_t ntiles = (np + tile - 1) / tile;
   if (grid > ntiles) grid = ntiles ? ntiles : 1;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok, peers, rank, world, root, step);
-  return true;
+  return launch_coop(kern, (unsigned)grid, THREADS, smem, st, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok, peers, rank, world, root, step);
 }
 size_t peer_staging_offset_bytes() { return (size_t)PEER_STAGING_WORD * 8; }
 bool launch_count_dense_peer(uint64_t nb, const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
@@ -1261,9 +1259,8 @@ static bool launch_mat_dense_fused_inst(const unsigned long long* bk, const unsi
   const uint64_t ntiles = (np + tile - 1) / tile;
   if (grid > ntiles) grid = ntiles ? ntiles : 1;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po.keys, po.vals, po.idx,
-                                              po.idx_base, vec_ok);
-  return true;
+  return launch_coop(kern, (unsigned)grid, THREADS, smem, st, bk, bv, nb, pk, np, bitmap, dwords, direct, ctl, gsync, po.keys, po.vals, po.idx,
+                     po.idx_base, vec_ok);
 }
 bool launch_mat_dense_fused(const unsigned long long* bk, const unsigned long long* bv, uint64_t nb, const unsigned long long* pk,
                             uint64_t np, uint32_t* bitmap, uint32_t dwords, unsigned long long* direct, Ctl* ctl, uint32_t* gsync,

@@ -70,8 +70,8 @@ typedef struct fj_stats {
   double partition_s;  /* radix histogram + scatter kernels (radix path)                           */
   double probe_s;      /* probe / partition-join kernels, including pair compaction                */
   double comm_s;       /* NCCL broadcast / all-to-all / all-reduce (distributed calls)             */
-  double device_s;     /* whole join on the device = the `seconds` returned (SimpleTimer scope of  */
-                       /* hash_join.cpp:319-379 etc. minus host<->device copies)                   */
+  double device_s;     /* whole join on the device (SimpleTimer scope of hash_join.cpp:319-379 etc.  */
+                       /* minus host<->device copies); the `seconds` returned = device_s + h2d_s     */
   double wall_s;       /* host wall clock of the whole call, copies included                       */
   uint64_t matches;
   uint64_t table_bytes;       /* hash table (+bloom) footprint in HBM                              */
@@ -96,8 +96,10 @@ typedef struct fj_stats {
 
 /* ---- lifecycle -------------------------------------------------------------------------------
  * Replaces initialize_memory_system() / flash_join.initialize() (hash_join.cpp:596, :639): creates
- * the CUDA context on `device` (-1 = current / LOCAL_RANK), the engine stream and the reusable
- * device arena.  Idempotent.  fj_shutdown releases everything. */
+ * the CUDA context on `device` (-1 = $LOCAL_RANK when set — one process per GPU — else the calling
+ * thread's current CUDA device), the engine stream and the reusable device arena.  Idempotent for
+ * the same device; FJ_ERR_STATE when the engine already lives on another device.  fj_shutdown
+ * releases everything. */
 FJ_API fj_status fj_init(int device);
 FJ_API fj_status fj_shutdown(void);
 FJ_API fj_status fj_device_count(int* count);
@@ -110,8 +112,10 @@ FJ_API const char* fj_version(void);
  *     num_matches = |{ j : probe_keys[j] in set(build_keys) }|   (build side de-duplicated on key,
  *     keep-first: hash_join.cpp:125; each probe row matches at most once: :176)
  * bk/bv have nb elements, pk has np elements (host pointers unless FJ_FLAG_DEVICE_INPUTS).
- * *out_matches receives the count, *out_seconds the device time of the join (see fj_stats.device_s);
- * both mirror the reference's return tuple (py::int_ total_results, double core_duration_sec).
+ * *out_matches receives the count, *out_seconds the time of the join: device time plus, for host
+ * inputs, the host->device copy of the columns (fj_stats.device_s + .h2d_s; the reference's seconds
+ * likewise cover the whole join from the arrays it was given); both mirror the reference's return
+ * tuple (py::int_ total_results, double core_duration_sec).
  * With FJ_FLAG_MATERIALIZE the pairs stay in HBM until the next join call and can be read with
  * fj_pairs_*.  `stats` may be NULL. */
 FJ_API fj_status fj_join_u64(int algo, unsigned flags,
