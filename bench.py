@@ -487,9 +487,9 @@ def main() -> None:
             x.free()
         capi.config_set(dense=1)
         if shuffle and last["dense"] == 2:
-            par = (f"both sides split over {world} GPUs; ONE partition pass per side whose sectors are stored straight into the owner GPU's "
-                   "IPC-mapped partition buffers over NVLink (k_part), device-side barriers / count push / result exchange (k_xsync), "
-                   f"shared-memory join of 2048/{world} partitions per GPU; no NCCL call in the step")
+            par = (f"both sides split over {world} GPUs; ONE local partition pass per side into the GPU's own IPC-mapped partition buffer "
+                   f"(k_part), device-side count push / barrier / result exchange (k_xsync), shared-memory join of 2048/{world} partitions per "
+                   "GPU whose TMA producer pulls the partition rows from every peer's buffer over NVLink (k_sjoin); no NCCL call in the step")
         elif shuffle:
             par = f"both sides split over {world} GPUs, rows hash-partitioned by destination, NCCL all-to-all-v, local radix join, count ncclAllReduce"
         elif world > 1 and last["dense"] and last["kernel_launches"] == 1 and not wl["mat"]:

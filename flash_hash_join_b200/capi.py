@@ -33,7 +33,7 @@ class Stats(C.Structure):
     def as_dict(self) -> dict:
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["path"] = {1: "scalar", 2: "radix"}.get(d["path"], str(d["path"]))
-        d["bloom_kind"] = {0: "none", 1: "smem", 2: "global", 3: "bitmap"}[d["bloom_kind"]]
+        d["bloom_kind"] = {0: "none", 1: "smem", 2: "global", 3: "bitmap", 4: "partition"}[d["bloom_kind"]]
         return d
 
 

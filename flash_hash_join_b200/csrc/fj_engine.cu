@@ -168,10 +168,16 @@ struct Engine {
     cfg["load_pct"] = 50;
     cfg["load_pct_auto"] = 1;
     cfg["bloom_bits_per_key"] = 16;
-    cfg["adaptive_table_l2_pct"] = 50;
+    // adaptive: global table while its bytes stay below this percentage of L2, radix beyond.  Measured crossover of the
+    // general hash paths on B200 (1e8 probe rows, profiles/r02t_sweep_adaptive.jsonl): 8e6 build rows 1.15 ms (table)
+    // vs 2.21 ms (radix), 1.6e7 rows 2.30 vs 2.30, 3e7 rows 3.86 vs 2.48 — the table wins until it is about twice L2
+    cfg["adaptive_table_l2_pct"] = 200;
+    cfg["dense16_min_rows"] = 8192;       // build rows from which the dense16 radix path (k_part + k_sjoin) is planned
+    cfg["dense16_min_probe"] = 1 << 24;   // adaptive materialize: probe rows from which dense16 is preferred to the dense table path
     cfg["radix_sub_rows"] = 0;  // 0 = derive from shared memory
     cfg["radix_optimistic"] = 1;
     cfg["smem_bloom"] = 1;
+    cfg["bloom_guard"] = 1;  // no filter when it would be read through L2 next to an L2-resident table
     cfg["probe_ctas_per_sm"] = 0;  // 0 = occupancy-derived
     cfg["narrow"] = 1;
     cfg["join3"] = 1;  // packed rows, two radix passes: collision-free pipelined k_join3 (0 = k_join)
@@ -516,11 +522,19 @@ fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const 
   t.slots = table.as<unsigned long long>();
   bool bloom_smem = false;
   size_t bloom_bytes = 0;
-  if (flags & FJ_FLAG_BLOOM) {
+  // Bloom guard: a filter that does not fit shared memory is read through L2 — one more random access per probe row.
+  // That pays only when it saves an HBM access, i.e. when the table itself does not stay in L2; next to an
+  // L2-resident table it can only lose (1.25e8 x 1e6, 90 % match: 0.91 ms with the filter, 0.52 ms without,
+  // profiles/r01i_quick_bench.jsonl).  The *_bloom entry points then run without a filter (bloom_kind 0) — results are
+  // identical, as on the reference, where the filter only ever changes the time.
+  const bool filter_fits_smem = cfg["smem_bloom"] && round4((nb * 8 + 31) / 32) <= probe_smem_bloom_limit_words(di);
+  const bool want_filter = (flags & FJ_FLAG_BLOOM) &&
+                           (filter_fits_smem || !cfg["bloom_guard"] || table_bytes > (size_t)di.l2_bytes / 2);
+  if (want_filter) {
     const uint64_t bits = (uint64_t)std::max<int64_t>(4, cfg["bloom_bits_per_key"]);
     uint64_t words = round4(std::max<uint64_t>(8, (nb * bits + 31) / 32));
     const uint64_t lim = probe_smem_bloom_limit_words(di);
-    if (cfg["smem_bloom"] && round4((nb * 8 + 31) / 32) <= lim) {  // >= 8 bits/key still fit shared memory
+    if (filter_fits_smem) {  // >= 8 bits/key still fit shared memory
       words = std::min(words, lim);
       bloom_smem = true;
     }
@@ -716,6 +730,19 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   j.ctl = d_ctl;
   j.out_keys = mat ? out_keys.as<unsigned long long>() : nullptr;
   j.out_vals = mat ? out_vals.as<unsigned long long>() : nullptr;
+  // radix + Bloom (hash_join_radix_bloom / hash_join_count_radix_bloom, hash_join.cpp:627, :636): k_join carries a
+  // per-partition register-blocked filter in shared memory (16 bits per key) when it fits next to the table; k_join3's
+  // collision-free membership bitmap already IS an exact filter in front of its value directory
+  int bloom_kind = 0;
+  if ((flags & FJ_FLAG_BLOOM) && !pl.join3) {
+    const uint32_t bw = std::max<uint32_t>(32u, (pl.smax / 2 + 3u) & ~3u);
+    if ((size_t)pl.smax * (pl.narrow ? 8 : 16) + (size_t)pl.tcap * 4 + (size_t)bw * 4 + 2048 <= di.smem_optin) {
+      j.bloom_words = bw;
+      bloom_kind = 4;
+    }
+  } else if ((flags & FJ_FLAG_BLOOM) && pl.join3) {
+    bloom_kind = 3;
+  }
   if (pl.join3) launch_join3(mat, j, 32 - pl.bits, di, st, &launches);
   else launch_join(pl.narrow, mat, j, st, &launches);
   if (!pl.narrow && !flat) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
@@ -732,7 +759,7 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   s->table_bytes = (uint64_t)pl.P * (pl.cap2_b * tb + pl.cap2_p * tp) + (two ? (uint64_t)pl.F1 * (pl.cap1_b * tb + pl.cap1_p * tp) : 0);
   s->path = FJ_ALGO_RADIX;
   s->narrow = pl.narrow ? 1 : 0;
-  s->bloom_kind = 0;
+  s->bloom_kind = bloom_kind;
   s->dedup_exact = 0;
   s->radix_bits1 = pl.bits1;
   s->radix_bits2 = pl.bits2;
@@ -833,12 +860,14 @@ static uint64_t round16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
 Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t np) const {
   Dense16Plan dp;
   if (!cfg.at("dense") || !cfg.at("dense16") || !cfg.at("narrow") || (flags & (FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX))) return dp;
-  if (nb < (uint64_t)std::max<int64_t>(cfg.at("dense_min_rows"), 1024) || np == 0) return dp;
+  if (nb < (uint64_t)std::max<int64_t>(std::min(cfg.at("dense_min_rows"), cfg.at("dense16_min_rows")), 1024) || np == 0) return dp;
   const uint64_t maxslots = sjoin_max_slots(di);
   const uint64_t need = nb + nb / 5 + 1024;  // h2o ids are 1..1.1*n
   int logp = (int)cfg.at("dense16_logp");
   if (logp <= 0) {
-    logp = nb >= (1ull << 23) ? 11 : (nb >= (1ull << 21) ? 10 : 9);
+    // 1024 partitions whenever the key domain fits them (1e8 probe rows against 1e4 .. 2e6 build rows: 0.63 - 0.65 ms
+    // with 1024 partitions, 0.68 - 0.70 with 512, 0.64 - 0.67 with 2048: profiles/r02u_exp_small_dense16.jsonl)
+    logp = 10;
     while (logp < 11 && (maxslots << logp) < need) ++logp;
   }
   if (logp < 8 || logp > 11 || (maxslots << logp) < need) return dp;
@@ -979,8 +1008,18 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
   // the direct-address radix join has no partition-size limit: it also serves build sides that two general scatter
   // passes cannot cut down to shared-memory size (plan.ok == false, > ~2.6e8 rows), which would otherwise fall back
   // to one huge global table
+  // adaptive on a dense key domain (measured with 1e8 probe rows, profiles/r02t_sweep_adaptive.jsonl and
+  // r02u_exp_small_dense16.jsonl): a materialize is fastest on the dense16 radix path at EVERY build size (0.63 - 0.70 ms
+  // for 1e4 .. 2e6 build rows, the dense table path 0.72 - 1.18 ms), a count only once the membership bitmap no longer
+  // fits shared memory (2e6 rows: 0.39 vs 0.50 ms; below that the bitmap kernel answers in 0.14 - 0.16 ms).  The attempt
+  // is optimistic: keys outside the domain cost one pass over the build side and the next layout answers.
+  bool prefer16 = false;
+  if (algo == FJ_ALGO_ADAPTIVE && narrow && cfg["dense"] && cfg["dense16"] && !(flags & (FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX))) {
+    if (mat) prefer16 = np >= (uint64_t)cfg["dense16_min_probe"];
+    else prefer16 = dense_bits == 0 && nb >= (1ull << 20);
+  }
   const bool radix_wanted =
-      path == FJ_ALGO_RADIX ||
+      path == FJ_ALGO_RADIX || prefer16 ||
       (!plan.ok && !((flags & FJ_FLAG_PROBE_IDX) && mat) &&
        (algo == FJ_ALGO_RADIX || (algo == FJ_ALGO_ADAPTIVE && (double)nb / ((double)cfg["load_pct"] / 100.0) * 8.0 >
                                                                  (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0)));
@@ -1357,9 +1396,10 @@ fj_status Engine::join_shuffle(int algo, unsigned jflags, const unsigned long lo
 // rows cross NVLink once (4 bytes per build row, 2 per probe row), in large transfers, overlapped with the join.
 // (Storing the 32-byte sectors straight into the owner's buffer from k_part was measured first: NVLink moved only
 // ~200 GB/s per GPU in 32-byte writes and the partition pass did not scale — profiles/r02q_bench_n4_peer_store.json.)
-// Three small k_xsync launches replace the collectives: entry barrier + slice-size check, count push + barrier, result
-// exchange.  One host synchronisation per step; no NCCL call in the steady state (the slice sizes are exchanged with
-// ncclAllGather only when some rank's sizes changed).
+// Two small k_xsync launches replace the collectives: count push + slice-size check + barrier, and the result exchange
+// (which doubles as the barrier that frees the partition buffers for the next step).  One host synchronisation per
+// step; no NCCL call in the steady state (the slice sizes are exchanged with ncclAllGather only when some rank's
+// sizes changed).
 fj_status Engine::xpart_ensure(size_t bytes) {
   if (xp.local && xp.bytes >= bytes) return FJ_OK;
   const int W = dist.world, R = dist.rank;
@@ -1484,8 +1524,6 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
     FJ_CUDA(cudaEventRecord(ev[0], st));
     launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st, cs, P, part_cursor_start(mat, nb, di), part_cursor_start(false, np, di));
     ++launches;
-    xa.phase = 0; xa.seq = 3 * step + 1;
-    launch_xsync(xa, st, &launches);
     FJ_CUDA(cudaEventRecord(ev[1], st));
     PartArgs a;
     a.ctl = d_ctl; a.klimit = gp.klimit; a.logp = gp.logp;

@@ -144,6 +144,7 @@ struct JoinArgs {
   uint64_t cap_p = 0;
   uint32_t smax = 0;        // build tuples that fit the shared-memory staging area (multiple of 4)
   uint32_t tcap = 0;        // slots of the shared-memory index table
+  uint32_t bloom_words = 0; // k_join: words of the per-partition Bloom filter behind the table (0 = no filter)
   uint32_t chunk = 0;       // probe rows per CTA (multiple of 4)
   uint32_t max_chunks = 1;  // ceil(cap_p / chunk)
   uint32_t nparts = 0;
@@ -241,8 +242,8 @@ size_t sjoin_tail_bytes(const DeviceInfo& di);
 uint64_t sjoin_out_slack_pairs(const DeviceInfo& di);
 bool launch_sjoin(bool mat, const SjoinArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
 
-// cross-GPU steps of the peer-memory shuffle (k_xsync, fj_part.cu): phase 0 entry barrier + slice-size check,
-// phase 1 count push + barrier, phase 2 result exchange.  ctrl[r] = rank r's exchange area (peer mapped), whose count
+// cross-GPU steps of the peer-memory shuffle (k_xsync, fj_part.cu): phase 1 count push + slice-size check + barrier,
+// phase 2 result exchange.  ctrl[r] = rank r's exchange area (peer mapped), whose count
 // arrays (uint32 [2 sides][world][P / world]) start at xsync_count_offset_bytes()
 struct XsyncArgs {
   void* ctrl[8] = {};

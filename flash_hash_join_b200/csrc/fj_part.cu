@@ -141,9 +141,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   __shared__ __align__(8) uint64_t s_full[PT_WARPS * PT_WSLOTS];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, wv = tid >> 5, h = tid & 1u;
-  // multi-GPU shuffle: the cross-GPU entry barrier gave up (a peer is missing / joins with other sizes) — peers may
-  // still be reading the partition buffers of the previous step: touch nothing
-  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_PEER_TIMEOUT | CTL_META_CHANGED)) return;
+  // the build-side pass of this attempt found a row outside the domain: the attempt is abandoned, spare the probe side's pass
+  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & CTL_NOT_DENSE16) return;
   const uint32_t GW = gridDim.x * PT_WARPS;          // warps of the grid
   const uint32_t gw = blockIdx.x * PT_WARPS + wv;    // this warp: batches gw, gw + GW, gw + 2 GW, ...
   const uint32_t nbatch = (uint32_t)((a.n + BROWS - 1) / BROWS);
@@ -470,14 +469,15 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
 // ================================================================================= k_xsync
 // Multi-GPU shuffle over peer memory (one process per GPU, every rank's exchange area mapped by every other rank through
 // CUDA IPC): the cross-GPU steps around k_part and k_sjoin, each ONE small launch on the rank's own stream.
-//   phase 0  entry barrier + size check: every rank posts (nb, np) of its slice into every peer's area and waits for
-//            all of them; afterwards nobody is still reading the partition buffers of the previous step, and every rank
-//            has compared the sizes with the ones the plan (capacities, partition count) was made for
-//            (CTL_META_CHANGED: every rank sees the same vector, so every rank re-plans)
-//   phase 1  count push + barrier: my reservation cursors of the partitions a peer owns go into that peer's count
-//            array (k_sjoin's bcnt / pcnt, indexed [source][local partition]); after the barrier that follows every
-//            rank's partition pass is complete and visible, so k_sjoin may pull partition rows from every peer
-//   phase 2  result exchange: (matches, flags, nb, np) of every rank -> sum / or on every rank (replaces ncclAllReduce)
+//   phase 1  count push + size check + barrier: my reservation cursors of the partitions a peer owns go into that
+//            peer's count array (k_sjoin's bcnt / pcnt, indexed [source][local partition]) and (nb, np) of my slice
+//            into every peer's area; after the barrier every rank's partition pass is complete and visible, so k_sjoin
+//            may pull partition rows from every peer, and every rank has compared the sizes with the ones the plan
+//            (capacities, partition count) was made for (CTL_META_CHANGED: every rank sees the same vector, so every
+//            rank abandons the step and re-plans; the partition pass of a stale plan only ever wrote local memory)
+//   phase 2  result exchange: (matches, flags, nb, np) of every rank -> sum / or on every rank (replaces
+//            ncclAllReduce).  It is also the barrier after which no rank reads any partition buffer of this step any
+//            more, so the next step's partition pass needs no entry barrier.
 // Barrier words carry a sequence number (3 * step + phase + 1) and are never reset.  Spins give up after 10 s.
 constexpr int XS_BAR = 0;          // + rank: barrier sequence number posted by `rank`
 constexpr int XS_META = 16;        // + 2 * rank: nb, np of `rank` (phase 0)
@@ -527,12 +527,11 @@ __global__ void __launch_bounds__(1024) k_xsync(const XsyncParams a) {
   const int tid = threadIdx.x;
   const int W = a.world;
   unsigned long long* const mine = a.ctrl[a.rank];
-  if (a.phase == 0) {
+  if (a.phase == 1) {
     if (tid < W) {
       xs_st_relaxed(a.ctrl[tid] + XS_META + 2 * a.rank, a.nb);
       xs_st_relaxed(a.ctrl[tid] + XS_META + 2 * a.rank + 1, a.np);
     }
-  } else if (a.phase == 1) {
     const uint32_t ppo = 1u << a.lpo;  // partitions per owner
     for (uint32_t d = tid; d < a.P; d += blockDim.x) {
       uint32_t* cnt = reinterpret_cast<uint32_t*>(a.ctrl[d >> a.lpo] + XS_CNT);
@@ -562,7 +561,7 @@ __global__ void __launch_bounds__(1024) k_xsync(const XsyncParams a) {
   if (tid == 0) {
     if (!s_ok) {
       atomicOr(&a.ctl->flags, CTL_PEER_TIMEOUT);
-    } else if (a.phase == 0) {
+    } else if (a.phase == 1) {
       bool same = true;
       for (int r = 0; r < W; ++r)
         same &= xs_ld_relaxed(mine + XS_META + 2 * r) == a.meta[2 * r] && xs_ld_relaxed(mine + XS_META + 2 * r + 1) == a.meta[2 * r + 1];
@@ -665,7 +664,7 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // an earlier kernel of this attempt gave up: nothing to do (uniform; before any copy is in flight)
-  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_NOT_DENSE16 | CTL_OVERFLOW)) {
+  if (*reinterpret_cast<volatile unsigned int*>(&a.ctl->flags) & (CTL_NOT_DENSE16 | CTL_OVERFLOW | CTL_META_CHANGED | CTL_PEER_TIMEOUT)) {
     if (MAT && tid == 0) a.tails[blockIdx.x * SJ_TAIL_WORDS] = ~0ull;
     return;
   }

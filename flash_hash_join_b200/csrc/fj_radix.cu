@@ -678,11 +678,15 @@ template <bool NARROW> struct ProbeVec;
 template <> struct ProbeVec<true> { static constexpr int K = 4; };   // uint4 = 4 x key32
 template <> struct ProbeVec<false> { static constexpr int K = 2; };  // 2 x key64
 
-template <bool NARROW, bool MAT>
+// BLOOM: the per-partition table carries a register-blocked Bloom filter in shared memory (one 32-bit word per key,
+// fj_common.cuh), filled during the build and checked before the table is probed — the counterpart of the
+// FlashHashTable<true> the reference builds per partition for hash_join_radix_bloom / hash_join_count_radix_bloom
+// (hash_join.cpp:344, :518, :627, :636).  As there, it changes the time only, never the result.
+template <bool NARROW, bool MAT, bool BLOOM>
 __global__ void __launch_bounds__(JN_THREADS, 2)
     k_join(const typename Elem<true, NARROW>::T* __restrict__ build, const uint32_t* __restrict__ bcnt, uint64_t cap_b,
            const typename Elem<false, NARROW>::T* __restrict__ probe, const uint32_t* __restrict__ pcnt, uint64_t cap_p,
-           uint32_t smax, uint32_t tcap, uint32_t chunk, uint32_t max_chunks, Ctl* __restrict__ ctl,
+           uint32_t smax, uint32_t tcap, uint32_t bwords, uint32_t chunk, uint32_t max_chunks, Ctl* __restrict__ ctl,
            unsigned long long* __restrict__ out_keys, unsigned long long* __restrict__ out_vals) {
   using TB = typename Elem<true, NARROW>::T;
   using TP = typename Elem<false, NARROW>::T;
@@ -690,6 +694,7 @@ __global__ void __launch_bounds__(JN_THREADS, 2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TB* tuples = reinterpret_cast<TB*>(smem_raw);
   uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw + (size_t)smax * sizeof(TB));
+  uint32_t* bf = table + tcap;  // BLOOM: bwords filter words
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_wcnt[MAT ? JN_WARPS * K : 1];
   __shared__ unsigned long long s_base;
@@ -721,7 +726,7 @@ __global__ void __launch_bounds__(JN_THREADS, 2)
       bulk_g2s(smem_raw + off, src + off, nn, &s_bar);
     }
   }
-  for (uint32_t i = tid; i < tcap; i += JN_THREADS) table[i] = 0u;
+  for (uint32_t i = tid; i < tcap + (BLOOM ? bwords : 0u); i += JN_THREADS) table[i] = 0u;  // table and filter are adjacent
   __syncthreads();
   mbar_wait(&s_bar, 0);
 
@@ -729,6 +734,10 @@ __global__ void __launch_bounds__(JN_THREADS, 2)
   for (uint32_t i = tid; i < nbp; i += JN_THREADS) {
     if (Hole<true, NARROW>::is(tuples[i])) continue;  // padding written by k_scatter2
     const unsigned long long key = Elem<true, NARROW>::key(tuples[i]);
+    if constexpr (BLOOM) {
+      const uint32_t bh = bloom_hash(key);
+      atomicOr(bf + bloom_word(bh, bwords), bloom_mask(bh));
+    }
     const uint32_t g = hash32(key) * 0x9E3779B1u;
     const uint32_t fp = g & 0xffffu;
     const uint32_t mine = (fp << 16) | (i + 1u);
@@ -776,6 +785,11 @@ __global__ void __launch_bounds__(JN_THREADS, 2)
 #pragma unroll
     for (int q = 0; q < K; ++q) {
       if (!valid[q]) continue;
+      if constexpr (BLOOM) {
+        const uint32_t bh = bloom_hash(key[q]);
+        const uint32_t m = bloom_mask(bh);
+        if ((bf[bloom_word(bh, bwords)] & m) != m) continue;  // definitely not in this partition's build side
+      }
       const uint32_t g = hash32(key[q]) * 0x9E3779B1u;
       const uint32_t fp = g & 0xffffu;
       uint32_t s = __umulhi(g, tcap);
@@ -852,20 +866,23 @@ __global__ void __launch_bounds__(JN_THREADS, 2)
 }
 
 void launch_join(bool narrow, bool mat, const JoinArgs& a, cudaStream_t st, int* launches) {
-  const size_t smem = (size_t)a.smax * (narrow ? 8 : 16) + (size_t)a.tcap * 4;
+  const bool bloom = a.bloom_words != 0;
+  const size_t smem = (size_t)a.smax * (narrow ? 8 : 16) + (size_t)a.tcap * 4 + (size_t)a.bloom_words * 4;
   const uint64_t grid = (uint64_t)a.nparts * a.max_chunks;
   if (grid == 0) return;
-#define FJ_JN(N, M)                                                                                           \
+#define FJ_JN(N, M, B)                                                                                        \
   do {                                                                                                        \
-    auto kern = k_join<N, M>;                                                                                 \
+    auto kern = k_join<N, M, B>;                                                                              \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
     kern<<<(unsigned)grid, JN_THREADS, smem, st>>>(                                                           \
         reinterpret_cast<const typename Elem<true, N>::T*>(a.build), a.bcnt, a.cap_b,                         \
-        reinterpret_cast<const typename Elem<false, N>::T*>(a.probe), a.pcnt, a.cap_p, a.smax, a.tcap, a.chunk, \
-        a.max_chunks, a.ctl, a.out_keys, a.out_vals);                                                         \
+        reinterpret_cast<const typename Elem<false, N>::T*>(a.probe), a.pcnt, a.cap_p, a.smax, a.tcap, a.bloom_words, \
+        a.chunk, a.max_chunks, a.ctl, a.out_keys, a.out_vals);                                                \
   } while (0)
-  if (narrow) { if (mat) FJ_JN(true, true); else FJ_JN(true, false); }
-  else { if (mat) FJ_JN(false, true); else FJ_JN(false, false); }
+#define FJ_JN2(N, M) do { if (bloom) FJ_JN(N, M, true); else FJ_JN(N, M, false); } while (0)
+  if (narrow) { if (mat) FJ_JN2(true, true); else FJ_JN2(true, false); }
+  else { if (mat) FJ_JN2(false, true); else FJ_JN2(false, false); }
+#undef FJ_JN2
 #undef FJ_JN
   ++*launches;
 }

@@ -938,11 +938,32 @@ __global__ void __launch_bounds__(THREADS)
     const unsigned long long* bk = root_buf + PEER_STAGING_WORD;
     bool bad = false;
     if (have) {
-      for (uint64_t i = gtid; i < nb; i += gthreads) {
-        const unsigned long long k = ld_relaxed_sys_u64(bk + i);
+      // pairs of keys with 16-byte system-scope loads, four loads in flight per thread before the first bitmap update:
+      // a load from the root's memory is an NVLink round trip (one 8-byte load per loop iteration, each waited for, cost
+      // 13 serial round trips per thread at 1e6 build keys: C4 count at 8 GPUs 0.30 ms vs 0.21 ms on one GPU,
+      // profiles/r02s_bench_n8.json)
+      auto put = [&](unsigned long long k) {
         if (k >= dbits) bad = true;
         else atomicOr(bitmap + (uint32_t)(k >> 5), 1u << ((uint32_t)k & 31u));
+      };
+      const uint64_t npair = nb / 2;  // the staging area is 16-byte aligned
+      for (uint64_t i0 = gtid; i0 < npair; i0 += 4 * gthreads) {
+        unsigned long long a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint64_t i = i0 + (uint64_t)u * gthreads;
+          a[u] = b[u] = ~0ull;
+          if (i < npair) asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a[u]), "=l"(b[u]) : "l"(bk + 2 * i));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + (uint64_t)u * gthreads < npair) {
+            put(a[u]);
+            put(b[u]);
+          }
+        }
       }
+      if ((nb & 1ull) && gtid == 0) put(ld_relaxed_sys_u64(bk + nb - 1));
     }
     if (bad) atomicOr(&ctl->flags, CTL_NOT_DENSE);
   }

@@ -80,7 +80,7 @@ py::dict last_stats() {
   d["h2d_bytes"] = s.h2d_bytes;
   d["path"] = s.path == FJ_ALGO_RADIX ? "radix" : "scalar";
   d["narrow"] = (bool)s.narrow;
-  d["bloom_kind"] = s.bloom_kind == 0 ? "none" : (s.bloom_kind == 1 ? "smem" : (s.bloom_kind == 2 ? "global" : "bitmap"));
+  d["bloom_kind"] = s.bloom_kind == 0 ? "none" : (s.bloom_kind == 1 ? "smem" : (s.bloom_kind == 2 ? "global" : (s.bloom_kind == 3 ? "bitmap" : "partition")));
   d["attempts"] = s.attempts; d["dedup_exact"] = (bool)s.dedup_exact; d["kernel_launches"] = s.kernel_launches;
   d["radix_bits"] = py::make_tuple(s.radix_bits1, s.radix_bits2);
   d["n_gpus"] = s.n_gpus;

@@ -80,7 +80,8 @@ typedef struct fj_stats {
   int32_t path;        /* FJ_ALGO_SCALAR or FJ_ALGO_RADIX actually taken                           */
   int32_t narrow;      /* 1 = packed 32-bit key|value slots were used, 0 = 16-byte slots           */
   int32_t bloom_kind;  /* 0 none, 1 shared-memory resident, 2 global (L2) resident,                */
-                       /* 3 exact membership bitmap (dense key domain, count only; no table)       */
+                       /* 3 exact membership bitmap (dense key domain / k_join3's partition bitmap), */
+                       /* 4 per-partition filter in shared memory (radix + Bloom, k_join)          */
   int32_t attempts;    /* 1 normally; >1 when an optimistic attempt was abandoned and re-run       */
   int32_t dedup_exact; /* 1 = duplicate build keys were seen and the keep-first slow path ran      */
   int32_t kernel_launches; /* number of this library's kernels launched by the call               */

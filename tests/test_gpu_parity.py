@@ -221,19 +221,51 @@ def test_bloom_invariance_and_kinds(fj):
     n_bloom, _ = fj.hash_join_count_bloom(bk, bv, pk)
     assert fj.last_stats()["bloom_kind"] == "smem" and fj.last_stats()["dense"] == 0
     assert n_dense == n_plain == n_bloom == O.np_join(bk, bv, pk)[0]
-    fj.configure(smem_bloom=0)
+    fj.configure(smem_bloom=0, bloom_guard=0)
     try:
         n_g, _ = fj.hash_join_count_bloom(bk, bv, pk)
         assert fj.last_stats()["bloom_kind"] == "global" and n_g == n_plain
         n_g, _ = fj.hash_join_bloom(bk, bv, pk)
         assert n_g == n_plain
-        # a build side too large for the shared-memory filter takes the global (L2) filter
+        # a build side too large for the shared-memory filter takes the global (L2) filter ...
         fj.configure(smem_bloom=1)
         bk, bv, pk = g1(600_000, 400_000, 10)
         n_b, _ = fj.hash_join_count_bloom(bk, bv, pk)
         assert fj.last_stats()["bloom_kind"] == "global" and n_b == O.np_join(bk, bv, pk)[0]
+        # ... unless the guard is on (the default): next to an L2-resident table a filter read through L2 only costs
+        fj.configure(bloom_guard=1)
+        n_b2, _ = fj.hash_join_count_bloom(bk, bv, pk)
+        assert fj.last_stats()["bloom_kind"] == "none" and n_b2 == n_b
     finally:
-        fj.configure(smem_bloom=1, dense=1)
+        fj.configure(smem_bloom=1, dense=1, bloom_guard=1)
+
+
+def test_radix_bloom_partition_filter(fj):
+    """hash_join_radix_bloom / hash_join_count_radix_bloom on the general radix path: k_join builds a per-partition
+    register-blocked filter in shared memory and checks it before the table (the FlashHashTable<true> per partition of
+    hash_join.cpp:344, :518); k_join3's membership bitmap is reported as the (exact) filter.  Results never change."""
+    fj.configure(dense=0)
+    try:
+        for N, ny, pct, kind in ((600_000, 150_000, 10, "partition"), (600_000, 150_000, 90, "partition"), (3_000_000, 3_000_000, 50, None)):
+            bk, bv, pk = g1(N, ny, pct)
+            n0, k0, v0 = O.np_join(bk, bv, pk)
+            n, _ = fj.hash_join_count_radix_bloom(bk, bv, pk)
+            st = fj.last_stats()
+            assert n == n0 and st["path"] == "radix", st
+            if kind:
+                assert st["bloom_kind"] == kind, st
+            else:
+                assert st["bloom_kind"] in ("partition", "bitmap"), st
+            n, _ = fj.hash_join_radix_bloom(bk, bv, pk)
+            k, v = fj.last_pairs()[:2]
+            assert n == n0 and np.array_equal(O.sorted_pairs(k, v), O.sorted_pairs(k0, v0))
+            # wide rows take k_join as well
+            bkw = bk | (np.uint64(1) << np.uint64(40))
+            pkw = pk | (np.uint64(1) << np.uint64(40))
+            n, _ = fj.hash_join_count_radix_bloom(bkw, bv, pkw)
+            assert n == n0
+    finally:
+        fj.configure(dense=1)
 
 
 def test_radix_two_pass_small_partitions(fj):
@@ -255,6 +287,29 @@ def test_radix_two_pass_small_partitions(fj):
         assert np.array_equal(O.sorted_pairs(*fj.last_pairs()), O.sorted_pairs(expect[1], expect[2]))
     finally:
         fj.configure(radix_sub_rows=0)
+
+
+def test_adaptive_prefers_dense16_for_big_probe_materialize(fj):
+    """Adaptive policy on a dense key domain (profiles/r02t_sweep_adaptive.jsonl, r02u_exp_small_dense16.jsonl): a
+    materialize with a big probe side takes the dense16 radix path whatever the build size, a count keeps the
+    shared-memory bitmap while it fits; a key outside the domain costs one abandoned attempt and never the result."""
+    N = (1 << 24) + 12_345
+    bk, bv, pk = g1(N, 50_000, 90)
+    expect = O.np_join(bk, bv, pk)
+    n, _ = fj.adaptive_join(bk, bv, pk)
+    st = fj.last_stats()
+    assert n == expect[0] and st["path"] == "radix" and st["dense"] == 2 and st["attempts"] == 1, st
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()[:2]), O.sorted_pairs(expect[1], expect[2]))
+    n, _ = fj.adaptive_join_count(bk, bv, pk)
+    st = fj.last_stats()
+    assert n == expect[0] and st["path"] == "scalar" and st["dense"] == 1, st
+    bk2 = bk.copy()
+    bk2[7] = np.uint64(3_000_000_000)  # outside every dense domain, still a packed row
+    expect2 = O.np_join(bk2, bv, pk)
+    n, _ = fj.adaptive_join(bk2, bv, pk)
+    st = fj.last_stats()
+    assert n == expect2[0] and st["attempts"] >= 2 and st["dense"] == 0, st
+    assert np.array_equal(O.sorted_pairs(*fj.last_pairs()[:2]), O.sorted_pairs(expect2[1], expect2[2]))
 
 
 def test_adaptive_equals_explicit_on_both_sides_of_threshold(fj):

@@ -79,6 +79,14 @@ if has ncu_general; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_scatter2|k_join" -s 5 -c 5 -f -o "$OUT/c3_radix_general" \
     python tools/prof_case.py C3 radix mat --reps 3 --set dense=0 > "$OUT/ncu_c3_general.log" 2>&1
 fi
+if has sweep_adaptive; then
+  timeout 900 python tools/sweep_adaptive.py > "$OUT/sweep_adaptive.jsonl" 2> "$OUT/sweep_adaptive.err"
+  cat "$OUT/sweep_adaptive.jsonl"; tail -3 "$OUT/sweep_adaptive.err"
+fi
+if has smoke; then
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
+  echo "smoke exit $?" >> "$OUT/smoke.log"; tail -3 "$OUT/smoke.log"
+fi
 if has ubench2; then
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 tools/ubench2.cu -o "$OUT/ubench2.bin" > "$OUT/ubench2.build.log" 2>&1 \
     && timeout 300 "$OUT/ubench2.bin" > "$OUT/ubench2.jsonl" 2> "$OUT/ubench2.err"
