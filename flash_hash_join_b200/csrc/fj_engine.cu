@@ -191,8 +191,12 @@ struct Engine {
     cfg["dense_delay_p"] = 3;       // k_djoin: steps between filling a group and probing it (sweep: profiles/r01f_sweep_djoin.jsonl)
     cfg["stage_threads"] = 8;       // host threads staging large pageable inputs through pinned buffers (0: plain cudaMemcpyAsync)
     cfg["stage_min_mb"] = 64;       // smallest pageable input column that is staged
-    cfg["part_warps_kv"] = 16;      // k_part warps per CTA, rows with values (16 | 32)
-    cfg["part_warps_k"] = 16;       // k_part warps per CTA, keys only (16 | 32)
+    // k_part input: per-warp TMA rings (0) or 128-bit loads straight into registers (1).  Measured on C3
+    // (profiles/r02w_exp_part_direct.jsonl): rows with values 536 vs 564 us, probe keys 292 vs 294 us, the key-only build
+    // pass of a count 323 vs 290 us — only that one takes the direct loads
+    cfg["part_direct_kv"] = 0;
+    cfg["part_direct_k"] = 0;
+    cfg["part_direct_count_build"] = 1;
     cfg["dist_peer_shuffle"] = 1;   // SHUFFLE on a dense key domain: one partition pass storing straight into the owners' buffers
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
     cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
@@ -224,7 +228,7 @@ struct Engine {
   DevBuf direct;
   // dense key domain, radix path, round 2: ONE partition pass (k_part) + shared-memory direct-address join (k_sjoin)
   struct Dense16Plan { bool ok = false; int logp = 0; uint64_t klimit = 0; uint32_t slots = 0; uint64_t cap_b = 0, cap_p = 0; };
-  Dense16Plan plan_dense16(unsigned flags, uint64_t nb, uint64_t np) const;
+  Dense16Plan plan_dense16(unsigned flags, uint64_t nb, uint64_t np, bool small_ok = false) const;
   fj_status attempt_dense16(unsigned flags, const Dense16Plan& dp, const unsigned long long* bk, const unsigned long long* bv,
                             uint64_t nb, const unsigned long long* pk, uint64_t np, fj_stats* s);
   // dense key domain, count only: exact membership bitmap in shared memory instead of table + filter
@@ -857,10 +861,13 @@ fj_status Engine::attempt_dense(unsigned flags, const DensePlan& dp, const unsig
 // build value <= 65534.  Partition count: enough that a partition's slice of the key domain fits the shared-memory
 // region of k_sjoin, and enough partitions to balance the SMs.
 static uint64_t round16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
-Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t np) const {
+Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t np, bool small_ok) const {
   Dense16Plan dp;
   if (!cfg.at("dense") || !cfg.at("dense16") || !cfg.at("narrow") || (flags & (FJ_FLAG_FORCE_WIDE | FJ_FLAG_PROBE_IDX))) return dp;
-  if (nb < (uint64_t)std::max<int64_t>(std::min(cfg.at("dense_min_rows"), cfg.at("dense16_min_rows")), 1024) || np == 0) return dp;
+  // small build sides only when the caller asked for them (adaptive materialize with a big probe side); an explicit radix
+  // request keeps the general radix path below dense_min_rows
+  const int64_t min_rows = small_ok ? std::min(cfg.at("dense_min_rows"), cfg.at("dense16_min_rows")) : cfg.at("dense_min_rows");
+  if (nb < (uint64_t)std::max<int64_t>(min_rows, 1024) || np == 0) return dp;
   const uint64_t maxslots = sjoin_max_slots(di);
   const uint64_t need = nb + nb / 5 + 1024;  // h2o ids are 1..1.1*n
   int logp = (int)cfg.at("dense16_logp");
@@ -915,11 +922,11 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = dp.logp;
   a.cursor_stride = cs;
   a.in_keys = bk; a.in_vals = mat ? bv : nullptr; a.n = nb; a.cap = dp.cap_b; a.cursor = cur_b; a.out = part_a_b.p; a.strict = true;
-  a.warps = (int)(mat ? cfg["part_warps_kv"] : cfg["part_warps_k"]);
+  a.direct_in = (mat ? cfg["part_direct_kv"] : cfg["part_direct_count_build"]) != 0;
   bool launched = launch_part(mat, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[12], st));
   a.in_keys = pk; a.in_vals = nullptr; a.n = np; a.cap = dp.cap_p; a.cursor = cur_p; a.out = part_a_p.p; a.strict = false;
-  a.warps = (int)cfg["part_warps_k"];
+  a.direct_in = cfg["part_direct_k"] != 0;
   launched = launched && launch_part(false, a, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[2], st));
   if (launched) {
@@ -1025,7 +1032,7 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
                                                                  (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0)));
   Dense16Plan d16;
   if (narrow && radix_wanted) {
-    d16 = plan_dense16(flags, nb, np);
+    d16 = plan_dense16(flags, nb, np, prefer16);
     dplan = plan_dense(flags, nb, np);
   }
   for (int attempt = 1; attempt <= 7; ++attempt) {
@@ -1532,14 +1539,14 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
     if (nb) {
       a.out = static_cast<char*>(xp.local) + ctrl_bytes;
       a.in_keys = d_bk; a.in_vals = mat ? d_bv : nullptr; a.n = nb; a.cap = cap_b; a.cursor = cur_b; a.strict = true;
-      a.warps = (int)(mat ? cfg["part_warps_kv"] : cfg["part_warps_k"]);
+      a.direct_in = (mat ? cfg["part_direct_kv"] : cfg["part_direct_count_build"]) != 0;
       launched = launch_part(mat, a, di, st, &launches);
     }
     FJ_CUDA(cudaEventRecord(ev[12], st));
     if (np && launched) {
       a.out = static_cast<char*>(xp.local) + ctrl_bytes + b_bytes;
       a.in_keys = d_pk; a.in_vals = nullptr; a.n = np; a.cap = cap_p; a.cursor = cur_p; a.strict = false;
-      a.warps = (int)cfg["part_warps_k"];
+      a.direct_in = cfg["part_direct_k"] != 0;
       launched = launch_part(false, a, di, st, &launches);
     }
     xa.phase = 1; xa.seq = 3 * step + 2;

@@ -206,7 +206,7 @@ struct PartArgs {
   void* out = nullptr;   // partition buffer: partition d at elements [d * cap, d * cap + cursor[d])
   int logp = 11;         // log2(partitions)
   bool strict = false;
-  int warps = 16;           // warps per CTA: 16 (2 KB batches per warp) or 32 (1 KB batches)
+  bool direct_in = false;   // input rows by 128-bit loads straight into registers instead of the per-warp TMA rings
 };
 size_t part_smem_bytes(int logp);
 uint32_t part_sector_elems(bool val);

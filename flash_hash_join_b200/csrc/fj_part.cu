@@ -112,9 +112,11 @@ __device__ __forceinline__ bool piece_has_hole(const uint4& v) {
 //     reservation of the partition's next global sector, whose answer is published a batch later.
 //   * Entries that cannot leave yet stay on the list; a warp never blocks (on input data, on a pending row) without
 //     servicing its list, so the oldest sector of every partition can always make progress.
-// NW: warps per CTA (16: batches of 2 KB per warp; 32: batches of 1 KB)
-template <bool VAL, bool STRICT, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
+// DIRECT: a warp's batches go from global memory straight into registers (128-bit streaming loads, the next batch in
+// flight while the current one is placed and flushed) instead of through the warp's TMA input ring
+template <bool VAL, bool STRICT, bool DIRECT>
+__global__ void __launch_bounds__(512, 1) k_part(const PartParams a) {
+  constexpr int NW = 16;  // (32 warps with 1 KB batches were slower on both sides: profiles/r02m_exp_part.jsonl)
   constexpr int PT_THREADS = NW * 32;
   constexpr int PT_WARPS = NW;
   constexpr int PT_SLOT_BYTES = PT_RING_BYTES / (NW * PT_WSLOTS);  // one batch of one warp
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   const uint32_t capsec = a.cap >> LOG_EPS;
   const uint32_t pmask = P - 1u;
 
-  if (tid == 0) {
+  if (!DIRECT && tid == 0) {
     for (int s = 0; s < PT_WARPS * PT_WSLOTS; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
     bulk_g2s(dst, a.in_keys + row0, BROWS * 8u, &my_full[s]);
     if constexpr (VAL) bulk_g2s(dst + BROWS * 8u, a.in_vals + row0, BROWS * 8u, &my_full[s]);
   };
-  if (lane == 0) {
+  if (!DIRECT && lane == 0) {
 #pragma unroll
     for (uint32_t kk = 0; kk < PT_WSLOTS; ++kk) issue(kk);
   }
@@ -215,16 +217,37 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   };
   // has batch B (this warp's batch number kk) arrived?  (warp-uniform)
   auto batch_ready = [&](uint32_t B, uint32_t kk) -> bool {
-    if (B >= nfull) return true;
+    if (DIRECT || B >= nfull) return true;
     return __all_sync(0xffffffffu, mbar_try_wait(&my_full[kk % PT_WSLOTS], (kk / PT_WSLOTS) & 1u));
   };
   // the rows of batch B.  Full batches of 16-byte aligned inputs come out of the warp's ring slot (which must be ready):
   // a lane reads pairs of adjacent rows with 128-bit loads; the slot is refilled as soon as it has been read.  The
   // ragged tail / unaligned inputs are loaded directly.
-  auto load_rows = [&](uint32_t B, uint32_t kk, Rows& r) {
+  // DIRECT: the loads of a full batch, issued one batch ahead of their use
+  struct Raw {
+    unsigned long long k[IPT], v[VAL ? IPT : 1];
+  };
+  auto issue_raw = [&](uint32_t B, Raw& x) {
+    if (B >= nfull) return;
+    const unsigned long long* kp = a.in_keys + (uint64_t)B * BROWS + 2u * lane;
+#pragma unroll
+    for (int q = 0; q < IPT / 2; ++q) ld_stream2(kp + q * 64, x.k[2 * q], x.k[2 * q + 1]);
+    if constexpr (VAL) {
+      const unsigned long long* vp = a.in_vals + (uint64_t)B * BROWS + 2u * lane;
+#pragma unroll
+      for (int q = 0; q < IPT / 2; ++q) ld_stream2(vp + q * 64, x.v[2 * q], x.v[2 * q + 1]);
+    }
+  };
+  auto load_rows = [&](uint32_t B, uint32_t kk, Rows& r, const Raw* x = nullptr) {
     r.pend = 0;
     r.inv = false;
-    if (B < nfull) {
+    if (DIRECT && B < nfull) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const unsigned long long v64 = VAL ? x->v[i] : 0ull;
+        decode((uint32_t)x->k[i], (uint32_t)(x->k[i] >> 32), (uint32_t)v64, (uint32_t)(v64 >> 32), true, i, r);
+      }
+    } else if (B < nfull) {
       const uint4* st = reinterpret_cast<const uint4*>(ring + (kk % PT_WSLOTS) * PT_SLOT_BYTES);
       uint4 k2[IPT / 2], v2[IPT / 2];
 #pragma unroll
@@ -367,18 +390,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
   uint32_t tk[IPT];
   uint32_t k = 0;
   uint32_t B = gw;
+  Raw raw;
   if (B < nbatch) {
+    if constexpr (DIRECT) issue_raw(B, raw);
     for (uint32_t spin = 0; !batch_ready(B, 0); ++spin)
       if (spin > (1u << 24)) __trap();
-    load_rows(B, 0, cur);
+    load_rows(B, 0, cur, &raw);
   }
   while (B < nbatch) {
+    const uint32_t Bn = B + GW;
+    if constexpr (DIRECT) {
+      if (Bn < nbatch) issue_raw(Bn, raw);  // in flight while this batch is placed and flushed
+    }
     if (__any_sync(0xffffffffu, cur.inv)) place(false, cur, tk);
     else place(true, cur, tk);
     // the next batch is fetched and decoded before the flush when it has arrived already
-    const uint32_t Bn = B + GW;
     bool have = false;
-    if (Bn < nbatch && batch_ready(Bn, k + 1)) {
+    if (!DIRECT && Bn < nbatch && batch_ready(Bn, k + 1)) {
       load_rows(Bn, k + 1, nxt);
       have = true;
     }
@@ -395,7 +423,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_part(const PartParams a) {
         if (wn) flush(true);  // never wait for data while other warps may wait for a sector on this list
         if (spin > SPIN_LIMIT) __trap();
       }
-      load_rows(Bn, k + 1, nxt);
+      load_rows(Bn, k + 1, nxt, &raw);
     }
     cur = nxt;
     B = Bn;
@@ -447,16 +475,16 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   const size_t smem = part_smem_bytes(x.logp);
   if (smem + 256 > di.smem_optin) return false;
   const uint32_t grid = part_grid(val, x.n, di);
-#define FJ_PART4(V, S, W)                                                                             \
+#define FJ_PART4(V, S, D)                                                                             \
   do {                                                                                                \
     static size_t smem_set = 0; /* the attribute call costs microseconds: once per size */            \
     if (smem_set != smem) {                                                                           \
-      cudaFuncSetAttribute(k_part<V, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaFuncSetAttribute(k_part<V, S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       smem_set = smem;                                                                                \
     }                                                                                                 \
-    k_part<V, S, W><<<grid, W * 32, smem, st>>>(a);                                                  \
+    k_part<V, S, D><<<grid, 512, smem, st>>>(a);                                                     \
   } while (0)
-#define FJ_PART(V, S) do { if (x.warps == 32) FJ_PART4(V, S, 32); else FJ_PART4(V, S, 16); } while (0)
+#define FJ_PART(V, S) do { if (x.direct_in) FJ_PART4(V, S, true); else FJ_PART4(V, S, false); } while (0)
   if (val) FJ_PART(true, true);  // rows with values are a build side
   else if (x.strict) FJ_PART(false, true);
   else FJ_PART(false, false);
