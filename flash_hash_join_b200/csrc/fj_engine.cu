@@ -1560,7 +1560,7 @@ fj_status Engine::join_shuffle_peer(unsigned jflags, const unsigned long long* d
         j.probe[r] = static_cast<char*>(xp.mapped[(size_t)r]) + ctrl_bytes + b_bytes;
       }
       j.cap_b = cap_b; j.cap_p = cap_p;
-      j.p_first = (uint32_t)R * ppo; j.p_count = ppo; j.logp = gp.logp; j.nsub = W; j.slots_alloc = gp.slots;
+      j.p_first = (uint32_t)R * ppo; j.p_count = ppo; j.logp = gp.logp; j.nsub = W; j.slots_alloc = gp.slots; j.rot = (uint32_t)R + 1u;
       // count arrays [source][local partition]; k_sjoin indexes them with the GLOBAL partition id
       j.cnt_stride = ppo; j.cursor_stride = 1;
       j.bcnt = cnt - j.p_first; j.pcnt = cnt + (size_t)W * ppo - j.p_first;

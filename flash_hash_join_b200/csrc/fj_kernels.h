@@ -228,6 +228,7 @@ struct SjoinArgs {
   uint32_t cursor_stride = 1;         // cursor of (sub, p) = cnt[(sub * cnt_stride + p) * cursor_stride]
   uint32_t p_first = 0, p_count = 0;  // global ids of the partitions joined by this GPU
   int logp = 11, nsub = 1;
+  uint32_t rot = 0;                   // rotation of the order in which the sources of a partition are visited (rank + 1)
   uint32_t slots_alloc = 0;           // shared-memory direct-address slots (>= klimit >> logp), multiple of 8, <= sjoin_max_slots
   Ctl* ctl = nullptr;
   unsigned long long* out_keys = nullptr;
