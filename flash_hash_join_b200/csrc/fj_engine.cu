@@ -125,6 +125,10 @@ struct Engine {
     std::vector<cudaEvent_t> done;     // [threads]
   } stager;
   fj_status h2d(void* dst, const void* src, size_t bytes);
+  // device -> host copy of a result column, the mirror image: large pageable destinations (fresh numpy arrays) are
+  // filled by the same host threads from the pinned ring (each thread also takes the page faults of its chunks)
+  fj_status d2h(void* dst, const void* src, size_t bytes);
+  fj_status stager_setup(int want_threads, size_t chunk);
   void stager_release();
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
   DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush, sj_tails;
@@ -434,19 +438,7 @@ fj_status Engine::h2d(void* dst, const void* src, size_t bytes) {
     return FJ_OK;
   }
   const size_t CH = size_t(8) << 20;
-  if (stager.threads != want_threads || stager.chunk != CH) {
-    stager_release();
-    stager.threads = want_threads;
-    stager.chunk = CH;
-    stager.bufs.assign((size_t)want_threads * 2, nullptr);
-    stager.evs.assign((size_t)want_threads * 2, nullptr);
-    stager.streams.assign((size_t)want_threads, nullptr);
-    stager.done.assign((size_t)want_threads, nullptr);
-    for (auto& b : stager.bufs) FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b), CH));
-    for (auto& e : stager.evs) FJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : stager.done) FJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& q : stager.streams) FJ_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
-  }
+  FJ_TRY(stager_setup(want_threads, CH));
   // the copy streams must not overtake work already queued on the engine's stream that still uses `dst`
   FJ_CUDA(cudaEventRecord(stager.done[0], st));
   for (int t = 0; t < want_threads; ++t) FJ_CUDA(cudaStreamWaitEvent(stager.streams[(size_t)t], stager.done[0], 0));
@@ -482,6 +474,80 @@ fj_status Engine::h2d(void* dst, const void* src, size_t bytes) {
   for (int t = 0; t < want_threads; ++t) {
     FJ_CUDA(cudaEventRecord(stager.done[(size_t)t], stager.streams[(size_t)t]));
     FJ_CUDA(cudaStreamWaitEvent(st, stager.done[(size_t)t], 0));
+  }
+  return FJ_OK;
+}
+
+fj_status Engine::stager_setup(int want_threads, size_t CH) {
+  if (stager.threads == want_threads && stager.chunk == CH) return FJ_OK;
+  stager_release();
+  stager.threads = want_threads;
+  stager.chunk = CH;
+  stager.bufs.assign((size_t)want_threads * 2, nullptr);
+  stager.evs.assign((size_t)want_threads * 2, nullptr);
+  stager.streams.assign((size_t)want_threads, nullptr);
+  stager.done.assign((size_t)want_threads, nullptr);
+  for (auto& b : stager.bufs) FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b), CH));
+  for (auto& e : stager.evs) FJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : stager.done) FJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& q : stager.streams) FJ_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  return FJ_OK;
+}
+
+fj_status Engine::d2h(void* dst, const void* src, size_t bytes) {
+  if (!bytes) return FJ_OK;
+  const int want_threads = (int)std::min<int64_t>(32, std::max<int64_t>(0, cfg["stage_threads"]));
+  bool staged = want_threads > 0 && bytes >= ((size_t)std::max<int64_t>(1, cfg["stage_min_mb"]) << 20);
+  if (staged) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, dst) != cudaSuccess) {
+      cudaGetLastError();
+    } else if (pa.type != cudaMemoryTypeUnregistered) {
+      staged = false;  // pinned / registered / managed: the DMA engine writes it directly
+    }
+  }
+  if (!staged) {
+    FJ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    return FJ_OK;
+  }
+  const size_t CH = size_t(8) << 20;
+  FJ_TRY(stager_setup(want_threads, CH));
+  FJ_CUDA(cudaStreamSynchronize(st));  // the pairs are final
+  const size_t nchunks = (bytes + CH - 1) / CH;
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  const int dev = di.device;
+  // every thread keeps two chunks in flight: the DMA of chunk i + 1 runs while chunk i is copied out of its pinned buffer
+  auto worker = [&](int t) {
+    if (cudaSetDevice(dev) != cudaSuccess) { failed = 1; return; }
+    cudaStream_t q = stager.streams[(size_t)t];
+    size_t idx[2] = {nchunks, nchunks};
+    auto start = [&](int b) {
+      const size_t i = next.fetch_add(1);
+      idx[b] = i;
+      if (i >= nchunks) return;
+      const size_t off = i * CH, len = std::min(CH, bytes - off);
+      if (cudaMemcpyAsync(stager.bufs[(size_t)t * 2 + b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, q) != cudaSuccess ||
+          cudaEventRecord(stager.evs[(size_t)t * 2 + b], q) != cudaSuccess) failed = 1;
+    };
+    start(0);
+    start(1);
+    for (int b = 0; idx[b] < nchunks && !failed.load(); b ^= 1) {
+      if (cudaEventSynchronize(stager.evs[(size_t)t * 2 + b]) != cudaSuccess) { failed = 1; break; }
+      const size_t off = idx[b] * CH, len = std::min(CH, bytes - off);
+      memcpy(static_cast<char*>(dst) + off, stager.bufs[(size_t)t * 2 + b], len);
+      start(b);
+    }
+    cudaStreamSynchronize(q);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < want_threads; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  if (failed.load()) {
+    cudaGetLastError();
+    return set_err(FJ_ERR_CUDA, "staged device->host copy failed");
   }
   return FJ_OK;
 }
@@ -1971,10 +2037,9 @@ FJ_API fj_status fj_pairs_fetch(uint64_t* keys, uint64_t* values, uint64_t* prob
   if (!keys || !values) return set_err(FJ_ERR_BAD_ARG, "NULL output pointer");
   if (probe_idx_or_null && !e.pairs_idx) return set_err(FJ_ERR_STATE, "probe indices were not requested (FJ_FLAG_PROBE_IDX)");
   FJ_CUDA(cudaSetDevice(e.di.device));
-  FJ_CUDA(cudaMemcpyAsync(keys, e.out_keys.p, e.pairs_n * 8, cudaMemcpyDeviceToHost, e.st));
-  FJ_CUDA(cudaMemcpyAsync(values, e.out_vals.p, e.pairs_n * 8, cudaMemcpyDeviceToHost, e.st));
-  if (probe_idx_or_null) FJ_CUDA(cudaMemcpyAsync(probe_idx_or_null, e.out_idx.p, e.pairs_n * 8, cudaMemcpyDeviceToHost, e.st));
-  FJ_CUDA(cudaStreamSynchronize(e.st));
+  FJ_TRY(e.d2h(keys, e.out_keys.p, e.pairs_n * 8));
+  FJ_TRY(e.d2h(values, e.out_vals.p, e.pairs_n * 8));
+  if (probe_idx_or_null) FJ_TRY(e.d2h(probe_idx_or_null, e.out_idx.p, e.pairs_n * 8));
   return FJ_OK;
 }
 FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values, const uint64_t** probe_idx, uint64_t* n) {
