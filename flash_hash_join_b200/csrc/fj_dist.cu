@@ -123,19 +123,6 @@ fj_status_t dist_allgather_u64(DistState& d, const void* send, void* recv, size_
   FJ_NCCL(g_api.AllGather(send, recv, count_per_rank, ncclUint64, reinterpret_cast<ncclComm_t>(d.comm), st));
   return 0;
 }
-fj_status_t dist_alltoallv_bytes(DistState& d, const void* send, const uint64_t* send_offs, const uint64_t* send_counts,
-                                 void* recv, const uint64_t* recv_offs, const uint64_t* recv_counts, cudaStream_t st) {
-  ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);
-  FJ_NCCL(g_api.GroupStart());
-  for (int r = 0; r < d.world; ++r) {
-    if (send_counts[r])
-      FJ_NCCL(g_api.Send(static_cast<const char*>(send) + send_offs[r], send_counts[r], ncclUint8, r, comm, st));
-    if (recv_counts[r])
-      FJ_NCCL(g_api.Recv(static_cast<char*>(recv) + recv_offs[r], recv_counts[r], ncclUint8, r, comm, st));
-  }
-  FJ_NCCL(g_api.GroupEnd());
-  return 0;
-}
 
 fj_status_t dist_exchange(DistState& d, const DistMsg* sends, size_t n_sends, const DistMsg* recvs, size_t n_recvs,
                           cudaStream_t st) {

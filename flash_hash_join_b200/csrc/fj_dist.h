@@ -32,10 +32,6 @@ fj_status_t dist_broadcast2_u64(DistState& d, const void* send_a, void* recv_a, 
                                 int root, cudaStream_t st);
 fj_status_t dist_allreduce_sum_u64(DistState& d, const void* send, void* recv, size_t count, cudaStream_t st);
 fj_status_t dist_allgather_u64(DistState& d, const void* send, void* recv, size_t count_per_rank, cudaStream_t st);
-// all-to-all-v of bytes: rank r sends send_counts[r] bytes from send + send_offs[r], receives recv_counts[r] at recv + recv_offs[r]
-fj_status_t dist_alltoallv_bytes(DistState& d, const void* send, const uint64_t* send_offs, const uint64_t* send_counts,
-                                 void* recv, const uint64_t* recv_offs, const uint64_t* recv_counts, cudaStream_t st);
-
 // grouped point-to-point exchange: every message of `sends` is ncclSend to its peer, every message of `recvs`
 // ncclRecv from its peer, all inside one ncclGroupStart/End.  Messages between the same pair of ranks are
 // matched in list order.

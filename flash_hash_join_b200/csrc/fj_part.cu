@@ -17,17 +17,19 @@
 //   * a partition's direct-address region (2 bytes per key of its slice of the domain, <= 128 KB) is zeroed, filled
 //     and probed in shared memory: no random access ever reaches L2 or HBM.
 //
-// k_part: persistent, one CTA per SM.  Shared memory holds, for EVERY partition, a 64-byte ring of two 32-byte
-// sectors.  Rows are appended with one shared-memory atomicAdd (slot) and one store; the row that completes a
-// sector puts the partition on a flush list; after a block barrier the listed sectors leave as full, aligned
-// 32-byte sectors to a position reserved IN ADVANCE with a global atomicAdd (the reservation for the next flush of
-// that partition is issued while this one is stored, so its latency is never waited for).  Probe/build keys arrive
-// through a 4-deep TMA (cp.async.bulk + mbarrier) ring; build values are prefetched one round ahead into registers.
-// At the end every CTA pads its partial sectors with holes (idx 0xFFFF) and flushes them.
+// k_part: persistent, one CTA of 16 independent warps per SM, no block barrier in the main loop.  Shared memory holds,
+// for EVERY partition, a 64-byte ring of two 32-byte sectors and a tail | count word: a row claims a ticket with one
+// shared-memory atomicAdd and stores its element into the slot the ticket names; the row that takes a sector's last
+// ticket lists the sector; a listed sector leaves as a full, aligned 32-byte sector — in ticket order per partition,
+// once no slot holds the hole marker any more — to a position reserved IN ADVANCE with a global atomicAdd (the next
+// reservation is issued while this sector is stored, its answer is consumed a batch later).  Every warp streams its own
+// batches through a private two-slot TMA (cp.async.bulk + mbarrier) input ring.  The protocol is described at the kernel.
 //
 // k_sjoin: persistent, one CTA per SM; warp 0 is the TMA producer, warps 1..31 consume.  The producer streams the
-// chunks of [build rows of p][probe rows of p][build rows of p'] ... through a 5-deep ring with full/empty
-// mbarriers, independent of the consumers' phase (zero | fill | probe), so HBM never idles at a phase change.
+// chunks of [build rows of p][probe rows of p][build rows of p'] ... — from the local partition buffer or, in the
+// multi-GPU shuffle, from every peer's buffer over NVLink — through a 3-deep ring with full/empty mbarriers, independent
+// of the consumers' phase (fill | probe | clear), so HBM never idles at a phase change.  k_pairs_compact closes the
+// tails of the output blocks; k_xsync carries the cross-GPU steps of the shuffle.
 #include <type_traits>
 
 #include "fj_kernels.h"
