@@ -201,6 +201,7 @@ struct Engine {
     cfg["part_direct_kv"] = 0;
     cfg["part_direct_k"] = 0;
     cfg["part_direct_count_build"] = 1;
+    cfg["dist_warmup"] = 1;         // fj_comm_init pays NCCL's first-use cost of broadcast and point-to-point channels
     cfg["dist_peer_shuffle"] = 1;   // SHUFFLE on a dense key domain: one partition pass storing straight into the owners' buffers
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
     cfg["dist_spec_allreduce"] = 1; // multi-GPU count: all-reduce enqueued behind the first attempt (one host sync per step)
@@ -2178,10 +2179,30 @@ FJ_API fj_status fj_comm_init(int rank, int world, const void* id128) {
   FJ_TRY(E().init(-1));
   FJ_CUDA(cudaSetDevice(E().di.device));
   FJ_TRY(dist_init(E().dist, rank, world, id128));
-  return E().peer_setup();
+  FJ_TRY(E().peer_setup());  // (its all-gather and all-reduce also pay NCCL's first-use cost of those collectives)
+  // first use of a broadcast and of point-to-point channels costs 0.5 - 3 s (connection setup): pay it here, not in
+  // the first join (profiles/r01m4_dist_check_2gpu.log)
+  Engine& e = E();
+  if (world > 1 && e.cfg["dist_warmup"]) {
+    FJ_TRY(e.dist_scratch.ensure(4096));
+    unsigned long long* w = e.dist_scratch.as<unsigned long long>();
+    FJ_CUDA(cudaMemsetAsync(w, 0, 4096, e.st));
+    FJ_TRY(dist_broadcast_u64(e.dist, w, 1, 0, e.st));
+    std::vector<DistMsg> sends, recvs;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      sends.push_back({r, reinterpret_cast<char*>(w + 8), 8});
+      recvs.push_back({r, reinterpret_cast<char*>(w + 16 + r), 8});
+    }
+    FJ_TRY(dist_exchange(e.dist, sends.data(), sends.size(), recvs.data(), recvs.size(), e.st));
+    FJ_CUDA(cudaStreamSynchronize(e.st));
+  }
+  return FJ_OK;
 }
 FJ_API fj_status fj_comm_destroy(void) {
   std::lock_guard<std::mutex> lk(E().mu);
+  E().xpart_teardown();
+  E().xp = Engine::XPart();
   E().peer_teardown();
   dist_destroy(E().dist);
   return FJ_OK;

@@ -739,22 +739,39 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
         const uint32_t* cnt = side ? a.pcnt : a.bcnt;
         const uint64_t cap = side ? a.cap_p : a.cap_b;
         const uint32_t eb = side ? 2u : EB;
+        // The rows of partition p on this side = the pieces every source keeps in ITS partition buffer (local, or a
+        // peer's over NVLink), concatenated in the rotated source order.  The stream is cut into ring stages of SJ_CH
+        // bytes; a stage is filled by one bulk copy per piece (or part of a piece) it covers, so the number of stages —
+        // and of producer / consumer handshakes — does not grow with the number of sources.
+        uint64_t stream = 0;
         for (int si = 0; si < a.nsub; ++si) {
-          const int sub = sub_at(si);
-          uint64_t c = cnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
-          if (c > cap) c = cap;
-          const uint64_t bytes_total = c * eb;  // multiple of 32 (sectors)
-          // source `sub` keeps the rows of partition p in ITS partition buffer (local, or a peer's over NVLink: the bulk
-          // copies below pull them in chunks of up to 31 KB)
-          const unsigned char* src = (side ? a.probe[sub] : a.build[sub]) + (uint64_t)(a.p_first + l) * cap * eb;
-          for (uint64_t off = 0; off < bytes_total; off += SJ_CH) {
-            const int s = it % SJ_STAGES;
-            mbar_wait_bounded(&s_empty[s], ((it / SJ_STAGES) & 1u) ^ 1u);
-            const uint32_t bytes = (uint32_t)(bytes_total - off < (uint64_t)SJ_CH ? bytes_total - off : (uint64_t)SJ_CH);
-            mbar_expect_tx(&s_full[s], bytes);
-            bulk_g2s(ring + (size_t)s * SJ_CH, src + off, bytes, &s_full[s]);
-            ++it;
+          uint64_t c = cnt[((size_t)sub_at(si) * a.cnt_stride + a.p_first + l) * a.cstride];
+          stream += (c < cap ? c : cap) * eb;
+        }
+        int si = 0;
+        uint64_t piece_left = 0;
+        const unsigned char* piece = nullptr;
+        for (uint64_t off = 0; off < stream; off += SJ_CH) {
+          const int s = it % SJ_STAGES;
+          mbar_wait_bounded(&s_empty[s], ((it / SJ_STAGES) & 1u) ^ 1u);
+          const uint32_t bytes = (uint32_t)(stream - off < (uint64_t)SJ_CH ? stream - off : (uint64_t)SJ_CH);
+          mbar_expect_tx(&s_full[s], bytes);
+          uint32_t filled = 0;
+          while (filled < bytes) {
+            while (piece_left == 0) {  // next source with rows of this partition
+              const int sub = sub_at(si++);
+              uint64_t c = cnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
+              if (c > cap) c = cap;
+              piece_left = c * eb;  // multiple of 32 (sectors)
+              piece = (side ? a.probe[sub] : a.build[sub]) + (uint64_t)(a.p_first + l) * cap * eb;
+            }
+            const uint32_t n = (uint32_t)(piece_left < (uint64_t)(bytes - filled) ? piece_left : (uint64_t)(bytes - filled));
+            bulk_g2s(ring + (size_t)s * SJ_CH + filled, piece, n, &s_full[s]);
+            piece += n;
+            piece_left -= n;
+            filled += n;
           }
+          ++it;
         }
       }
     }
@@ -795,15 +812,12 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     const uint32_t plow = a.p_first + l;  // the key bits the partition implies
     // ---- fill: region[idx] = value + 1 (count: 1)
     unsigned long long rowsum = 0;
-    for (int si = 0; si < a.nsub; ++si) {
-      const int sub = sub_at(si);
-      uint64_t c = a.bcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
-      if (c > a.cap_b) c = a.cap_b;
-      const uint32_t bytes_total = (uint32_t)(c * EB);
-      for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
+    {
+      const uint64_t bytes_total = side_total(a.bcnt, a.cap_b, l) * EB;  // the concatenated pieces of every source
+      for (uint64_t off = 0; off < bytes_total; off += SJ_CH) {
         const int s = it % SJ_STAGES;
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
-        const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
+        const uint32_t bytes = (uint32_t)(bytes_total - off < (uint64_t)SJ_CH ? bytes_total - off : (uint64_t)SJ_CH);
         const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
         uint4 v[SJ_NPC];
 #pragma unroll
@@ -846,15 +860,12 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
     sj_bar_consumers();
     // ---- probe: one pass
     uint32_t mine = 0;
-    for (int si = 0; si < a.nsub; ++si) {
-      const int sub = sub_at(si);
-      uint64_t c = a.pcnt[((size_t)sub * a.cnt_stride + a.p_first + l) * a.cstride];
-      if (c > a.cap_p) c = a.cap_p;
-      const uint32_t bytes_total = (uint32_t)(c * 2u);
-      for (uint32_t off = 0; off < bytes_total; off += SJ_CH) {
+    {
+      const uint64_t bytes_total = side_total(a.pcnt, a.cap_p, l) * 2u;
+      for (uint64_t off = 0; off < bytes_total; off += SJ_CH) {
         const int s = it % SJ_STAGES;
         mbar_wait_bounded(&s_full[s], (it / SJ_STAGES) & 1u);
-        const uint32_t bytes = bytes_total - off < (uint32_t)SJ_CH ? bytes_total - off : (uint32_t)SJ_CH;
+        const uint32_t bytes = (uint32_t)(bytes_total - off < (uint64_t)SJ_CH ? bytes_total - off : (uint64_t)SJ_CH);
         const uint4* st = reinterpret_cast<const uint4*>(ring + (size_t)s * SJ_CH);
         uint4 v[SJ_NPC];
 #pragma unroll
