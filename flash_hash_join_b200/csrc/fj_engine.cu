@@ -302,6 +302,11 @@ fj_status Engine::init(int device) {
   di.smem_optin = prop.sharedMemPerBlockOptin;
   di.cc_major = prop.major;
   di.cc_minor = prop.minor;
+  // tunables from the environment (experiments, sweeps): FJ_CFG_<key>=<integer> for any key of fj_config_set
+  for (auto& kv : cfg) {
+    const std::string name = "FJ_CFG_" + kv.first;
+    if (const char* v = getenv(name.c_str())) kv.second = atoll(v);
+  }
   FJ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto& x : ev) FJ_CUDA(cudaEventCreate(&x));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl)));
