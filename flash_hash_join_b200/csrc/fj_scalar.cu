@@ -1369,6 +1369,9 @@ void launch_probe(const TableView& t, const unsigned long long* pk, uint64_t np,
   const int bloom = t.bloom == nullptr ? 0 : (bloom_in_smem ? 1 : 2);
   const bool mat = out != nullptr;
   const bool idx = mat && out->idx != nullptr;
+  // (shared-memory filter: ONE 1024-thread CTA per SM.  Two 512-thread CTAs with a filter of 8 bits per key instead of
+  // 16 were measured at C2: 0.477 vs 0.185 ms — more false positives reach the table stage and every SM holds the
+  // filter twice: profiles/r02D_exp_bloom.jsonl)
   if (!mat) {
 #define FJ_CNT(N)                                                                       \
   do {                                                                                  \
