@@ -201,6 +201,7 @@ struct Engine {
     cfg["part_direct_kv"] = 0;
     cfg["part_direct_k"] = 0;
     cfg["part_direct_count_build"] = 1;
+    cfg["peer_relay_min_rows"] = 1 << 18;  // multi-GPU count over peer memory: build rows from which the key slices / partial bitmaps relay is used
     cfg["dist_warmup"] = 1;         // fj_comm_init pays NCCL's first-use cost of broadcast and point-to-point channels
     cfg["dist_peer_shuffle"] = 1;   // SHUFFLE on a dense key domain: one partition pass storing straight into the owners' buffers
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
@@ -1714,7 +1715,7 @@ fj_status Engine::peer_setup() {
   peer_teardown();
   const int W = dist.world, R = dist.rank;
   if (!dist.ready || W < 2 || W > 32 || !cfg["dist_peer"]) return FJ_OK;
-  const size_t bytes = peer_staging_offset_bytes() + (size_t(16) << 20);  // staging area: 2 Mi build keys
+  const size_t bytes = peer_buffer_bytes();  // control words + staging area (2 Mi build keys) + partial bitmap
   bool ok = cudaMalloc(&peer.local, bytes) == cudaSuccess;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
@@ -1784,8 +1785,9 @@ fj_status Engine::attempt_count_peer(uint64_t dbits, int root, const unsigned lo
   if (dist.rank == root)
     FJ_CUDA(cudaMemcpyAsync(static_cast<char*>(peer.local) + peer_staging_offset_bytes(), bk_root, nb * 8,
                             bk_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  const bool relay = nb >= (uint64_t)std::max<int64_t>(1, cfg["peer_relay_min_rows"]);
   if (!launch_count_dense_peer(nb, pk, np, bloom.as<uint32_t>(), (uint32_t)(dbits / 32), d_ctl, gsync, peer.d_ptrs, dist.rank,
-                               dist.world, root, step, di, st, &launches))
+                               dist.world, root, step, relay, di, st, &launches))
     return set_err(FJ_ERR_CUDA, "k_count_dense_peer: no co-resident launch configuration");
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
@@ -1839,7 +1841,7 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
       const bool scalar_path = algo == FJ_ALGO_SCALAR ||
                                (algo == FJ_ALGO_ADAPTIVE && table_bytes <= (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0);
       const uint64_t dbits = (peer.ready && cfg["dist_peer"] && cfg["dense_fused"] && !(jflags & FJ_FLAG_MATERIALIZE) && narrow_cfg &&
-                              scalar_path && nb > 0 && nb * 8 <= peer.bytes - peer_staging_offset_bytes())
+                              scalar_path && nb > 0 && nb * 8 <= peer_staging_bytes())
                                  ? dense_bitmap_bits(nb) : 0;
       if (dbits) {
         const unsigned long long* d_pk;

@@ -91,10 +91,13 @@ bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const u
 // multi-GPU count over peer memory (one kernel per GPU, no NCCL in the step): `peers` = device array of every rank's
 // IPC-mapped exchange buffer; the root's build keys must already lie at peer_staging_offset_bytes() of ITS buffer
 // (stream-ordered before the launch); the sum of all ranks' counts arrives in Ctl::global_count
+// relay: every rank pulls only its slice of the keys and the ranks exchange partial bitmaps (large build sides)
 size_t peer_staging_offset_bytes();
+size_t peer_staging_bytes();
+size_t peer_buffer_bytes();  // exchange buffer every rank allocates: control words, key staging area, partial bitmap
 bool launch_count_dense_peer(uint64_t nb, const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
                              uint32_t* gsync, unsigned long long* const* peers, int rank, int world, int root,
-                             unsigned long long step, const DeviceInfo& di, cudaStream_t st, int* launches);
+                             unsigned long long step, bool relay, const DeviceInfo& di, cudaStream_t st, int* launches);
 // dense key domain, materialize: bitmap + direct-address value table direct[key] (8 bytes per key of the domain,
 // L2 resident), one persistent launch; a duplicate build key raises CTL_DUP, a key >= dbits CTL_NOT_DENSE
 bool launch_mat_dense_fused(const unsigned long long* bk, const unsigned long long* bv, uint64_t nb, const unsigned long long* pk,

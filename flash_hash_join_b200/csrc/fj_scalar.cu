@@ -852,6 +852,14 @@ bool launch_count_dense_fused(const unsigned long long* bk, uint64_t nb, const u
 constexpr int PEER_READY_WORD = 0;
 constexpr int PEER_SLOT_WORD = 8;       // + 8 * rank
 constexpr int PEER_STAGING_WORD = 8192;  // 64 KB into the buffer
+// Relay (large build sides): every rank pulls only ITS slice of the build keys from the root and sets their bits in a
+// partial bitmap that lives in its exchange buffer (PEER_PARTIAL bytes behind the staging area); after a cross-GPU
+// barrier every rank ORs the partial bitmaps of all ranks into its own full bitmap.  The root then sends every key once
+// (nb * 8 bytes leave it instead of (world - 1) * nb * 8: at 1e6 keys and 8 GPUs the root's NVLink egress made the
+// count step 0.30 ms against 0.21 ms on one GPU, profiles/r02A_bench_n8.json); a bitmap is 2 bits per key.
+constexpr int PEER_PARTIAL_WORD = 4096;            // + rank: step | bad << 63 posted by `rank` when its partial bitmap is complete
+constexpr size_t PEER_STAGING_BYTES = size_t(16) << 20;
+constexpr size_t PEER_PARTIAL_BYTES = size_t(256) << 10;
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -889,7 +897,7 @@ __global__ void __launch_bounds__(THREADS)
     k_count_dense_peer(uint64_t nb, const unsigned long long* __restrict__ pk, uint64_t np, uint32_t* __restrict__ bitmap,
                        uint32_t dwords /*multiple of 4*/, Ctl* __restrict__ ctl, uint32_t* __restrict__ gsync, int vec_ok,
                        unsigned long long* const* __restrict__ peers /*[world] exchange buffers, peers[rank] is local*/,
-                       int rank, int world, int root, unsigned long long step) {
+                       int rank, int world, int root, unsigned long long step, int relay) {
   constexpr uint32_t TILE = THREADS * PROBE_KPT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_flag;
@@ -915,7 +923,10 @@ __global__ void __launch_bounds__(THREADS)
     ctl->global_count = 0;
     if (rank == root) st_release_sys_u64(root_buf + PEER_READY_WORD, step);
   }
-  for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // relay: the bits go into the partial bitmap in my exchange buffer (peers read it), the full bitmap is assembled later
+  uint32_t* const partial = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(my_buf) + (size_t)PEER_STAGING_WORD * 8 + PEER_STAGING_BYTES);
+  uint32_t* const target = relay ? partial : bitmap;
+  for (uint64_t i = gtid; i < dwords / 4; i += gthreads) reinterpret_cast<uint4*>(target)[i] = make_uint4(0u, 0u, 0u, 0u);
   const uint64_t ntiles = (np + TILE - 1) / TILE;
   unsigned long long ka[PROBE_KPT], kb[PROBE_KPT];
   uint32_t va = 0, vb = 0;
@@ -944,30 +955,76 @@ __global__ void __launch_bounds__(THREADS)
       // profiles/r02s_bench_n8.json)
       auto put = [&](unsigned long long k) {
         if (k >= dbits) bad = true;
-        else atomicOr(bitmap + (uint32_t)(k >> 5), 1u << ((uint32_t)k & 31u));
+        else atomicOr(target + (uint32_t)(k >> 5), 1u << ((uint32_t)k & 31u));
       };
       const uint64_t npair = nb / 2;  // the staging area is 16-byte aligned
-      for (uint64_t i0 = gtid; i0 < npair; i0 += 4 * gthreads) {
+      // relay: pairs [p0, p1) are this rank's slice
+      const uint64_t per = relay ? (npair + (uint64_t)world - 1) / (uint64_t)world : npair;
+      const uint64_t p0 = relay ? (uint64_t)rank * per : 0, p1 = p0 + per < npair ? p0 + per : npair;
+      for (uint64_t i0 = p0 + gtid; i0 < p1; i0 += 4 * gthreads) {
         unsigned long long a[4], b[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const uint64_t i = i0 + (uint64_t)u * gthreads;
           a[u] = b[u] = ~0ull;
-          if (i < npair) asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a[u]), "=l"(b[u]) : "l"(bk + 2 * i));
+          if (i < p1) asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a[u]), "=l"(b[u]) : "l"(bk + 2 * i));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (i0 + (uint64_t)u * gthreads < npair) {
+          if (i0 + (uint64_t)u * gthreads < p1) {
             put(a[u]);
             put(b[u]);
           }
         }
       }
-      if ((nb & 1ull) && gtid == 0) put(ld_relaxed_sys_u64(bk + nb - 1));
+      if ((nb & 1ull) && gtid == 0 && (!relay || rank == world - 1)) put(ld_relaxed_sys_u64(bk + nb - 1));
     }
     if (bad) atomicOr(&ctl->flags, CTL_NOT_DENSE);
   }
   grid_barrier(gsync + 1);
+  if (relay) {
+    // ---- phase 1b: my partial bitmap is complete: tell every rank (with my verdict on the keys I saw), wait for all
+    // partial bitmaps, OR them into my full bitmap
+    if (gtid == 0) {
+      __threadfence_system();
+      const unsigned long long bad_here = (*reinterpret_cast<volatile unsigned int*>(&ctl->flags) & CTL_NOT_DENSE) ? (1ull << 63) : 0ull;
+      for (int r = 0; r < world; ++r) st_release_sys_u64(peers[r] + PEER_PARTIAL_WORD + rank, step | bad_here);
+    }
+    if (tid == 0) {
+      int ok = 1, anybad = 0;
+      for (int r = 0; r < world && ok; ++r) {
+        const unsigned long long* wd = my_buf + PEER_PARTIAL_WORD + r;
+        unsigned long long v = ld_acquire_sys_u64(wd);
+        if ((v & ~(1ull << 63)) < step) {
+          const unsigned long long t0 = globaltimer_ns();
+          for (;;) {
+            v = ld_acquire_sys_u64(wd);
+            if ((v & ~(1ull << 63)) >= step) break;
+            __nanosleep(200);
+            if (globaltimer_ns() - t0 > 10000000000ull) { ok = 0; break; }
+          }
+        }
+        anybad |= (int)(v >> 63);
+      }
+      if (!ok) atomicOr(&ctl->flags, CTL_PEER_TIMEOUT);
+      if (anybad) atomicOr(&ctl->flags, CTL_NOT_DENSE);  // some rank saw a key outside the domain: everybody falls back
+      s_flag = ok;
+    }
+    __syncthreads();
+    if (s_flag) {
+      for (uint64_t i = gtid; i < dwords / 4; i += gthreads) {
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = 0; r < world; ++r) {
+          const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(peers[r]) + (size_t)PEER_STAGING_WORD * 8 + PEER_STAGING_BYTES) + i;
+          uint4 v;
+          asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pp));
+          acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+        }
+        reinterpret_cast<uint4*>(bitmap)[i] = acc;
+      }
+    }
+    grid_barrier(gsync + 3);  // (a barrier word serves once per launch: the fourth word is this kernel's own)
+  }
 
   // ---- phase 2: private copy of the bitmap, stream the probe tiles
   uint32_t cnt = 0;
@@ -1042,6 +1099,7 @@ __global__ void __launch_bounds__(THREADS)
       gsync[0] = 0;
       gsync[1] = 0;
       gsync[2] = 0;
+      gsync[3] = 0;
     }
   }
 }
@@ -1049,7 +1107,7 @@ __global__ void __launch_bounds__(THREADS)
 template <int THREADS>
 static bool launch_count_dense_peer_inst(uint64_t nb, const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords,
                                          Ctl* ctl, uint32_t* gsync, unsigned long long* const* peers, int rank, int world, int root,
-                                         unsigned long long step, const DeviceInfo& di, cudaStream_t st) {
+                                         unsigned long long step, int relay, const DeviceInfo& di, cudaStream_t st) {
   auto kern = k_count_dense_peer<THREADS>;
   const size_t smem = (size_t)dwords * 4;
   static size_t smem_set = 0;
@@ -1066,17 +1124,20 @@ static bool launch_count_dense_peer_inst(uint64_t nb, const unsigned long long* 
   const uint64_t ntiles = (np + tile - 1) / tile;
   if (grid > ntiles) grid = ntiles ? ntiles : 1;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
-  return launch_coop(kern, (unsigned)grid, THREADS, smem, st, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok, peers, rank, world, root, step);
+  return launch_coop(kern, (unsigned)grid, THREADS, smem, st, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok, peers, rank, world, root, step, relay);
 }
 size_t peer_staging_offset_bytes() { return (size_t)PEER_STAGING_WORD * 8; }
+size_t peer_staging_bytes() { return PEER_STAGING_BYTES; }
+size_t peer_buffer_bytes() { return (size_t)PEER_STAGING_WORD * 8 + PEER_STAGING_BYTES + PEER_PARTIAL_BYTES; }
 bool launch_count_dense_peer(uint64_t nb, const unsigned long long* pk, uint64_t np, uint32_t* bitmap, uint32_t dwords, Ctl* ctl,
                              uint32_t* gsync, unsigned long long* const* peers, int rank, int world, int root,
-                             unsigned long long step, const DeviceInfo& di, cudaStream_t st, int* launches) {
+                             unsigned long long step, bool relay, const DeviceInfo& di, cudaStream_t st, int* launches) {
   bool ok;
+  const int rl = relay && world > 1 && (size_t)dwords * 4 <= PEER_PARTIAL_BYTES ? 1 : 0;
   if ((size_t)dwords * 4 * 2 + 4096 <= di.smem_optin)
-    ok = launch_count_dense_peer_inst<512>(nb, pk, np, bitmap, dwords, ctl, gsync, peers, rank, world, root, step, di, st);
+    ok = launch_count_dense_peer_inst<512>(nb, pk, np, bitmap, dwords, ctl, gsync, peers, rank, world, root, step, rl, di, st);
   else
-    ok = launch_count_dense_peer_inst<1024>(nb, pk, np, bitmap, dwords, ctl, gsync, peers, rank, world, root, step, di, st);
+    ok = launch_count_dense_peer_inst<1024>(nb, pk, np, bitmap, dwords, ctl, gsync, peers, rank, world, root, step, rl, di, st);
   if (ok) ++*launches;
   return ok;
 }

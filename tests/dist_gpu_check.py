@@ -92,24 +92,31 @@ def main():
                                                    C.byref(g), C.byref(l), C.byref(sec), C.byref(st)))
         return g.value, l.value, st.as_dict()
 
-    N, ny = 2_000_000, 1_200_000
+    N, ny = 2_000_000, 500_000  # the membership bitmap of the peer-memory count kernel must fit shared memory
     fbk, fbv = g2_slice(N, ny, 90, 108, "build", 0, ny)
     fpk = g2_slice(N, ny, 90, 108, "probe", 0, N)
     p0, p1 = row_slice(N, world, rank)
-    for label, algo, bk, pk_local in (
-            ("symmetric retry (key outside the domain)", capi.ALGO_SCALAR, np.concatenate([fbk[:-1], np.array([10**12], np.uint64)]), fpk[p0:p1]),
-            ("asymmetric retry (one rank's probe slice skewed)", capi.ALGO_RADIX, fbk,
-             np.full(p1 - p0, fbk[5], np.uint64) if rank == world - 1 else fpk[p0:p1]),
-            ("no retry", capi.ALGO_ADAPTIVE, fbk, fpk[p0:p1])):
-        g, l, st = bcast_count(algo, bk, fbv, ny, pk_local)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (g, l, st["attempts"], pk_local))
-        if rank == 0:
-            n0 = O.np_join(bk, fbv, np.concatenate([x[3] for x in gathered]))[0]
-            case_ok = all(x[0] == n0 for x in gathered) and sum(x[1] for x in gathered) == n0
-            ok = ok and case_ok
-            report["cases"].append({"mode": "broadcast count, " + label, "matches": g, "expected": n0, "ok": bool(case_ok),
-                                    "attempts": [x[2] for x in gathered]})
+    # every case with the plain peer kernel (every rank pulls all keys from the root) and with the relay (key slices +
+    # partial bitmaps; forced here, by default only from 2^18 build rows): the verdict on a key outside the domain must
+    # reach every rank in both
+    for relay_min in (1 << 30, 1):
+        capi.config_set(peer_relay_min_rows=relay_min)
+        for label, algo, bk, pk_local in (
+                ("symmetric retry (key outside the domain)", capi.ALGO_SCALAR, np.concatenate([fbk[:-1], np.array([10**12], np.uint64)]), fpk[p0:p1]),
+                ("asymmetric retry (one rank's probe slice skewed)", capi.ALGO_RADIX, fbk,
+                 np.full(p1 - p0, fbk[5], np.uint64) if rank == world - 1 else fpk[p0:p1]),
+                ("no retry", capi.ALGO_ADAPTIVE, fbk, fpk[p0:p1]),
+                ("no retry, odd build size", capi.ALGO_SCALAR, fbk[:-3], fpk[p0:p1])):
+            g, l, st = bcast_count(algo, bk, fbv[:bk.size], bk.size, pk_local)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (g, l, st["attempts"], pk_local))
+            if rank == 0:
+                n0 = O.np_join(bk, fbv[:bk.size], np.concatenate([x[3] for x in gathered]))[0]
+                case_ok = all(x[0] == n0 for x in gathered) and sum(x[1] for x in gathered) == n0
+                ok = ok and case_ok
+                report["cases"].append({"mode": "broadcast count, " + label + (" [relay]" if relay_min == 1 else ""), "matches": g, "expected": n0,
+                                        "ok": bool(case_ok), "attempts": [x[2] for x in gathered]})
+    capi.config_set(peer_relay_min_rows=1 << 18)
     if rank == 0:
         report["ok"] = bool(ok)
         print(json.dumps(report))
