@@ -131,7 +131,7 @@ struct Engine {
   fj_status stager_setup(int want_threads, size_t chunk);
   void stager_release();
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
-  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush, sj_tails;
+  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush, sj_tails, bcast_rows;
   uint64_t pairs_n = 0;
   bool pairs_valid = false, pairs_idx = false;
   std::map<std::string, int64_t> cfg;
@@ -202,6 +202,7 @@ struct Engine {
     cfg["part_direct_k"] = 0;
     cfg["part_direct_count_build"] = 1;
     cfg["peer_relay_min_rows"] = 1 << 18;  // multi-GPU count over peer memory: build rows from which the key slices / partial bitmaps relay is used
+    cfg["dist_peer_bcast"] = 1;     // BROADCAST: build sides that fit the staging area travel over peer memory (k_peer_bcast), not ncclBroadcast
     cfg["dist_warmup"] = 1;         // fj_comm_init pays NCCL's first-use cost of broadcast and point-to-point channels
     cfg["dist_peer_shuffle"] = 1;   // SHUFFLE on a dense key domain: one partition pass storing straight into the owners' buffers
     cfg["dist_peer"] = 1;           // multi-GPU count over IPC-mapped peer memory (one kernel per GPU, no NCCL in the step)
@@ -326,7 +327,7 @@ void Engine::shutdown() {
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
                     &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &direct, &dist_scratch, &send_b, &send_p, &recv_b,
-                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv, &sj_tails})
+                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv, &sj_tails, &bcast_rows})
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
@@ -1903,16 +1904,46 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
     // broadcast the raw build rows (keys and values in one NCCL group; a count never reads the values, so only
     // the keys travel then)
     FJ_CUDA(cudaEventRecord(ev[4], st));
+    bool peer_bcast_used = false;
+    const unsigned long long* d_bkeys = in_bk.as<unsigned long long>();
+    const unsigned long long* d_bvals = mat ? in_bv.as<unsigned long long>() : in_bk.as<unsigned long long>();
     if (nb) {
-      if (mat) FJ_TRY(dist_broadcast2_u64(dist, src_bk, in_bk.p, src_bv, in_bv.p, nb, root, st));
-      else FJ_TRY(dist_broadcast_oop_u64(dist, src_bk, in_bk.p, nb, root, st));
+      // Build sides that fit the exchange buffer's staging area travel over peer memory in two hops (k_peer_bcast: the
+      // root sends every row once, the ranks gather the slices from each other) — decided from nb and the configuration,
+      // which every rank knows identically.  Keys and values land in ONE buffer (keys first).
+      const uint64_t nb2 = (nb + 1) & ~uint64_t(1);  // both halves 16-byte aligned
+      const uint64_t words = mat ? 2 * nb2 : nb2;
+      bool done = false;
+      if (peer.ready && cfg["dist_peer_bcast"] && words * 8 <= peer_staging_bytes()) {
+        FJ_TRY(bcast_rows.ensure(words * 8));
+        unsigned long long* stage = reinterpret_cast<unsigned long long*>(static_cast<char*>(peer.local) + peer_staging_offset_bytes());
+        if (is_root) {
+          FJ_CUDA(cudaMemcpyAsync(stage, src_bk, nb * 8, cudaMemcpyDeviceToDevice, st));
+          if (mat) FJ_CUDA(cudaMemcpyAsync(stage + nb2, src_bv, nb * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        int l0 = 0;
+        uint32_t* gsync = reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 256);
+        uint32_t* d_err = reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 384);  // zero since fj_init; read back with the result
+        const unsigned long long step = ++peer.step;
+        if (!launch_peer_bcast(peer.d_ptrs, dist.rank, dist.world, root, step, words, bcast_rows.as<unsigned long long>(), d_err, gsync, di, st,
+                               &l0))
+          return set_err(FJ_ERR_CUDA, "k_peer_bcast: no co-resident launch configuration");
+        s.kernel_launches += l0;
+        peer_bcast_used = true;
+        d_bkeys = bcast_rows.as<unsigned long long>();
+        d_bvals = mat ? d_bkeys + nb2 : d_bkeys;
+        done = true;
+      }
+      if (!done) {
+        if (mat) FJ_TRY(dist_broadcast2_u64(dist, src_bk, in_bk.p, src_bv, in_bv.p, nb, root, st));
+        else FJ_TRY(dist_broadcast_oop_u64(dist, src_bk, in_bk.p, nb, root, st));
+      }
     }
     FJ_CUDA(cudaEventRecord(ev[5], st));
-    const unsigned long long* d_bvals = mat ? in_bv.as<unsigned long long>() : in_bk.as<unsigned long long>();
     // count: the all-reduce of the control block rides behind the first attempt's kernels (one host sync per step)
     spec_ar = !mat && cfg["dist_spec_allreduce"] != 0;
     spec_done = false;
-    fj_status js = join_device(algo, jflags, in_bk.as<unsigned long long>(), d_bvals, nb, d_pk, np, 0, &s);
+    fj_status js = join_device(algo, jflags, d_bkeys, d_bvals, nb, d_pk, np, 0, &s);
     const bool spec = spec_ar;
     spec_ar = false;
     if (js != FJ_OK) return js;
@@ -1945,7 +1976,11 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
       FJ_CUDA(cudaMemcpyAsync(&total, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
     }
     FJ_CUDA(cudaEventRecord(ev[1], st));
+    uint32_t bcast_err = 0;
+    if (peer_bcast_used)
+      FJ_CUDA(cudaMemcpyAsync(&bcast_err, static_cast<char*>(ctl.p) + 384, 4, cudaMemcpyDeviceToHost, st));
     FJ_CUDA(cudaStreamSynchronize(st));
+    if (bcast_err) return set_err(FJ_ERR_NCCL, "peer-memory broadcast timed out (a rank did not join the step)");
     s.comm_s = (ms(4, 5) + ms(0, 1)) * 1e-3;
     s.device_s += s.comm_s;
     *out_global = total;

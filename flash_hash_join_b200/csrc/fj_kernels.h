@@ -104,6 +104,12 @@ bool launch_mat_dense_fused(const unsigned long long* bk, const unsigned long lo
                             uint64_t np, uint32_t* bitmap, uint32_t dwords, unsigned long long* direct, Ctl* ctl, uint32_t* gsync,
                             const ProbeOut& po, const DeviceInfo& di, cudaStream_t st, int* launches);
 
+// broadcast of `words` 64-bit words (a multiple of 2, at most peer_staging_bytes()) lying in the ROOT's staging area to
+// `out` on every rank, over peer memory in two hops (k_peer_bcast); gsync words 0 and 2 must be zero (left zero); *err is
+// set to 1 when a peer did not show up within 10 s
+bool launch_peer_bcast(unsigned long long* const* peers, int rank, int world, int root, unsigned long long step, uint64_t words,
+                       unsigned long long* out, uint32_t* err, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st, int* launches);
+
 // ---------------------------------------------------------------- radix-partitioned path
 // key / value domain of the packed (narrow) stage-1 scatter.  General packed rows: keys < 2^32 - 1, values < 2^32,
 // digit from hash32, a row outside raises CTL_NEED_WIDE.  Dense key domain: keys < the optimistic bound `klimit`,

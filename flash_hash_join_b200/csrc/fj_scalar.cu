@@ -858,6 +858,7 @@ constexpr int PEER_STAGING_WORD = 8192;  // 64 KB into the buffer
 // (nb * 8 bytes leave it instead of (world - 1) * nb * 8: at 1e6 keys and 8 GPUs the root's NVLink egress made the
 // count step 0.30 ms against 0.21 ms on one GPU, profiles/r02A_bench_n8.json); a bitmap is 2 bits per key.
 constexpr int PEER_PARTIAL_WORD = 4096;            // + rank: step | bad << 63 posted by `rank` when its partial bitmap is complete
+constexpr int PEER_BCAST_WORD = 4160;              // + rank: step posted by `rank` when its slice of the broadcast rows has arrived
 constexpr size_t PEER_STAGING_BYTES = size_t(16) << 20;
 constexpr size_t PEER_PARTIAL_BYTES = size_t(256) << 10;
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
@@ -1126,6 +1127,96 @@ static bool launch_count_dense_peer_inst(uint64_t nb, const unsigned long long* 
   const int vec_ok = ((reinterpret_cast<uintptr_t>(pk) & 15u) == 0) ? 1 : 0;
   return launch_coop(kern, (unsigned)grid, THREADS, smem, st, nb, pk, np, bitmap, dwords, ctl, gsync, vec_ok, peers, rank, world, root, step, relay);
 }
+// Broadcast of the root's build rows to every rank over peer memory (replaces ncclBroadcast for build sides that fit the
+// staging area; BASELINE.json configs[3]: 1e6 rows x 16 bytes to 8 GPUs took 0.2 ms with NCCL).  The root's rows lie in
+// its staging area (keys, then values: `words` 64-bit words).  Two hops, like an all-gather: every rank first pulls ITS
+// 1/world slice from the root into the same place of its own staging area, the ranks meet at a cross-GPU barrier, then
+// every rank pulls the other slices from the ranks that hold them into `out` — the root sends every word once, every
+// link carries words / world, and the pulls of the second hop come from world - 1 different sources at once.
+__global__ void __launch_bounds__(512) k_peer_bcast(unsigned long long* const* __restrict__ peers, int rank, int world, int root,
+                                                     unsigned long long step, uint64_t words /*multiple of 2*/,
+                                                     unsigned long long* __restrict__ out, uint32_t* __restrict__ err /*set on a timeout*/,
+                                                     uint32_t* __restrict__ gsync) {
+  __shared__ int s_flag;
+  const int tid = threadIdx.x;
+  const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + tid, gthreads = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long* const my_stage = peers[rank] + PEER_STAGING_WORD;
+  const unsigned long long* const root_stage = peers[root] + PEER_STAGING_WORD;
+  const uint64_t pairs = words / 2, per = (pairs + (uint64_t)world - 1) / (uint64_t)world;
+  auto copy_pairs = [&](const unsigned long long* src, unsigned long long* dst, uint64_t p0, uint64_t p1, bool remote) {
+    for (uint64_t i0 = p0 + gtid; i0 < p1; i0 += 4 * gthreads) {  // four 16-byte loads in flight per thread
+      unsigned long long a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t i = i0 + (uint64_t)u * gthreads;
+        if (i < p1) {
+          if (remote) asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a[u]), "=l"(b[u]) : "l"(src + 2 * i));
+          else { a[u] = src[2 * i]; b[u] = src[2 * i + 1]; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t i = i0 + (uint64_t)u * gthreads;
+        if (i < p1) { dst[2 * i] = a[u]; dst[2 * i + 1] = b[u]; }
+      }
+    }
+  };
+  // ---- hop 1: my slice, from the root (the root's copy into its staging area preceded this kernel in its stream)
+  if (rank == root) {
+    if (gtid == 0) st_release_sys_u64(peers[root] + PEER_READY_WORD, step);
+  } else {
+    if (tid == 0) s_flag = wait_sys_ge(root_stage - PEER_STAGING_WORD + PEER_READY_WORD, step) ? 1 : 0;
+    __syncthreads();
+    if (!s_flag) {
+      if (tid == 0) atomicOr(err, 1u);
+    } else {
+      const uint64_t p0 = (uint64_t)rank * per, p1 = p0 + per < pairs ? p0 + per : pairs;
+      if (p0 < p1) copy_pairs(root_stage, my_stage, p0, p1, true);
+    }
+  }
+  grid_barrier(gsync + 0);
+  // ---- my slice is in place: tell everybody, wait for everybody
+  if (gtid == 0) {
+    __threadfence_system();
+    for (int r = 0; r < world; ++r) st_release_sys_u64(peers[r] + PEER_BCAST_WORD + rank, step);
+  }
+  if (tid == 0) {
+    int ok = 1;
+    for (int r = 0; r < world && ok; ++r) ok = wait_sys_ge(peers[rank] + PEER_BCAST_WORD + r, step) ? 1 : 0;
+    if (!ok) atomicOr(err, 1u);
+    s_flag = ok;
+  }
+  __syncthreads();
+  // ---- hop 2: every slice from the rank that holds it (my own and, on the root, all of them: local copies)
+  if (s_flag) {
+    for (int q = 0; q < world; ++q) {
+      const int src_rank = (rank + q) % world;  // start with the local slice, then a different peer on every rank
+      const uint64_t p0 = (uint64_t)src_rank * per, p1 = p0 + per < pairs ? p0 + per : pairs;
+      if (p0 >= p1) continue;
+      const bool local = src_rank == rank || rank == root;
+      copy_pairs((local ? my_stage : peers[src_rank] + PEER_STAGING_WORD), out, p0, p1, !local);
+    }
+  }
+  // the barrier word cleans itself: the last CTA to get here resets both
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(gsync + 2, 1u) == gridDim.x - 1) {
+      gsync[0] = 0;
+      gsync[2] = 0;
+    }
+  }
+}
+bool launch_peer_bcast(unsigned long long* const* peers, int rank, int world, int root, unsigned long long step, uint64_t words,
+                       unsigned long long* out, uint32_t* err, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  if (words == 0 || (words & 1ull) || words * 8 > PEER_STAGING_BYTES) return false;
+  const uint64_t want = (words / 2 + 511) / 512;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)di.sms));  // one CTA per SM: co-resident
+  if (!launch_coop(k_peer_bcast, grid, 512u, 0, st, peers, rank, world, root, step, words, out, err, gsync)) return false;
+  ++*launches;
+  return true;
+}
+
 size_t peer_staging_offset_bytes() { return (size_t)PEER_STAGING_WORD * 8; }
 size_t peer_staging_bytes() { return PEER_STAGING_BYTES; }
 size_t peer_buffer_bytes() { return (size_t)PEER_STAGING_WORD * 8 + PEER_STAGING_BYTES + PEER_PARTIAL_BYTES; }
