@@ -202,6 +202,7 @@ struct Engine {
     cfg["part_direct_k"] = 0;
     cfg["part_direct_count_build"] = 1;
     cfg["peer_relay_min_rows"] = 1 << 18;  // multi-GPU count over peer memory: build rows from which the key slices / partial bitmaps relay is used
+    cfg["dist_peer_reduce"] = 1;    // BROADCAST: 8-byte reductions (failure agreement, global count) over peer memory instead of ncclAllReduce
     cfg["dist_peer_bcast"] = 1;     // BROADCAST: build sides that fit the staging area travel over peer memory (k_peer_bcast), not ncclBroadcast
     cfg["dist_warmup"] = 1;         // fj_comm_init pays NCCL's first-use cost of broadcast and point-to-point channels
     cfg["dist_peer_shuffle"] = 1;   // SHUFFLE on a dense key domain: one partition pass storing straight into the owners' buffers
@@ -1700,10 +1701,21 @@ fj_status Engine::agree(fj_status local) {
   if (dist_scratch.ensure(4096) != FJ_OK) return local != FJ_OK ? local : FJ_ERR_OOM;  // nothing collective has been started yet
   unsigned long long* d_w = dist_scratch.as<unsigned long long>() + 128;
   unsigned long long mine = local == FJ_OK ? 0ull : 1ull, sum = 0;
-  FJ_CUDA(cudaMemcpyAsync(d_w, &mine, 8, cudaMemcpyHostToDevice, st));
-  FJ_TRY(dist_allreduce_sum_u64(dist, d_w, d_w + 1, 1, st));
-  FJ_CUDA(cudaMemcpyAsync(&sum, d_w + 1, 8, cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
+  if (peer.ready && dist.world <= 32 && cfg["dist_peer_reduce"]) {  // one small kernel over peer memory instead of an NCCL call
+    int l0 = 0;
+    uint32_t perr = 0;
+    uint32_t* d_err = reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 384);
+    launch_peer_reduce(peer.d_ptrs, dist.rank, dist.world, ++peer.step, nullptr, mine, nullptr, d_w, d_err, st, &l0);
+    FJ_CUDA(cudaMemcpyAsync(&sum, d_w, 8, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaMemcpyAsync(&perr, d_err, 4, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    if (perr) return set_err(FJ_ERR_NCCL, "peer-memory reduction timed out (a rank did not join the call)");
+  } else {
+    FJ_CUDA(cudaMemcpyAsync(d_w, &mine, 8, cudaMemcpyHostToDevice, st));
+    FJ_TRY(dist_allreduce_sum_u64(dist, d_w, d_w + 1, 1, st));
+    FJ_CUDA(cudaMemcpyAsync(&sum, d_w + 1, 8, cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+  }
   if (local != FJ_OK) { g_err = err; return local; }
   if (sum) return set_err(FJ_ERR_STATE, "a peer rank failed before the collective (see its fj_last_error)");
   return FJ_OK;
@@ -1972,7 +1984,15 @@ fj_status Engine::join_dist(int mode, int algo, unsigned flags, int root, const 
         FJ_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
         cnt_src = d_cnt;
       }
-      FJ_TRY(dist_allreduce_sum_u64(dist, cnt_src, d_cnt + 1, 1, st));
+      if (peer.ready && dist.world <= 32 && cfg["dist_peer_reduce"]) {
+        int l0 = 0;
+        launch_peer_reduce(peer.d_ptrs, dist.rank, dist.world, ++peer.step, static_cast<const unsigned long long*>(cnt_src), 0, nullptr, d_cnt + 1,
+                           reinterpret_cast<uint32_t*>(static_cast<char*>(ctl.p) + 384), st, &l0);
+        s.kernel_launches += l0;
+        peer_bcast_used = true;  // (the error word is read back below)
+      } else {
+        FJ_TRY(dist_allreduce_sum_u64(dist, cnt_src, d_cnt + 1, 1, st));
+      }
       FJ_CUDA(cudaMemcpyAsync(&total, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
     }
     FJ_CUDA(cudaEventRecord(ev[1], st));

@@ -104,6 +104,11 @@ bool launch_mat_dense_fused(const unsigned long long* bk, const unsigned long lo
                             uint64_t np, uint32_t* bitmap, uint32_t dwords, unsigned long long* direct, Ctl* ctl, uint32_t* gsync,
                             const ProbeOut& po, const DeviceInfo& di, cudaStream_t st, int* launches);
 
+// sum / OR of two words over all ranks through peer memory (k_peer_reduce): result[0] = sum of *sum_src (or sum_imm when
+// sum_src is null), result[1] = OR of *or_src; world <= 32
+void launch_peer_reduce(unsigned long long* const* peers, int rank, int world, unsigned long long step, const unsigned long long* sum_src,
+                        unsigned long long sum_imm, const unsigned int* or_src, unsigned long long* result, uint32_t* err, cudaStream_t st,
+                        int* launches);
 // broadcast of `words` 64-bit words (a multiple of 2, at most peer_staging_bytes()) lying in the ROOT's staging area to
 // `out` on every rank, over peer memory in two hops (k_peer_bcast); gsync words 0 and 2 must be zero (left zero); *err is
 // set to 1 when a peer did not show up within 10 s

@@ -859,6 +859,7 @@ constexpr int PEER_STAGING_WORD = 8192;  // 64 KB into the buffer
 // count step 0.30 ms against 0.21 ms on one GPU, profiles/r02A_bench_n8.json); a bitmap is 2 bits per key.
 constexpr int PEER_PARTIAL_WORD = 4096;            // + rank: step | bad << 63 posted by `rank` when its partial bitmap is complete
 constexpr int PEER_BCAST_WORD = 4160;              // + rank: step posted by `rank` when its slice of the broadcast rows has arrived
+constexpr int PEER_RED_WORD = 4224;                // + 8 * rank: { step, -, sum[2], or[2] } of the small reductions (k_peer_reduce), by step parity
 constexpr size_t PEER_STAGING_BYTES = size_t(16) << 20;
 constexpr size_t PEER_PARTIAL_BYTES = size_t(256) << 10;
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
@@ -1207,6 +1208,52 @@ __global__ void __launch_bounds__(512) k_peer_bcast(unsigned long long* const* _
     }
   }
 }
+// Sum / OR of two words over all ranks through peer memory (replaces an 8-byte ncclAllReduce: the agreement on
+// rank-local failures and the global match count of the broadcast path).  One CTA; two entries per rank by step parity
+// (a rank can be at most one reduction ahead of another).  sum_src / or_src may be null (then sum_imm / 0 are used).
+__global__ void __launch_bounds__(32) k_peer_reduce(unsigned long long* const* __restrict__ peers, int rank, int world,
+                                                     unsigned long long step, const unsigned long long* __restrict__ sum_src,
+                                                     unsigned long long sum_imm, const unsigned int* __restrict__ or_src,
+                                                     unsigned long long* __restrict__ result /*[2]: sum, or*/, uint32_t* __restrict__ err) {
+  const int lane = threadIdx.x;
+  const int par = (int)(step & 1ull);
+  const unsigned long long mine = sum_src ? *sum_src : sum_imm;
+  const unsigned long long mor = or_src ? (unsigned long long)*or_src : 0ull;
+  if (lane < world) {
+    unsigned long long* slot = peers[lane] + PEER_RED_WORD + 8 * rank;
+    st_relaxed_sys_u64(slot + 2 + par, mine);
+    st_relaxed_sys_u64(slot + 4 + par, mor);
+    st_release_sys_u64(slot, step);
+  }
+  unsigned long long gs = 0, go = 0;
+  bool ok = true;
+  if (lane < world) {
+    const unsigned long long* slot = peers[rank] + PEER_RED_WORD + 8 * lane;
+    ok = wait_sys_ge(slot, step);
+    if (ok) {
+      gs = ld_relaxed_sys_u64(slot + 2 + par);
+      go = ld_relaxed_sys_u64(slot + 4 + par);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    gs += __shfl_xor_sync(0xffffffffu, gs, d);
+    go |= __shfl_xor_sync(0xffffffffu, go, d);
+  }
+  const bool all_ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    if (!all_ok) atomicOr(err, 1u);
+    result[0] = gs;
+    result[1] = go;
+  }
+}
+void launch_peer_reduce(unsigned long long* const* peers, int rank, int world, unsigned long long step, const unsigned long long* sum_src,
+                        unsigned long long sum_imm, const unsigned int* or_src, unsigned long long* result, uint32_t* err, cudaStream_t st,
+                        int* launches) {
+  k_peer_reduce<<<1, 32, 0, st>>>(peers, rank, world, step, sum_src, sum_imm, or_src, result, err);
+  ++*launches;
+}
+
 bool launch_peer_bcast(unsigned long long* const* peers, int rank, int world, int root, unsigned long long step, uint64_t words,
                        unsigned long long* out, uint32_t* err, uint32_t* gsync, const DeviceInfo& di, cudaStream_t st, int* launches) {
   if (words == 0 || (words & 1ull) || words * 8 > PEER_STAGING_BYTES) return false;
