@@ -39,3 +39,42 @@ def test_g2_slices_compose():
 def test_configs_match_baseline():
     assert CONFIGS["C2"] == (10**8, 10**5, 10)
     assert CONFIGS["C3"] == (10**8, 10**8, 90)
+
+
+def test_g2_build_rows_come_in_pseudo_random_order():
+    """The build row order is a cycle-walked bijective hash of the row index (like the shuffled RHS tables of
+    join-datagen.R): a bijection for every size, and no arithmetic progression of keys (which made a radix partition
+    pass conflict-free and the round-1 G2 numbers too good)."""
+    from flash_hash_join_b200.datagen import _shuffle_index
+
+    for n in (1, 2, 3, 7, 1000, 4096, 4097, 150_000):
+        x = _shuffle_index(np.arange(n, dtype=np.uint64), n, 108)
+        assert np.array_equal(np.sort(x), np.arange(n, dtype=np.uint64)), n
+    bk, bv, pk = g2(50_000, 40_000, 90)
+    d = np.diff(bk.astype(np.int64))
+    assert np.unique(d).size > 20_000  # an affine order has a handful of distinct steps
+    low = (bk[:4096] & np.uint64(31)).reshape(-1, 32)
+    assert np.mean([np.unique(r).size for r in low]) < 24  # 32 consecutive rows collide in the low key bits, like random keys (~20.4 distinct)
+    # the (key, value) SET is what the goldens pin: value is a function of the key id, not of the row
+    k2, v2 = g2_slice(50_000, 40_000, 90, 108, "build", 0, 40_000)
+    assert np.array_equal(k2, bk) and np.array_equal(v2, bv)
+
+
+def test_bench_expected_counts_cover_the_multi_gpu_workloads():
+    """bench.py checks `matches` at every GPU count against tests/golden: C3 / C2 / C4 slices from the compiled reference
+    (g1_goldens.json, gen == g2) and the C4 / C5 totals (g2_counts.json), where the reference's count on probe slices and the
+    generator-implied count agree."""
+    import json
+    from pathlib import Path
+
+    import bench
+
+    assert bench.expected_matches(100_000_000, 100_000_000, 90)[0] == 89_999_578
+    assert bench.expected_matches(100_000_000, 100_000, 10)[0] == 9_999_927
+    for g, want in ((1, 112_499_618), (2, 225_002_176), (4, 449_999_272), (8, 900_003_207)):
+        n, src = bench.expected_matches(g * 125_000_000, 1_000_000, 90)
+        assert n == want and "reference" in src, (g, n, src)
+    assert bench.expected_matches(1_000_000_000, 1_000_000_000, 90) == (899_998_249, "generator-implied count (tests/golden/g2_counts.json)")
+    assert bench.expected_matches(12345, 678, 90) == (None, None)
+    cases = json.loads((Path(bench.__file__).parent / "tests" / "golden" / "g2_counts.json").read_text())["cases"]
+    assert all(c["reference_count"] in (None, c["generator_count"]) for c in cases)
