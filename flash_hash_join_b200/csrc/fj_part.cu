@@ -296,10 +296,9 @@ __global__ void __launch_bounds__(512, 1) k_part(const PartParams a) {
       const uint32_t cnt = old[i] & 0xFFFFu;
       const uint32_t T = ((old[i] >> 16) + cnt) & 0xFFFFu;
       tk[i] = T;
-      if (v) {
-        if (cnt < SLOTS) reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + (T & (SLOTS - 1u))] = (ET)r.e[i];
-        else r.pend |= 1u << i;
-      }
+      const bool room = cnt < SLOTS;  // (one predicated store and a select: nested branches cost 11 instructions per row here)
+      if (v && room) reinterpret_cast<ET*>(buf)[r.d[i] * SLOTS + (T & (SLOTS - 1u))] = (ET)r.e[i];
+      r.pend |= (v && !room) ? (1u << i) : 0u;
       const bool closer = v && (T & (EPS - 1u)) == EPS - 1u;
       const unsigned m = __ballot_sync(0xffffffffu, closer);
       if (closer) wl[wn + __popc(m & lanemask_lt())] = r.d[i] | ((T >> LOG_EPS) << 11);
