@@ -478,10 +478,12 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   const uint32_t grid = part_grid(val, x.n, di);
 #define FJ_PART4(V, S, D)                                                                             \
   do {                                                                                                \
-    static size_t smem_set = 0; /* the attribute call costs microseconds: once per size */            \
-    if (smem_set != smem) {                                                                           \
+    static size_t smem_set = 0; /* the attribute call costs microseconds: once per size and device */ \
+    static int dev_set = -1;                                                                          \
+    if (smem_set != smem || dev_set != di.device) {                                                   \
       cudaFuncSetAttribute(k_part<V, S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       smem_set = smem;                                                                                \
+      dev_set = di.device;                                                                            \
     }                                                                                                 \
     k_part<V, S, D><<<grid, 512, smem, st>>>(a);                                                     \
   } while (0)
@@ -1106,14 +1108,14 @@ bool launch_sjoin(bool mat, const SjoinArgs& x, const DeviceInfo& di, cudaStream
   const uint32_t grid = sjoin_grid(x.p_count, di);
   if (mat) {
     if (!x.tails || 2u * grid > (uint32_t)PC_MAXH) return false;
-    static bool attr_mat = false;
-    if (!attr_mat) { cudaFuncSetAttribute(k_sjoin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_mat = true; }
+    static int attr_mat_dev = -1;
+    if (attr_mat_dev != di.device) { cudaFuncSetAttribute(k_sjoin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_mat_dev = di.device; }
     k_sjoin<true><<<grid, SJ_THREADS, smem, st>>>(a);
     k_pairs_compact<<<di.sms, PC_THREADS, 0, st>>>(x.ctl, x.tails, grid, x.out_keys, x.out_vals);
     ++*launches;
   } else {
-    static bool attr_cnt = false;
-    if (!attr_cnt) { cudaFuncSetAttribute(k_sjoin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_cnt = true; }
+    static int attr_cnt_dev = -1;
+    if (attr_cnt_dev != di.device) { cudaFuncSetAttribute(k_sjoin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_cnt_dev = di.device; }
     k_sjoin<false><<<grid, SJ_THREADS, smem, st>>>(a);
   }
   ++*launches;

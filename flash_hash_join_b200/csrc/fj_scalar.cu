@@ -807,9 +807,10 @@ static bool launch_count_dense_fused_inst(const unsigned long long* bk, uint64_t
                                           cudaStream_t st) {
   auto kern = k_count_dense_fused<THREADS>;
   const size_t smem = (size_t)dwords * 4;
-  static size_t smem_set = 0;   // per instantiation: attribute and occupancy are looked up once per size
-  static int occ_cached = 0;
-  if (smem != smem_set || occ_cached == 0) {
+  static size_t smem_set = 0;   // per instantiation: attribute and occupancy are looked up once per size and device
+  static int occ_cached = 0, dev_cached = -1;
+  if (smem != smem_set || occ_cached == 0 || dev_cached != di.device) {
+    dev_cached = di.device;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) return false;
@@ -1113,8 +1114,9 @@ static bool launch_count_dense_peer_inst(uint64_t nb, const unsigned long long* 
   auto kern = k_count_dense_peer<THREADS>;
   const size_t smem = (size_t)dwords * 4;
   static size_t smem_set = 0;
-  static int occ_cached = 0;
-  if (smem != smem_set || occ_cached == 0) {
+  static int occ_cached = 0, dev_cached = -1;
+  if (smem != smem_set || occ_cached == 0 || dev_cached != di.device) {
+    dev_cached = di.device;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) return false;
@@ -1466,8 +1468,9 @@ static bool launch_mat_dense_fused_inst(const unsigned long long* bk, const unsi
   auto kern = k_mat_dense_fused<IDX, THREADS>;
   const size_t smem = (size_t)dwords * 4;
   static size_t smem_set = 0;
-  static int occ_cached = 0;
-  if (smem != smem_set || occ_cached == 0) {
+  static int occ_cached = 0, dev_cached = -1;
+  if (smem != smem_set || occ_cached == 0 || dev_cached != di.device) {
+    dev_cached = di.device;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) return false;
