@@ -35,6 +35,7 @@ enum : unsigned {
   CTL_PEER_TIMEOUT = 16u,  // a peer GPU did not show up in the peer-memory exchange (k_count_dense_peer)
   CTL_NOT_DENSE16 = 32u,   // k_part: a build key outside the 16-bit-index dense domain, or a build value > 65534
   CTL_META_CHANGED = 64u,  // k_xsync: some rank joined the step with other slice sizes than the plan was made for
+  CTL_LOW_SEL = 128u,      // k_sel_sample: too few probe rows match for dense16 to beat the dense table path (with CTL_NOT_DENSE16)
 };
 
 // ---- hashing -----------------------------------------------------------------------------------

@@ -131,7 +131,7 @@ struct Engine {
   fj_status stager_setup(int want_threads, size_t chunk);
   void stager_release();
   DevBuf in_bk, in_bv, in_pk, table, bloom, ctl, out_keys, out_vals, out_idx;
-  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush, sj_tails, bcast_rows;
+  DevBuf part_a_b, part_a_p, part_b_b, part_b_p, cursors, flush, sj_tails, bcast_rows, sel_area;
   uint64_t pairs_n = 0;
   bool pairs_valid = false, pairs_idx = false;
   std::map<std::string, int64_t> cfg;
@@ -177,6 +177,10 @@ struct Engine {
     // vs 2.21 ms (radix), 1.6e7 rows 2.30 vs 2.30, 3e7 rows 3.86 vs 2.48 — the table wins until it is about twice L2
     cfg["adaptive_table_l2_pct"] = 200;
     cfg["dense16_min_rows"] = 8192;       // build rows from which the dense16 radix path (k_part + k_sjoin) is planned
+    cfg["dense16_sel_min_pct"] = 50;      // adaptive materialize, build side small enough for the dense table path: sampled match rate
+                                          // (percent, up to 2^17 build rows; x sqrt(2^17 / rows) beyond) below which that path is
+                                          // taken instead of dense16 (0 = never sample)
+    cfg["dense16_sel_max_rows"] = 1 << 19;  // build rows beyond which the match rate is not sampled (the table path hardly ever wins)
     cfg["dense16_min_probe"] = 1 << 24;   // adaptive materialize: probe rows from which dense16 is preferred to the dense table path
     cfg["radix_sub_rows"] = 0;  // 0 = derive from shared memory
     cfg["radix_optimistic"] = 1;
@@ -237,8 +241,10 @@ struct Engine {
   // dense key domain, radix path, round 2: ONE partition pass (k_part) + shared-memory direct-address join (k_sjoin)
   struct Dense16Plan { bool ok = false; int logp = 0; uint64_t klimit = 0; uint32_t slots = 0; uint64_t cap_b = 0, cap_p = 0; };
   Dense16Plan plan_dense16(unsigned flags, uint64_t nb, uint64_t np, bool small_ok = false) const;
+  // sel_min_pct != 0: k_sel_sample runs first and abandons the attempt (CTL_LOW_SEL) below that match rate
   fj_status attempt_dense16(unsigned flags, const Dense16Plan& dp, const unsigned long long* bk, const unsigned long long* bv,
-                            uint64_t nb, const unsigned long long* pk, uint64_t np, fj_stats* s);
+                            uint64_t nb, const unsigned long long* pk, uint64_t np, fj_stats* s, uint32_t sel_min_pct = 0,
+                            uint64_t sel_table_bits = 0);
   // dense key domain, count only: exact membership bitmap in shared memory instead of table + filter
   uint64_t dense_bitmap_bits(uint64_t nb) const;
   fj_status attempt_scalar_dense(unsigned flags, uint64_t dbits, const unsigned long long* bk, const unsigned long long* bv,
@@ -328,7 +334,7 @@ void Engine::shutdown() {
   cudaStreamSynchronize(st);
   for (DevBuf* b : {&in_bk, &in_bv, &in_pk, &table, &bloom, &ctl, &out_keys, &out_vals, &out_idx, &part_a_b,
                     &part_a_p, &part_b_b, &part_b_p, &cursors, &flush, &direct, &dist_scratch, &send_b, &send_p, &recv_b,
-                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv, &sj_tails, &bcast_rows})
+                    &recv_p, &shuf_cur, &shuf_meta, &exp_bk, &exp_bv, &exp_pk, &all_bk, &all_bv, &sj_tails, &bcast_rows, &sel_area})
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
@@ -963,7 +969,11 @@ Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t n
   const bool mat = flags & FJ_FLAG_MATERIALIZE;
   // every CTA of the pass leaves one (padded) sector per partition behind
   dp.cap_b = round16(cap_build(nb, P) + ((uint64_t)part_grid(mat, nb, di) + 2) * part_sector_elems(mat));
-  dp.cap_p = round16(cap_probe(np, P) + ((uint64_t)part_grid(false, np, di) + 2) * part_sector_elems(false));
+  // a partition holds nb / P distinct keys: with few of them the probe rows per partition follow the number of keys that
+  // fell into it, not the number of rows (1e4 build keys, 1024 partitions: 10 +- 2 keys, +-21 % rows) — room for 4.5 sigma
+  const double keys_per_part = std::max(1.0, (double)nb / (double)P);
+  const uint64_t few_keys = (uint64_t)((double)np / (double)P * std::min(2.0, 4.5 / std::sqrt(keys_per_part)));
+  dp.cap_p = round16(cap_probe(np, P) + few_keys + ((uint64_t)part_grid(false, np, di) + 2) * part_sector_elems(false));
   if (dp.cap_b > 0xfffffff0ull || dp.cap_p > 0xfffffff0ull) return dp;
   dp.ok = true;
   return dp;
@@ -971,7 +981,7 @@ Engine::Dense16Plan Engine::plan_dense16(unsigned flags, uint64_t nb, uint64_t n
 
 fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const unsigned long long* bk,
                                   const unsigned long long* bv, uint64_t nb, const unsigned long long* pk, uint64_t np,
-                                  fj_stats* s) {
+                                  fj_stats* s, uint32_t sel_min_pct, uint64_t sel_table_bits) {
   const bool mat = flags & FJ_FLAG_MATERIALIZE;
   const uint32_t P = 1u << dp.logp;
   const size_t eb = mat ? 4 : 2;
@@ -990,8 +1000,11 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   Ctl* d_ctl = ctl.as<Ctl>();
   int launches = 0;
   FJ_CUDA(cudaEventRecord(ev[0], st));
-  launch_prepare(d_ctl, nullptr, 0, cursors.p, 2 * (size_t)P * cs * 4, di, st, cs, P, part_cursor_start(mat, nb, di), part_cursor_start(false, np, di));
+  if (sel_min_pct) FJ_TRY(sel_area.ensure(sel_sample_bytes(dp.klimit)));
+  launch_prepare(d_ctl, sel_min_pct ? sel_area.p : nullptr, sel_min_pct ? sel_sample_bytes(dp.klimit) : 0, cursors.p, 2 * (size_t)P * cs * 4, di, st,
+                 cs, P, part_cursor_start(mat, nb, di), part_cursor_start(false, np, di));
   ++launches;
+  if (sel_min_pct) launch_sel_sample(d_ctl, bk, nb, pk, np, sel_area.p, dp.klimit, sel_table_bits, sel_min_pct, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[1], st));
   PartArgs a;
   a.ctl = d_ctl; a.klimit = dp.klimit; a.logp = dp.logp;
@@ -1100,11 +1113,22 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
     if (mat) prefer16 = np >= (uint64_t)cfg["dense16_min_probe"];
     else prefer16 = dense_bits == 0 && nb >= (1ull << 20);
   }
-  const bool radix_wanted =
+  bool radix_wanted =
       path == FJ_ALGO_RADIX || prefer16 ||
       (!plan.ok && !((flags & FJ_FLAG_PROBE_IDX) && mat) &&
        (algo == FJ_ALGO_RADIX || (algo == FJ_ALGO_ADAPTIVE && (double)nb / ((double)cfg["load_pct"] / 100.0) * 8.0 >
                                                                  (double)di.l2_bytes * (double)cfg["adaptive_table_l2_pct"] / 100.0)));
+  // with a build side small enough for the dense table path the match rate decides (k_sel_sample); explicit radix requests
+  // and build sides beyond the shared-memory bitmaps never sample.  Measured with 1e8 probe rows
+  // (profiles/r02O_exp_selectivity.jsonl): up to 1e5 build rows the table path wins below ~50 % matches (10 %: 0.35 vs 0.51 ms,
+  // 40 %: 0.46 vs 0.52), at 4e5 rows only below ~27 % (its L2-resident value table grows with the build side) — the
+  // threshold falls with the square root of the build size; the sample costs the dense16 path 13 us of 0.63 ms.
+  uint32_t sel_min_pct = 0;
+  if (prefer16 && mat && path == FJ_ALGO_SCALAR && dense_bits != 0 && nb <= (uint64_t)cfg["dense16_sel_max_rows"]) {
+    double t = (double)std::max<int64_t>(0, std::min<int64_t>(100, cfg["dense16_sel_min_pct"]));
+    if (nb > 131072) t *= std::sqrt(131072.0 / (double)nb);
+    sel_min_pct = (uint32_t)t;
+  }
   Dense16Plan d16;
   if (narrow && radix_wanted) {
     d16 = plan_dense16(flags, nb, np, prefer16);
@@ -1125,13 +1149,17 @@ fj_status Engine::join_device(int algo, unsigned flags, const unsigned long long
     }
     const bool dense_radix = !dense16 && radix_wanted && narrow && dplan.ok;
     const bool dense_scalar = path == FJ_ALGO_SCALAR && narrow && !exact && dense_bits != 0;
-    if (dense16) FJ_TRY(attempt_dense16(flags, d16, bk, bv, nb, pk, np, s));
+    if (dense16) FJ_TRY(attempt_dense16(flags, d16, bk, bv, nb, pk, np, s, sel_min_pct, dense_bits));
     else if (dense_radix) FJ_TRY(attempt_dense(flags, dplan, bk, bv, nb, pk, np, s));
     else if (dense_scalar) FJ_TRY(attempt_scalar_dense(flags, dense_bits, bk, bv, nb, pk, np, idx_base, s));
     else if (path == FJ_ALGO_RADIX) FJ_TRY(attempt_radix(flags, plan, bk, bv, nb, pk, np, s));
     else FJ_TRY(attempt_scalar(flags, narrow, exact, bk, bv, nb, pk, np, idx_base, s));
     const unsigned f = h_ctl->flags;
-    if (dense16 && (f & (CTL_NOT_DENSE16 | CTL_OVERFLOW))) { d16.ok = false; continue; }  // wider layouts answer
+    if (dense16 && (f & (CTL_NOT_DENSE16 | CTL_OVERFLOW))) {  // wider layouts answer
+      d16.ok = false;
+      if (f & CTL_LOW_SEL) radix_wanted = path == FJ_ALGO_RADIX;  // few probe rows match: the dense table path (dense_bits != 0)
+      continue;
+    }
     if (f & CTL_NOT_DENSE) { dplan.ok = false; dense_bits = 0; continue; }
     if ((f & CTL_OVERFLOW) && dense_radix) { dplan.ok = false; continue; }  // skewed low key bits: hash partitioning instead
     if ((f & CTL_NEED_WIDE) && narrow) { narrow = false; continue; }

@@ -230,6 +230,12 @@ uint32_t part_grid(bool val, uint64_t n, const DeviceInfo& di);
 // (0 when the pass is not launched at all, n == 0)
 uint32_t part_cursor_start(bool val, uint64_t n, const DeviceInfo& di);
 bool launch_part(bool val, const PartArgs& a, const DeviceInfo& di, cudaStream_t st, int* launches);
+// match-rate sample in front of a dense16 attempt (k_sel_sample): `area` holds sel_sample_bytes(bits) bytes prepared as
+// all-ones; fewer than min_pct % sampled probe keys in the build set raise CTL_NOT_DENSE16 | CTL_LOW_SEL, provided every
+// build key is below table_bits (the domain of the path taken instead)
+size_t sel_sample_bytes(uint64_t bits);
+void launch_sel_sample(Ctl* ctl, const unsigned long long* bk, uint64_t nb, const unsigned long long* pk, uint64_t np, void* area,
+                       uint64_t bits, uint64_t table_bits, uint32_t min_pct, const DeviceInfo& di, cudaStream_t st, int* launches);
 struct SjoinArgs {
   const void* build[8] = {};       // [nsub] every source's partition buffer (peer mapped for remote sources): partition p at
                                    // elements [p * cap_b, +bcnt); mat: 4-byte idx | value << 16; count: 2-byte idx

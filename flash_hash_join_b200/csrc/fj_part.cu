@@ -497,6 +497,71 @@ bool launch_part(bool val, const PartArgs& x, const DeviceInfo& di, cudaStream_t
   return true;
 }
 
+// ================================================================================= k_sel_sample
+// Match-rate sample ahead of a dense16 attempt.  With a small build side the dense table path (bitmap in shared memory,
+// values in an L2-resident table) only touches the probe rows that hit, while dense16 partitions every probe row: below
+// ~50 % match rate the table path wins, above it dense16 does (profiles/r02N_exp_selectivity.jsonl).  The rate is unknown
+// up front, so the adaptive materialize measures it: every CTA clears the membership bits of its slice of the build keys
+// in a global bitmap (all-ones = empty, prepared by k_prepare together with the two words behind it), and the last CTA to
+// arrive tests SS_SAMPLES probe keys spread evenly (with a hashed offset inside each stride) over the probe side, all of
+// a thread's loads in flight at once.  A rate below min_pct raises CTL_NOT_DENSE16 | CTL_LOW_SEL — unless a build key
+// lies outside the table path's own domain (table_bits), where that path could not answer: the k_part / k_sjoin launches
+// queued behind return at once and the host takes the table path.  A few microseconds in front of a 0.6 ms join.
+constexpr int SS_THREADS = 512;
+constexpr int SS_PER_THREAD = 16;
+constexpr uint32_t SS_SAMPLES = SS_THREADS * SS_PER_THREAD;
+__global__ void __launch_bounds__(SS_THREADS) k_sel_sample(Ctl* __restrict__ ctl, const unsigned long long* __restrict__ bk, uint64_t nb,
+                                                           const unsigned long long* __restrict__ pk, uint64_t np,
+                                                           uint32_t* __restrict__ bitmap, uint64_t bits, uint64_t table_bits,
+                                                           uint32_t* __restrict__ words, uint32_t min_pct) {
+  __shared__ uint32_t s_last, s_hits;
+  const uint64_t stride = (uint64_t)gridDim.x * SS_THREADS;
+  bool outside = false;
+  for (uint64_t i = blockIdx.x * (uint64_t)SS_THREADS + threadIdx.x; i < nb; i += stride) {
+    const unsigned long long k = bk[i];
+    if (k < bits) atomicAnd(&bitmap[k >> 5], ~(1u << (k & 31)));
+    outside |= k >= table_bits;
+  }
+  if (__syncthreads_or(outside) && threadIdx.x == 0) atomicAnd(&words[1], 0u);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = (atomicAdd(&words[0], 1u) + 1u) == gridDim.x - 1u;  // the arrival counter starts at 0xFFFFFFFF
+    s_hits = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const uint32_t ns = (uint32_t)(np < SS_SAMPLES ? np : SS_SAMPLES);
+  const uint64_t step = np / ns;
+  unsigned long long k[SS_PER_THREAD];
+#pragma unroll
+  for (int r = 0; r < SS_PER_THREAD; ++r) {
+    const uint32_t j = r * SS_THREADS + threadIdx.x;
+    k[r] = j < ns ? __ldg(&pk[j * step + (hash32(j) % step)]) : ~0ull;
+  }
+  uint32_t w[SS_PER_THREAD];
+#pragma unroll
+  for (int r = 0; r < SS_PER_THREAD; ++r) w[r] = k[r] < bits ? __ldcg(&bitmap[k[r] >> 5]) : 0xFFFFFFFFu;
+  uint32_t hits = 0;
+#pragma unroll
+  for (int r = 0; r < SS_PER_THREAD; ++r) hits += ((w[r] >> (k[r] & 31)) & 1u) ^ 1u;
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_hits, hits);
+  __syncthreads();
+  if (threadIdx.x == 0 && __ldcg(&words[1]) != 0u && (uint64_t)s_hits * 100u < (uint64_t)min_pct * ns)
+    atomicOr(&ctl->flags, CTL_NOT_DENSE16 | CTL_LOW_SEL);
+}
+size_t sel_sample_bytes(uint64_t bits) { return (size_t)((bits + 127) / 128 * 16 + 16); }
+void launch_sel_sample(Ctl* ctl, const unsigned long long* bk, uint64_t nb, const unsigned long long* pk, uint64_t np, void* area,
+                       uint64_t bits, uint64_t table_bits, uint32_t min_pct, const DeviceInfo& di, cudaStream_t st, int* launches) {
+  uint32_t* bitmap = static_cast<uint32_t*>(area);
+  uint32_t* words = bitmap + (bits + 127) / 128 * 4;  // arrival counter, "every build key inside the table domain"
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)di.sms, (nb + 4 * SS_THREADS - 1) / (4 * SS_THREADS)));
+  k_sel_sample<<<grid, SS_THREADS, 0, st>>>(ctl, bk, nb, pk, np, bitmap, bits, table_bits, words, min_pct);
+  if (launches) ++*launches;
+}
+
 // ================================================================================= k_xsync
 // Multi-GPU shuffle over peer memory (one process per GPU, every rank's exchange area mapped by every other rank through
 // CUDA IPC): the cross-GPU steps around k_part and k_sjoin, each ONE small launch on the rank's own stream.

@@ -312,6 +312,36 @@ def test_adaptive_prefers_dense16_for_big_probe_materialize(fj):
     assert np.array_equal(O.sorted_pairs(*fj.last_pairs()[:2]), O.sorted_pairs(expect2[1], expect2[2]))
 
 
+def test_adaptive_materialize_samples_the_match_rate(fj):
+    """Small dense build side, big probe side: k_sel_sample measures the match rate in front of the dense16 attempt; few
+    matches abandon it for the dense table path (one extra attempt), many keep it — the pairs are the oracle's either way,
+    and the threshold is a config key (0 = never sample)."""
+    N = (1 << 24) + 4_321
+    for pct, low in ((10, True), (90, False)):
+        bk, bv, pk = g1(N, 60_000, pct)
+        expect = O.np_join(bk, bv, pk)
+        n, _ = fj.adaptive_join(bk, bv, pk)
+        st = fj.last_stats()
+        assert n == expect[0], (pct, st)
+        if low:
+            assert st["path"] == "scalar" and st["dense"] == 1 and st["attempts"] == 2, st
+        else:
+            assert st["path"] == "radix" and st["dense"] == 2 and st["attempts"] == 1, st
+        assert np.array_equal(O.sorted_pairs(*fj.last_pairs()[:2]), O.sorted_pairs(expect[1], expect[2]))
+    fj.configure(dense16_sel_min_pct=0)
+    try:
+        n, _ = fj.adaptive_join(bk, bv, pk)  # the 90 % inputs
+        assert n == expect[0] and fj.last_stats()["dense"] == 2
+        bk, bv, pk = g1(N, 60_000, 10)
+        expect = O.np_join(bk, bv, pk)
+        n, _ = fj.adaptive_join(bk, bv, pk)
+        st = fj.last_stats()
+        assert n == expect[0] and st["path"] == "radix" and st["dense"] == 2 and st["attempts"] == 1, st
+        assert np.array_equal(O.sorted_pairs(*fj.last_pairs()[:2]), O.sorted_pairs(expect[1], expect[2]))
+    finally:
+        fj.configure(dense16_sel_min_pct=50)
+
+
 def test_adaptive_equals_explicit_on_both_sides_of_threshold(fj):
     for ny in (20_000, 3_000_000):
         bk, bv, pk = g1(3_000_000, ny, 90)

@@ -40,7 +40,7 @@ if has sanitize_general; then  # the general-path kernels und
   tail -n 4 "$OUT"/memcheck_*_general.log "$OUT"/racecheck_*_general.log
 fi
 if has tests16; then
-  timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 --timeout-method thread -k "dense16 or smoke" > "$OUT/pytest_dense16.log" 2>&1
+  timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 --timeout-method thread -k "dense16 or smoke or adaptive" > "$OUT/pytest_dense16.log" 2>&1
   echo "pytest exit $?" >> "$OUT/pytest_dense16.log"
   tail -15 "$OUT/pytest_dense16.log"
 fi
@@ -82,6 +82,10 @@ fi
 if has sweep_adaptive; then
   timeout 900 python tools/sweep_adaptive.py > "$OUT/sweep_adaptive.jsonl" 2> "$OUT/sweep_adaptive.err"
   cat "$OUT/sweep_adaptive.jsonl"; tail -3 "$OUT/sweep_adaptive.err"
+fi
+if has exp_selectivity; then
+  timeout 600 python tools/exp_selectivity.py > "$OUT/exp_selectivity.jsonl" 2> "$OUT/exp_selectivity.err"
+  cat "$OUT/exp_selectivity.jsonl"; tail -3 "$OUT/exp_selectivity.err"
 fi
 if has smoke; then
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
