@@ -106,6 +106,11 @@ struct Engine {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[16] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases, 12 build | probe partition pass, 13 end of the result exchange
   Ctl* h_ctl = nullptr;  // pinned
+  // mapped pinned: [Ctl][sequence word], written by k_publish_ctl; d_pub is the device-side address
+  unsigned long long* h_pub = nullptr;
+  void* d_pub = nullptr;
+  unsigned long long pub_seq = 0;
+  fj_status fetch_ctl(Ctl* d_ctl);
   // multi-GPU count: the ncclAllReduce of the control block is enqueued right behind the first attempt's kernels
   // (before the host has seen the flags), so a step has ONE host synchronisation instead of two.  The summed
   // flags word tells every rank whether any rank has to retry; only then a second all-reduce follows.
@@ -177,6 +182,7 @@ struct Engine {
     // vs 2.21 ms (radix), 1.6e7 rows 2.30 vs 2.30, 3e7 rows 3.86 vs 2.48 — the table wins until it is about twice L2
     cfg["adaptive_table_l2_pct"] = 200;
     cfg["dense16_min_rows"] = 8192;       // build rows from which the dense16 radix path (k_part + k_sjoin) is planned
+    cfg["mapped_result"] = 1;             // the attempt's control block returns through mapped pinned memory (k_publish_ctl) instead of a D2H copy
     cfg["dense16_sel_min_pct"] = 50;      // adaptive materialize, build side small enough for the dense table path: sampled match rate
                                           // (percent, up to 2^17 build rows; x sqrt(2^17 / rows) beyond) below which that path is
                                           // taken instead of dense16 (0 = never sample)
@@ -320,6 +326,10 @@ fj_status Engine::init(int device) {
   for (auto& x : ev) FJ_CUDA(cudaEventCreate(&x));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl)));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_spec), sizeof(Ctl)));
+  FJ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_pub), sizeof(Ctl) + 8, cudaHostAllocMapped));
+  FJ_CUDA(cudaHostGetDevicePointer(&d_pub, h_pub, 0));
+  memset(h_pub, 0, sizeof(Ctl) + 8);
+  pub_seq = 0;
   FJ_TRY(ctl.ensure(4096));  // [0, 256): Ctl; [256, 272): grid-barrier words of the fused kernels (zero between launches)
   FJ_CUDA(cudaMemset(ctl.p, 0, 4096));
   inited = true;
@@ -338,6 +348,9 @@ void Engine::shutdown() {
     b->release();
   if (h_ctl) cudaFreeHost(h_ctl);
   h_ctl = nullptr;
+  if (h_pub) cudaFreeHost(h_pub);
+  h_pub = nullptr;
+  d_pub = nullptr;
   if (h_spec) cudaFreeHost(h_spec);
   h_spec = nullptr;
   stager_release();
@@ -647,9 +660,7 @@ fj_status Engine::attempt_scalar(unsigned flags, bool narrow, bool exact, const 
   launch_probe(t, pk, np, bv, mat ? &po : nullptr, bloom_smem, (int)cfg["probe_ctas_per_sm"], d_ctl, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
-  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
-  FJ_CUDA(cudaGetLastError());
+  FJ_TRY(fetch_ctl(d_ctl));
   s->clear_s += ms(0, 1) * 1e-3;
   s->build_s += ms(1, 2) * 1e-3;
   s->probe_s += ms(2, 3) * 1e-3;
@@ -715,9 +726,7 @@ fj_status Engine::attempt_scalar_dense(unsigned flags, uint64_t dbits, const uns
   }
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
-  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
-  FJ_CUDA(cudaGetLastError());
+  FJ_TRY(fetch_ctl(d_ctl));
   if (fused) {
     s->probe_s += ms(0, 3) * 1e-3;  // one kernel: clear, build and probe are phases of it
   } else {
@@ -833,9 +842,7 @@ fj_status Engine::attempt_radix(unsigned flags, const RadixPlan& pl, const unsig
   if (!pl.narrow && !flat) launch_emit_sentinel(d_ctl, bv, j.out_keys, j.out_vals, mat, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
   FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
-  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
-  FJ_CUDA(cudaGetLastError());
+  FJ_TRY(fetch_ctl(d_ctl));
   s->clear_s += ms(0, 1) * 1e-3;
   s->partition_s += ms(1, 2) * 1e-3;
   s->probe_s += ms(2, 3) * 1e-3;
@@ -915,9 +922,7 @@ fj_status Engine::attempt_dense(unsigned flags, const DensePlan& dp, const unsig
   const bool launched = launch_djoin(mat, j, di, st, &launches);
   FJ_CUDA(cudaEventRecord(ev[3], st));
   if (launched) FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
-  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
-  FJ_CUDA(cudaGetLastError());
+  FJ_TRY(fetch_ctl(d_ctl));
   if (!launched) h_ctl->flags |= CTL_NOT_DENSE;  // the host falls back to the general radix path
   // fewer non-empty slots than rows stored: some key was stored twice (duplicate build keys)
   if (mat && !(h_ctl->flags & (CTL_NOT_DENSE | CTL_OVERFLOW)) && h_ctl->dense_slots != h_ctl->dense_rows) h_ctl->flags |= CTL_DUP;
@@ -1030,9 +1035,7 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   }
   FJ_CUDA(cudaEventRecord(ev[3], st));
   if (launched) FJ_TRY(spec_allreduce());  // multi-GPU count only (no-op otherwise)
-  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
-  FJ_CUDA(cudaGetLastError());
+  FJ_TRY(fetch_ctl(d_ctl));
   if (!launched) h_ctl->flags |= CTL_NOT_DENSE16;  // no launch configuration: the next layout answers
   if (mat && launched && !(h_ctl->flags & (CTL_NOT_DENSE16 | CTL_OVERFLOW))) {
     // out_cursor counts whole reserved blocks; k_pairs_compact has made [0, match_count) dense
@@ -1056,6 +1059,33 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
   s->dense = 2;
   s->part_build_us = (int32_t)(ms(1, 12) * 1e3f);
   s->part_probe_us = (int32_t)(ms(12, 2) * 1e3f);
+  return FJ_OK;
+}
+
+// The control block of the attempt just queued, into *h_ctl; returns once the stream has drained up to here.
+// (the one-thread publishing kernel is not counted in fj_stats.kernel_launches, which keeps meaning "kernels of the join")
+fj_status Engine::fetch_ctl(Ctl* d_ctl) {
+  if (!cfg["mapped_result"]) {
+    FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    FJ_CUDA(cudaStreamSynchronize(st));
+    FJ_CUDA(cudaGetLastError());
+    return FJ_OK;
+  }
+  const unsigned long long seq = ++pub_seq;
+  launch_publish_ctl(d_ctl, d_pub, seq, st);
+  volatile unsigned long long* word = h_pub + sizeof(Ctl) / 8;
+  // a faulted kernel never publishes: look at the stream now and then so that the error surfaces instead of a hang
+  for (unsigned spins = 1; *word != seq; ++spins) {
+    if ((spins & 4095u) == 0) {
+      const cudaError_t q = cudaStreamQuery(st);
+      if (q == cudaErrorNotReady) continue;
+      if (q != cudaSuccess) return set_err(FJ_ERR_CUDA, "%s", cudaGetErrorString(q));
+      if (*word != seq) return set_err(FJ_ERR_STATE, "internal: the stream drained without publishing the control block");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  memcpy(h_ctl, h_pub, sizeof(Ctl));
+  FJ_CUDA(cudaGetLastError());
   return FJ_OK;
 }
 
@@ -1831,9 +1861,7 @@ fj_status Engine::attempt_count_peer(uint64_t dbits, int root, const unsigned lo
                                dist.world, root, step, relay, di, st, &launches))
     return set_err(FJ_ERR_CUDA, "k_count_dense_peer: no co-resident launch configuration");
   FJ_CUDA(cudaEventRecord(ev[3], st));
-  FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  FJ_CUDA(cudaStreamSynchronize(st));
-  FJ_CUDA(cudaGetLastError());
+  FJ_TRY(fetch_ctl(d_ctl));
   if (h_ctl->flags & CTL_PEER_TIMEOUT) return set_err(FJ_ERR_NCCL, "peer-memory exchange timed out (a rank did not join the step)");
   s->probe_s += ms(0, 3) * 1e-3;
   s->device_s += ms(0, 3) * 1e-3;

@@ -58,6 +58,8 @@ struct ProbeOut {
 };
 
 void launch_init_ctl(Ctl* ctl, cudaStream_t st);
+// copies *ctl into mapped pinned memory (sizeof(Ctl) bytes) and then stores seq into the 64-bit word behind it
+void launch_publish_ctl(const Ctl* ctl, void* mapped_dst, unsigned long long seq, cudaStream_t st);
 // control block reset + `ones` filled with 0xFF (empty table) + `zeros` cleared, in one launch; sizes are
 // rounded up to 16 bytes (either region may be empty)
 // counter_stride != 0: the zeros region is an array of 32-bit counters, one every counter_stride words (a multiple of

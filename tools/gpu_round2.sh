@@ -96,4 +96,9 @@ if has ubench2; then
     && timeout 300 "$OUT/ubench2.bin" > "$OUT/ubench2.jsonl" 2> "$OUT/ubench2.err"
   cat "$OUT/ubench2.jsonl"
 fi
+if has ubench3; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/ubench3.cu -o "$OUT/ubench3.bin" > "$OUT/ubench3.build.log" 2>&1 \
+    && timeout 120 "$OUT/ubench3.bin" > "$OUT/ubench3.jsonl" 2> "$OUT/ubench3.err"
+  cat "$OUT/ubench3.jsonl"
+fi
 ls -la "$OUT"
