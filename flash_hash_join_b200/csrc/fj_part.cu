@@ -1066,13 +1066,39 @@ __global__ void __launch_bounds__(SJ_THREADS, 1) k_sjoin(const SjoinParams a) {
 // positions at or above M (sources; as many as destinations) — then fills its share of the holes.
 constexpr int PC_MAXH = 512;  // holes: two per k_sjoin CTA
 constexpr int PC_THREADS = 512;
-__device__ __forceinline__ void pc_scan(unsigned long long* x, unsigned long long* tmp, uint32_t n) {  // inclusive, in place; n <= PC_THREADS + 1
-  for (uint32_t d = 1; d < n; d <<= 1) {
-    for (uint32_t i = threadIdx.x; i < n; i += PC_THREADS) tmp[i] = x[i] + (i >= d ? x[i - d] : 0ull);
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += PC_THREADS) x[i] = tmp[i];
-    __syncthreads();
+static_assert(PC_MAXH + 1 <= 2 * PC_THREADS, "pc_scan2 handles two elements per thread");
+// inclusive prefix sums of a[0, n) and b[0, n) in place, n <= 2 * PC_THREADS: two elements per thread, warp shuffles, one
+// pass over the 16 warp totals (three block barriers instead of the four per doubling step of a ping-pong scan)
+__device__ __forceinline__ void pc_scan2(unsigned long long* a, unsigned long long* b, unsigned long long* wsum /* [2 * PC_THREADS / 32] */,
+                                         uint32_t n) {
+  constexpr int NW = PC_THREADS / 32;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t i0 = 2u * threadIdx.x, i1 = i0 + 1u;
+  const unsigned long long a0 = i0 < n ? a[i0] : 0ull, a1 = i1 < n ? a[i1] : 0ull;
+  const unsigned long long b0 = i0 < n ? b[i0] : 0ull, b1 = i1 < n ? b[i1] : 0ull;
+  unsigned long long sa = a0 + a1, sb = b0 + b1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long oa = __shfl_up_sync(0xffffffffu, sa, d), ob = __shfl_up_sync(0xffffffffu, sb, d);
+    if ((int)lane >= d) { sa += oa; sb += ob; }
   }
+  if (lane == 31u) { wsum[warp] = sa; wsum[NW + warp] = sb; }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long va = lane < (uint32_t)NW ? wsum[lane] : 0ull, vb = lane < (uint32_t)NW ? wsum[NW + lane] : 0ull;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+      const unsigned long long oa = __shfl_up_sync(0xffffffffu, va, d), ob = __shfl_up_sync(0xffffffffu, vb, d);
+      if ((int)lane >= d) { va += oa; vb += ob; }
+    }
+    if (lane < (uint32_t)NW) { wsum[lane] = va; wsum[NW + lane] = vb; }
+  }
+  __syncthreads();
+  const unsigned long long ea = (warp ? wsum[warp - 1] : 0ull) + sa - (a0 + a1);  // sum of everything in front of this thread's pair
+  const unsigned long long eb = (warp ? wsum[NW + warp - 1] : 0ull) + sb - (b0 + b1);
+  if (i0 < n) { a[i0] = ea + a0; b[i0] = eb + b0; }
+  if (i1 < n) { a[i1] = ea + a0 + a1; b[i1] = eb + b0 + b1; }
+  __syncthreads();
 }
 __global__ void __launch_bounds__(PC_THREADS) k_pairs_compact(const Ctl* ctl, const unsigned long long* tails, uint32_t ncta,
                                                                unsigned long long* out_keys, unsigned long long* out_vals) {
@@ -1080,7 +1106,9 @@ __global__ void __launch_bounds__(PC_THREADS) k_pairs_compact(const Ctl* ctl, co
   __shared__ unsigned long long hs[PC_MAXH], he[PC_MAXH];  // holes sorted by start, clipped to [0, R]
   __shared__ unsigned long long dsum[PC_MAXH + 1];         // inclusive prefix sums: hole positions below M
   __shared__ unsigned long long fs[PC_MAXH + 1], fsum[PC_MAXH + 1];  // filled segments at or above M: start, inclusive prefix sums of lengths
-  __shared__ unsigned long long tmp[PC_MAXH + 1];
+  __shared__ unsigned long long wsum[2 * PC_THREADS / 32];
+  // the attempt was abandoned (k_sjoin returned at once, or overflowed): nothing to compact
+  if (ctl->flags & (CTL_NOT_DENSE16 | CTL_OVERFLOW | CTL_META_CHANGED | CTL_PEER_TIMEOUT)) return;
   const unsigned long long R = ctl->out_cursor, M = ctl->match_count;
   const uint32_t nh = 2u * ncta;
   for (uint32_t i = threadIdx.x; i < nh; i += PC_THREADS) {
@@ -1113,8 +1141,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_pairs_compact(const Ctl* ctl, co
     dsum[k] = k < nh ? (e < M ? e : M) - (s < M ? s : M) : 0ull;
   }
   __syncthreads();
-  pc_scan(dsum, tmp, nh + 1);
-  pc_scan(fsum, tmp, nh + 1);
+  pc_scan2(dsum, fsum, wsum, nh + 1);
   // hole k receives the sources number [dsum[k - 1], dsum[k]) (numbered along the filled segments); every thread
   // has all its loads in flight before the first store
   for (uint32_t k = blockIdx.x; k < nh; k += gridDim.x) {
