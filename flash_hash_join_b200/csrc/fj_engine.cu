@@ -106,7 +106,7 @@ struct Engine {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[16] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases, 12 build | probe partition pass, 13 end of the result exchange
   Ctl* h_ctl = nullptr;  // pinned
-  // mapped pinned: [Ctl][sequence word], written by k_publish_ctl; d_pub is the device-side address
+  // mapped pinned: [Ctl + padding = PUB_WORDS words][sequence word], written by k_publish_ctl; d_pub is the device-side address
   unsigned long long* h_pub = nullptr;
   void* d_pub = nullptr;
   unsigned long long pub_seq = 0;
@@ -326,9 +326,9 @@ fj_status Engine::init(int device) {
   for (auto& x : ev) FJ_CUDA(cudaEventCreate(&x));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl)));
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_spec), sizeof(Ctl)));
-  FJ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_pub), sizeof(Ctl) + 8, cudaHostAllocMapped));
+  FJ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_pub), (PUB_WORDS + 2) * 8, cudaHostAllocMapped));
   FJ_CUDA(cudaHostGetDevicePointer(&d_pub, h_pub, 0));
-  memset(h_pub, 0, sizeof(Ctl) + 8);
+  memset(h_pub, 0, (PUB_WORDS + 2) * 8);
   pub_seq = 0;
   FJ_TRY(ctl.ensure(4096));  // [0, 256): Ctl; [256, 272): grid-barrier words of the fused kernels (zero between launches)
   FJ_CUDA(cudaMemset(ctl.p, 0, 4096));
@@ -1073,7 +1073,7 @@ fj_status Engine::fetch_ctl(Ctl* d_ctl) {
   }
   const unsigned long long seq = ++pub_seq;
   launch_publish_ctl(d_ctl, d_pub, seq, st);
-  volatile unsigned long long* word = h_pub + sizeof(Ctl) / 8;
+  volatile unsigned long long* word = h_pub + PUB_WORDS;
   // a faulted kernel never publishes: look at the stream now and then so that the error surfaces instead of a hang
   for (unsigned spins = 1; *word != seq; ++spins) {
     if ((spins & 4095u) == 0) {

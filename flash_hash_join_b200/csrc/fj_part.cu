@@ -517,10 +517,15 @@ __global__ void __launch_bounds__(SS_THREADS) k_sel_sample(Ctl* __restrict__ ctl
   __shared__ uint32_t s_last, s_hits;
   const uint64_t stride = (uint64_t)gridDim.x * SS_THREADS;
   bool outside = false;
-  for (uint64_t i = blockIdx.x * (uint64_t)SS_THREADS + threadIdx.x; i < nb; i += stride) {
-    const unsigned long long k = bk[i];
-    if (k < bits) atomicAnd(&bitmap[k >> 5], ~(1u << (k & 31)));
-    outside |= k >= table_bits;
+  for (uint64_t i = blockIdx.x * (uint64_t)SS_THREADS + threadIdx.x; i < nb; i += 4 * stride) {  // four loads in flight
+    unsigned long long k[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) k[r] = i + r * stride < nb ? bk[i + r * stride] : ~0ull;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (k[r] < bits) atomicAnd(&bitmap[k[r] >> 5], ~(1u << (k[r] & 31)));
+      outside |= (k[r] != ~0ull) & (k[r] >= table_bits);
+    }
   }
   if (__syncthreads_or(outside) && threadIdx.x == 0) atomicAnd(&words[1], 0u);
   __threadfence();
@@ -557,7 +562,7 @@ void launch_sel_sample(Ctl* ctl, const unsigned long long* bk, uint64_t nb, cons
                        uint64_t bits, uint64_t table_bits, uint32_t min_pct, const DeviceInfo& di, cudaStream_t st, int* launches) {
   uint32_t* bitmap = static_cast<uint32_t*>(area);
   uint32_t* words = bitmap + (bits + 127) / 128 * 4;  // arrival counter, "every build key inside the table domain"
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)di.sms, (nb + 4 * SS_THREADS - 1) / (4 * SS_THREADS)));
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(2ull * di.sms, (nb + SS_THREADS - 1) / SS_THREADS));
   k_sel_sample<<<grid, SS_THREADS, 0, st>>>(ctl, bk, nb, pk, np, bitmap, bits, table_bits, words, min_pct);
   if (launches) ++*launches;
 }

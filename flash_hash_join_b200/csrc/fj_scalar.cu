@@ -40,11 +40,16 @@ void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ct
 // call's sequence number behind it; the host spins on that word.  6 us less per call than cudaMemcpyAsync +
 // cudaStreamSynchronize (profiles/r02S_ubench3.jsonl: 13.9 vs 20.4 us turn-around) — it shows on the small joins (C1).
 __global__ void k_publish_ctl(const Ctl* __restrict__ ctl, volatile unsigned long long* dst, unsigned long long seq) {
-  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(ctl);
+  static_assert(sizeof(Ctl) <= PUB_WORDS * 8 && PUB_WORDS % 2 == 0, "the control block travels as 16-byte stores");
+  const uint4* src = reinterpret_cast<const uint4*>(ctl);  // the arena keeps 256 bytes for the block: reading its padding is fine
+  uint4* out = reinterpret_cast<uint4*>(const_cast<unsigned long long*>(dst));
+  uint4 v[PUB_WORDS / 2];
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(Ctl) / 8); ++i) dst[i] = src[i];
+  for (int i = 0; i < PUB_WORDS / 2; ++i) v[i] = src[i];
+#pragma unroll
+  for (int i = 0; i < PUB_WORDS / 2; ++i) out[i] = v[i];
   __threadfence_system();
-  dst[sizeof(Ctl) / 8] = seq;
+  dst[PUB_WORDS] = seq;
 }
 void launch_publish_ctl(const Ctl* ctl, void* mapped_dst, unsigned long long seq, cudaStream_t st) {
   k_publish_ctl<<<1, 1, 0, st>>>(ctl, static_cast<volatile unsigned long long*>(mapped_dst), seq);
