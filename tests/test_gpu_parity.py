@@ -342,7 +342,30 @@ def test_adaptive_materialize_samples_the_match_rate(fj):
         fj.configure(dense16_sel_min_pct=50)
 
 
-def test_adaptive_equals_explicit_on_both_sides_of_threshold(fj):
+def test_result_word_mapped_and_copied_agree(fj):
+    """The attempt's control block comes back through mapped pinned memory (k_publish_ctl + host spin) by default and through
+    cudaMemcpyAsync + cudaStreamSynchronize with mapped_result = 0: same counts, same pairs, on a path with one attempt and
+    on one that abandons its first attempt."""
+    bk, bv, pk = g1(400_000, 40_000, 90)
+    bk2 = bk.copy()
+    bk2[11] = np.uint64(2**40)  # forces a second attempt (wide rows)
+    for keys in (bk, bk2):
+        expect = O.np_join(keys, bv, pk)
+        got = {}
+        for mapped in (1, 0):
+            fj.configure(mapped_result=mapped)
+            try:
+                for name in ("hash_join_count", "hash_join_radix", "adaptive_join"):
+                    n, _ = getattr(fj, name)(keys, bv, pk)
+                    assert n == expect[0], (name, mapped, fj.last_stats())
+                    if name != "hash_join_count":
+                        assert np.array_equal(O.sorted_pairs(*fj.last_pairs()[:2]), O.sorted_pairs(expect[1], expect[2])), (name, mapped)
+                    got[(name, mapped)] = fj.last_stats()["attempts"]
+            finally:
+                fj.configure(mapped_result=1)
+        assert all(got[(nm, 1)] == got[(nm, 0)] for nm in ("hash_join_count", "hash_join_radix", "adaptive_join")), got
+
+
     for ny in (20_000, 3_000_000):
         bk, bv, pk = g1(3_000_000, ny, 90)
         n_a, _ = fj.adaptive_join_count(bk, bv, pk)
