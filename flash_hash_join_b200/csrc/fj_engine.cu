@@ -106,7 +106,7 @@ struct Engine {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[16] = {};  // 0-3 attempt phases, 4-5 distributed call, 6-7 fj_timer_*, 8-11 shuffle phases, 12 build | probe partition pass, 13 end of the result exchange
   Ctl* h_ctl = nullptr;  // pinned
-  // mapped pinned: [Ctl + padding = PUB_WORDS words][sequence word], written by k_publish_ctl; d_pub is the device-side address
+  // mapped pinned: PUB_WORDS words of tag << 32 | control-block word, written by k_publish_ctl; d_pub is the device-side address
   unsigned long long* h_pub = nullptr;
   void* d_pub = nullptr;
   unsigned long long pub_seq = 0;
@@ -328,7 +328,7 @@ fj_status Engine::init(int device) {
   FJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_spec), sizeof(Ctl)));
   FJ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_pub), (PUB_WORDS + 2) * 8, cudaHostAllocMapped));
   FJ_CUDA(cudaHostGetDevicePointer(&d_pub, h_pub, 0));
-  memset(h_pub, 0, (PUB_WORDS + 2) * 8);
+  memset(h_pub, 0, (PUB_WORDS + 2) * 8);  // tag 0 is never used
   pub_seq = 0;
   FJ_TRY(ctl.ensure(4096));  // [0, 256): Ctl; [256, 272): grid-barrier words of the fused kernels (zero between launches)
   FJ_CUDA(cudaMemset(ctl.p, 0, 4096));
@@ -1063,7 +1063,7 @@ fj_status Engine::attempt_dense16(unsigned flags, const Dense16Plan& dp, const u
 }
 
 // The control block of the attempt just queued, into *h_ctl; returns once the stream has drained up to here.
-// (the one-thread publishing kernel is not counted in fj_stats.kernel_launches, which keeps meaning "kernels of the join")
+// (the publishing kernel is not counted in fj_stats.kernel_launches, which keeps meaning "kernels of the join")
 fj_status Engine::fetch_ctl(Ctl* d_ctl) {
   if (!cfg["mapped_result"]) {
     FJ_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
@@ -1071,20 +1071,31 @@ fj_status Engine::fetch_ctl(Ctl* d_ctl) {
     FJ_CUDA(cudaGetLastError());
     return FJ_OK;
   }
-  const unsigned long long seq = ++pub_seq;
-  launch_publish_ctl(d_ctl, d_pub, seq, st);
-  volatile unsigned long long* word = h_pub + PUB_WORDS;
+  if ((uint32_t)++pub_seq == 0) ++pub_seq;
+  const uint32_t tag = (uint32_t)pub_seq;
+  launch_publish_ctl(d_ctl, d_pub, tag, st);
+  volatile unsigned long long* words = h_pub;
+  uint32_t data[PUB_WORDS];
   // a faulted kernel never publishes: look at the stream now and then so that the error surfaces instead of a hang
-  for (unsigned spins = 1; *word != seq; ++spins) {
+  for (unsigned spins = 1;; ++spins) {
+    bool all = true;
+    for (int i = 0; i < PUB_WORDS; ++i) {
+      const unsigned long long w = words[i];
+      data[i] = (uint32_t)w;
+      all &= (uint32_t)(w >> 32) == tag;
+    }
+    if (all) break;
     if ((spins & 4095u) == 0) {
       const cudaError_t q = cudaStreamQuery(st);
       if (q == cudaErrorNotReady) continue;
       if (q != cudaSuccess) return set_err(FJ_ERR_CUDA, "%s", cudaGetErrorString(q));
-      if (*word != seq) return set_err(FJ_ERR_STATE, "internal: the stream drained without publishing the control block");
+      bool late = true;  // the stream has drained: the words are there unless the launch itself was lost
+      for (int i = 0; i < PUB_WORDS; ++i) late &= (uint32_t)(words[i] >> 32) == tag;
+      if (!late) return set_err(FJ_ERR_STATE, "internal: the stream drained without publishing the control block");
     }
   }
-  std::atomic_thread_fence(std::memory_order_acquire);
-  memcpy(h_ctl, h_pub, sizeof(Ctl));
+  static_assert(sizeof(Ctl) == sizeof(data), "control block words");
+  memcpy(h_ctl, data, sizeof(Ctl));
   FJ_CUDA(cudaGetLastError());
   return FJ_OK;
 }

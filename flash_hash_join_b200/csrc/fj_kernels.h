@@ -58,10 +58,9 @@ struct ProbeOut {
 };
 
 void launch_init_ctl(Ctl* ctl, cudaStream_t st);
-// copies *ctl into mapped pinned memory (PUB_WORDS 64-bit words, the block and its padding) and then stores seq into the
-// word behind them: the destination holds PUB_WORDS + 1 words
-constexpr int PUB_WORDS = 10;
-void launch_publish_ctl(const Ctl* ctl, void* mapped_dst, unsigned long long seq, cudaStream_t st);
+// publishes *ctl into mapped pinned memory: PUB_WORDS 64-bit words, word t = tag << 32 | t-th 32-bit word of the block
+constexpr int PUB_WORDS = 18;
+void launch_publish_ctl(const Ctl* ctl, void* mapped_dst, unsigned int tag, cudaStream_t st);
 // control block reset + `ones` filled with 0xFF (empty table) + `zeros` cleared, in one launch; sizes are
 // rounded up to 16 bytes (either region may be empty)
 // counter_stride != 0: the zeros region is an array of 32-bit counters, one every counter_stride words (a multiple of

@@ -36,23 +36,19 @@ __global__ void k_init_ctl(Ctl* ctl) {
 }
 void launch_init_ctl(Ctl* ctl, cudaStream_t st) { k_init_ctl<<<1, 1, 0, st>>>(ctl); }
 
-// The attempt's verdict goes back through MAPPED pinned memory: one thread copies the control block and then stores the
-// call's sequence number behind it; the host spins on that word.  6 us less per call than cudaMemcpyAsync +
-// cudaStreamSynchronize (profiles/r02S_ubench3.jsonl: 13.9 vs 20.4 us turn-around) — it shows on the small joins (C1).
-__global__ void k_publish_ctl(const Ctl* __restrict__ ctl, volatile unsigned long long* dst, unsigned long long seq) {
-  static_assert(sizeof(Ctl) <= PUB_WORDS * 8 && PUB_WORDS % 2 == 0, "the control block travels as 16-byte stores");
-  const uint4* src = reinterpret_cast<const uint4*>(ctl);  // the arena keeps 256 bytes for the block: reading its padding is fine
-  uint4* out = reinterpret_cast<uint4*>(const_cast<unsigned long long*>(dst));
-  uint4 v[PUB_WORDS / 2];
-#pragma unroll
-  for (int i = 0; i < PUB_WORDS / 2; ++i) v[i] = src[i];
-#pragma unroll
-  for (int i = 0; i < PUB_WORDS / 2; ++i) out[i] = v[i];
-  __threadfence_system();
-  dst[PUB_WORDS] = seq;
+// The attempt's verdict goes back through MAPPED pinned memory: thread t stores the t-th 32-bit word of the control block
+// together with the call's 32-bit sequence tag as ONE 64-bit store (single-copy atomic, so the host can never see a torn
+// word), and the host spins until every word carries the tag.  No system-scope fence is needed — it alone cost ~5 us in
+// a one-thread version that stored the block, fenced and then stored a sequence word (profiles/r02fin ncu: membar 100 %).
+// Against cudaMemcpyAsync + cudaStreamSynchronize the turn-around of a short call drops from 20 to 14 us
+// (profiles/r02S_ubench3.jsonl) — it shows on the small joins (C1).
+__global__ void k_publish_ctl(const Ctl* __restrict__ ctl, volatile unsigned long long* dst, unsigned int tag) {
+  static_assert(sizeof(Ctl) == PUB_WORDS * 4, "one 64-bit store per 32-bit word of the control block");
+  const unsigned int t = threadIdx.x;
+  if (t < (unsigned int)PUB_WORDS) dst[t] = ((unsigned long long)tag << 32) | reinterpret_cast<const unsigned int*>(ctl)[t];
 }
-void launch_publish_ctl(const Ctl* ctl, void* mapped_dst, unsigned long long seq, cudaStream_t st) {
-  k_publish_ctl<<<1, 1, 0, st>>>(ctl, static_cast<volatile unsigned long long*>(mapped_dst), seq);
+void launch_publish_ctl(const Ctl* ctl, void* mapped_dst, unsigned int tag, cudaStream_t st) {
+  k_publish_ctl<<<1, 32, 0, st>>>(ctl, static_cast<volatile unsigned long long*>(mapped_dst), tag);
 }
 
 // One launch instead of {k_init_ctl, cudaMemsetAsync(table), cudaMemsetAsync(bloom | cursors)}: the control

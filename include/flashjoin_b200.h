@@ -84,8 +84,8 @@ typedef struct fj_stats {
                        /* 4 per-partition filter in shared memory (radix + Bloom, k_join)          */
   int32_t attempts;    /* 1 normally; >1 when an optimistic attempt was abandoned and re-run       */
   int32_t dedup_exact; /* 1 = duplicate build keys were seen and the keep-first slow path ran      */
-  int32_t kernel_launches; /* number of this library's join kernels launched by the call (the one- */
-                           /* thread kernel that hands the verdict to the host is not counted)     */
+  int32_t kernel_launches; /* number of this library's join kernels launched by the call (the      */
+                           /* small kernel that hands the verdict to the host is not counted)      */
   int32_t radix_bits1, radix_bits2; /* fan-out of the radix passes (0 = pass not run)              */
   int32_t n_gpus;
   int32_t dense;       /* 1 = a dense-key-domain fast path produced the result (bitmap count or     */
