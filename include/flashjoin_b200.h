@@ -145,6 +145,14 @@ FJ_API fj_status fj_pairs_device(const uint64_t** keys, const uint64_t** values,
  *       fj_comm_init and per call), "dist_spec_allreduce" (0/1: NCCL count all-reduce enqueued behind the first attempt).
  *       "stage_threads" / "stage_min_mb" (host threads that stage pageable input columns of at least that many MB through
  *       pinned buffers; 0 threads = plain cudaMemcpyAsync).
+ *       Round 2: "dense16" (0/1: the one-pass dense-key-domain radix join k_part + k_sjoin), "dense16_logp" (partitions,
+ *       0 = derive), "dense16_min_rows" / "dense16_min_probe" (adaptive materialize: smallest build / probe side that prefers
+ *       dense16), "dense16_sel_min_pct" / "dense16_sel_max_rows" (adaptive materialize with a small build side: sampled match
+ *       rate below which the dense table path is taken, and the largest build side that is sampled), "bloom_guard" (0/1: skip a
+ *       filter that spills out of shared memory next to an L2-resident table), "mapped_result" (0/1: the attempt's control
+ *       block returns through mapped pinned memory instead of a device->host copy), "dist_peer_shuffle" / "dist_peer_bcast" /
+ *       "dist_peer_reduce" (0/1: SHUFFLE / build broadcast / 8-byte reductions over IPC-mapped peer memory instead of NCCL),
+ *       "peer_relay_min_rows" (build rows from which k_count_dense_peer relays key slices and partial bitmaps).
  *       Every key can also be preset from the environment as FJ_CFG_<KEY>=<integer>. */
 FJ_API fj_status fj_config_set(const char* key, int64_t value);
 FJ_API fj_status fj_config_get(const char* key, int64_t* value);
